@@ -1,0 +1,384 @@
+// C ABI of libp3d.so (see include/p3d.h): model lifetime, variables by TF name, forward dispatch,
+// the host-buffer evaluation step, misc.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace p3d {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long>* launch_counter() {
+  static std::atomic<long long> c{0};
+  return &c;
+}
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { launch_counter()->fetch_add(n); }
+
+namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const float*, __nv_bfloat16*, int64_t, cudaStream_t); }
+namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t);
+               int debug_umma_gemm(const void*, const void*, float*, int, int, cudaStream_t); }
+namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
+                 int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t); }
+namespace train { void free_workspace(p3d_model*); }
+
+constexpr int kSmallBatchMax = 16;   // rows served by the latency (GEMV) path
+
+__global__ void fill_kernel(float* p, size_t n, float v) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) p[i] = v;
+}
+
+// sum((y-t)^2) into a double accumulator
+__global__ void sqerr_kernel(const float* __restrict__ y, const float* __restrict__ t, size_t n, double* __restrict__ acc) {
+  double s = 0.0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float d = y[i] - t[i];
+    s += static_cast<double>(d) * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+    atomicAdd(acc, tot);
+  }
+}
+__global__ void finish_mse_kernel(const double* acc, double denom, float* loss) { *loss = static_cast<float>(*acc / denom); }
+
+static int fill(float* p, size_t n, float v) {
+  if (n == 0) return P3D_OK;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  fill_kernel<<<blocks, 256>>>(p, n, v);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st) {
+  int blocks = static_cast<int>((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sqerr_kernel<<<blocks, 256, 0, st>>>(y, t, n, acc);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+static NamedParam* find_param(p3d_model* m, const char* name) {
+  for (auto& p : m->params)
+    if (p.name == name) return &p;
+  return nullptr;
+}
+
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" {
+
+const char* p3d_last_error(void) { return g_err; }
+int p3d_version(void) { return 100; }
+int64_t p3d_launch_count(void) { return launch_counter()->load(); }
+
+int p3d_host_alloc(void** out, size_t bytes) {
+  P3D_REQUIRE(out, "host_alloc: null out");
+  P3D_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return P3D_OK;
+}
+int p3d_host_free(void* p) {
+  P3D_CUDA(cudaFreeHost(p));
+  return P3D_OK;
+}
+
+int p3d_model_create(const p3d_cfg* cfg, p3d_model** out) {
+  P3D_REQUIRE(cfg && out, "model_create: null argument");
+  P3D_REQUIRE(cfg->linear_size >= 16 && cfg->linear_size % 4 == 0, "linear_size must be a positive multiple of 4");
+  P3D_REQUIRE(cfg->num_layers >= 0 && cfg->num_layers <= 64, "num_layers out of range");
+  P3D_REQUIRE(cfg->mode == P3D_MODE_BF16 || cfg->mode == P3D_MODE_FP32, "unknown mode %d", cfg->mode);
+  int ndev = 0;
+  P3D_CUDA(cudaGetDeviceCount(&ndev));
+  P3D_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d devices)", cfg->device, ndev);
+  P3D_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  P3D_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("libp3d is built for sm_100a only; device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+    return P3D_ERR_CUDA;
+  }
+  p3d_model* m = new p3d_model();
+  m->cfg = *cfg;
+  m->L = cfg->linear_size;
+  m->out_size = cfg->predict_14 ? 42 : 48;
+  m->num_sms = prop.multiProcessorCount;
+  const int L = m->L;
+  const int nlay = 2 * cfg->num_layers + 2;
+  m->layers.resize(nlay);
+  // layer table + TF names (src/linear_model.py:106-107,121-122,176-193)
+  for (int l = 0; l < nlay; ++l) {
+    Layer& ly = m->layers[l];
+    ly.K = (l == 0) ? kIn : L;
+    ly.N = (l == nlay - 1) ? m->out_size : L;
+    ly.hidden = (l != nlay - 1);
+    ly.has_bn = ly.hidden && cfg->batch_norm;
+    char buf[128];
+    if (l == 0) { ly.wname = "linear_model/w1"; ly.bname = "linear_model/b1"; ly.bnscope = "linear_model/batch_normalization"; }
+    else if (l == nlay - 1) { ly.wname = "linear_model/w4"; ly.bname = "linear_model/b4"; }
+    else {
+      const int blk = (l - 1) / 2, which = (l - 1) % 2;   // 0 -> w2/b2/bn1, 1 -> w3/b3/bn2
+      snprintf(buf, sizeof(buf), "linear_model/two_linear_%d/w%d_%d", blk, which + 2, blk); ly.wname = buf;
+      snprintf(buf, sizeof(buf), "linear_model/two_linear_%d/b%d_%d", blk, which + 2, blk); ly.bname = buf;
+      snprintf(buf, sizeof(buf), "linear_model/two_linear_%d/batch_normalization%d%d", blk, which + 1, blk); ly.bnscope = buf;
+    }
+  }
+  // flat layout: [all W][b, gamma, beta per layer]
+  size_t off = 0, wf = 0;
+  int row = 0;
+  for (auto& ly : m->layers) {
+    ly.off_w = off; off += static_cast<size_t>(ly.K) * ly.N;
+    ly.off_wfold = wf; wf += static_cast<size_t>(ly.K) * ly.N;
+    ly.row_off = row; row += ly.N;
+  }
+  const size_t n_w = off;
+  size_t mo = 0;
+  for (auto& ly : m->layers) {
+    ly.off_b = off; off += ly.N;
+    if (ly.has_bn) {
+      ly.off_gamma = off; off += ly.N;
+      ly.off_beta = off; off += ly.N;
+      ly.off_mm = mo; mo += ly.N;
+      ly.off_mv = mo; mo += ly.N;
+    }
+  }
+  (void)n_w;
+  m->n_train = off;
+  m->n_moving = mo;
+  m->rows_total = row + 16;   // slack so the padded output rows exist (zero)
+  m->kpad = L < 64 ? 64 : L;
+  auto fail = [&](int rc) { p3d_model_destroy(m); return rc; };
+#define P3D_ALLOC(ptr, bytes)                                                                  \
+  do {                                                                                         \
+    cudaError_t e__ = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                   \
+    if (e__ != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e__)); return fail(P3D_ERR_CUDA); } \
+    cudaMemset((ptr), 0, (bytes));                                                             \
+  } while (0)
+  P3D_ALLOC(m->theta, sizeof(float) * m->n_train);
+  P3D_ALLOC(m->grad, sizeof(float) * m->n_train);
+  P3D_ALLOC(m->adam_m, sizeof(float) * m->n_train);
+  P3D_ALLOC(m->adam_v, sizeof(float) * m->n_train);
+  P3D_ALLOC(m->moving, sizeof(float) * (m->n_moving ? m->n_moving : 1));
+  P3D_ALLOC(m->wt_bf16, sizeof(__nv_bfloat16) * static_cast<size_t>(m->rows_total) * m->kpad);
+  P3D_ALLOC(m->bias_fold, sizeof(float) * m->rows_total);
+  P3D_ALLOC(m->wfold, sizeof(float) * wf);
+  P3D_ALLOC(m->norm2, sizeof(double) * nlay);
+  P3D_ALLOC(m->pipe_loss, sizeof(double));
+#undef P3D_ALLOC
+  // TF default BN state: gamma 1, beta 0, moving_mean 0, moving_variance 1
+  for (auto& ly : m->layers) {
+    if (!ly.has_bn) continue;
+    if (fill(m->theta + ly.off_gamma, ly.N, 1.f) != P3D_OK) return fail(P3D_ERR_CUDA);
+    if (fill(m->moving + ly.off_mv, ly.N, 1.f) != P3D_OK) return fail(P3D_ERR_CUDA);
+  }
+  for (auto& ly : m->layers) {
+    m->params.push_back({ly.wname, m->theta + ly.off_w, static_cast<size_t>(ly.K) * ly.N, true});
+    m->params.push_back({ly.bname, m->theta + ly.off_b, static_cast<size_t>(ly.N), true});
+    if (ly.has_bn) {
+      m->params.push_back({ly.bnscope + "/gamma", m->theta + ly.off_gamma, static_cast<size_t>(ly.N), true});
+      m->params.push_back({ly.bnscope + "/beta", m->theta + ly.off_beta, static_cast<size_t>(ly.N), true});
+      m->params.push_back({ly.bnscope + "/moving_mean", m->moving + ly.off_mm, static_cast<size_t>(ly.N), true});
+      m->params.push_back({ly.bnscope + "/moving_variance", m->moving + ly.off_mv, static_cast<size_t>(ly.N), true});
+    }
+  }
+  // Adam slots (tf.train.AdamOptimizer slot names "Adam" = m, "Adam_1" = v)
+  const size_t nvars = m->params.size();
+  for (size_t i = 0; i < nvars; ++i) {
+    const NamedParam p = m->params[i];
+    if (p.ptr < m->theta || p.ptr >= m->theta + m->n_train) continue;
+    const size_t o = p.ptr - m->theta;
+    m->params.push_back({p.name + "/Adam", m->adam_m + o, p.numel, false});
+    m->params.push_back({p.name + "/Adam_1", m->adam_v + o, p.numel, false});
+    // last computed gradient (what the reference exposes as model.gradients, src/linear_model.py:143-144)
+    m->params.push_back({p.name + "/gradient", m->grad + o, p.numel, false});
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("model_create: device error"); return fail(P3D_ERR_CUDA); }
+  *out = m;
+  return P3D_OK;
+}
+
+void p3d_model_destroy(p3d_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  cudaDeviceSynchronize();
+  train::free_workspace(m);
+  cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
+  cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
+  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a);
+  for (int i = 0; i < 3; ++i) {
+    if (m->pipe_streams[i]) cudaStreamDestroy(m->pipe_streams[i]);
+    cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
+  }
+  delete m;
+}
+
+int p3d_model_param_count(p3d_model* m) { return m ? static_cast<int>(m->params.size()) + 1 : 0; }
+
+int p3d_model_param_name(p3d_model* m, int index, char* out, size_t cap, size_t* numel) {
+  P3D_REQUIRE(m && out && cap > 0, "param_name: null argument");
+  const int n = static_cast<int>(m->params.size());
+  P3D_REQUIRE(index >= 0 && index <= n, "param_name: index %d out of range", index);
+  if (index == n) { snprintf(out, cap, "global_step"); if (numel) *numel = 1; return P3D_OK; }
+  snprintf(out, cap, "%s", m->params[index].name.c_str());
+  if (numel) *numel = m->params[index].numel;
+  return P3D_OK;
+}
+
+int p3d_model_set_param_host(p3d_model* m, const char* name, const float* host, size_t n) {
+  P3D_REQUIRE(m && name && host, "set_param: null argument");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  if (strcmp(name, "global_step") == 0) {
+    P3D_REQUIRE(n == 1, "global_step is a scalar");
+    m->global_step = static_cast<int64_t>(host[0]);
+    return P3D_OK;
+  }
+  NamedParam* p = find_param(m, name);
+  P3D_REQUIRE(p, "unknown variable '%s'", name);
+  P3D_REQUIRE(p->numel == n, "variable '%s' has %zu elements, got %zu", name, p->numel, n);
+  P3D_CUDA(cudaMemcpy(p->ptr, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (p->affects_inference) m->pack_valid = false;
+  return P3D_OK;
+}
+
+int p3d_model_get_param_host(p3d_model* m, const char* name, float* host, size_t n) {
+  P3D_REQUIRE(m && name && host, "get_param: null argument");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  if (strcmp(name, "global_step") == 0) {
+    P3D_REQUIRE(n == 1, "global_step is a scalar");
+    host[0] = static_cast<float>(m->global_step);
+    return P3D_OK;
+  }
+  NamedParam* p = find_param(m, name);
+  P3D_REQUIRE(p, "unknown variable '%s'", name);
+  P3D_REQUIRE(p->numel == n, "variable '%s' has %zu elements, got %zu", name, p->numel, n);
+  P3D_CUDA(cudaDeviceSynchronize());
+  P3D_CUDA(cudaMemcpy(host, p->ptr, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return P3D_OK;
+}
+
+int64_t p3d_model_global_step(p3d_model* m) { return m ? m->global_step : -1; }
+
+int p3d_model_prepare_inference(p3d_model* m, void* stream) {
+  P3D_REQUIRE(m, "prepare_inference: null model");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  return prep::prepare(m, static_cast<cudaStream_t>(stream));
+}
+
+int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* stream) {
+  P3D_REQUIRE(m && x && y, "forward: null argument");
+  P3D_REQUIRE(B >= 0, "forward: negative batch");
+  if (B == 0) return P3D_OK;
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
+  if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
+  if (B <= kSmallBatchMax || (m->L % 256) != 0) {
+    if (B <= kSmallBatchMax) return simt::forward_small(m, x, y, B, st);
+    return simt::forward_fp32(m, x, y, B, st);   // widths the tensor-core tiling does not cover
+  }
+  if (m->xb_cap < B) {
+    if (m->xb) cudaFree(m->xb);
+    m->xb = nullptr; m->xb_cap = 0;
+    P3D_CUDA(cudaMalloc(&m->xb, sizeof(__nv_bfloat16) * 64ull * B));
+    m->xb_cap = B;
+  }
+  P3D_TRY(prep::pack_input(x, m->xb, B, st));
+  return tc::forward_bf16(m, m->xb, y, B, st);
+}
+
+int p3d_model_mse(p3d_model* m, const float* y, const float* t, int64_t B, float* loss, void* stream) {
+  P3D_REQUIRE(m && y && t && loss && B > 0, "mse: bad argument");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  P3D_CUDA(cudaMemsetAsync(m->pipe_loss, 0, sizeof(double), st));
+  P3D_TRY(sqerr_accumulate(y, t, static_cast<size_t>(B) * m->out_size, m->pipe_loss, st));
+  finish_mse_kernel<<<1, 1, 0, st>>>(m->pipe_loss, static_cast<double>(B) * m->out_size, loss);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_host, float* y_host, float* loss_host, int64_t B) {
+  P3D_REQUIRE(m && x_host && y_host, "step_eval_host: null argument");
+  P3D_REQUIRE(B >= 0, "step_eval_host: negative batch");
+  if (loss_host) *loss_host = 0.f;
+  if (B == 0) return P3D_OK;
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  const int out = m->out_size;
+  const int64_t chunk = B < 65536 ? B : 65536;
+  if (!m->pipe_streams[0])
+    for (int i = 0; i < 3; ++i) P3D_CUDA(cudaStreamCreateWithFlags(&m->pipe_streams[i], cudaStreamNonBlocking));
+  if (m->pipe_chunk < chunk) {
+    for (int i = 0; i < 3; ++i) {
+      cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
+      m->pipe_x[i] = m->pipe_t[i] = m->pipe_y[i] = nullptr;
+    }
+    m->pipe_chunk = 0;
+    for (int i = 0; i < 3; ++i) {
+      P3D_CUDA(cudaMalloc(&m->pipe_x[i], sizeof(float) * chunk * kIn));
+      P3D_CUDA(cudaMalloc(&m->pipe_t[i], sizeof(float) * chunk * out));
+      P3D_CUDA(cudaMalloc(&m->pipe_y[i], sizeof(float) * chunk * out));
+    }
+    m->pipe_chunk = chunk;
+  }
+  cudaStream_t s_in = m->pipe_streams[0], s_cmp = m->pipe_streams[1], s_out = m->pipe_streams[2];
+  cudaEvent_t ev_in[3], ev_cmp[3], ev_out[3];
+  for (int i = 0; i < 3; ++i) {
+    P3D_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+    P3D_CUDA(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
+    P3D_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+  }
+  int rc = P3D_OK;
+  if (!m->pack_valid) rc = prep::prepare(m, s_cmp);
+  if (rc == P3D_OK && cudaMemsetAsync(m->pipe_loss, 0, sizeof(double), s_cmp) != cudaSuccess) rc = P3D_ERR_CUDA;
+  int64_t done = 0;
+  for (int it = 0; rc == P3D_OK && done < B; ++it) {
+    const int slot = it % 3;
+    const int64_t n = (B - done < chunk) ? (B - done) : chunk;
+    if (it >= 3) cudaStreamWaitEvent(s_in, ev_out[slot], 0);      // slot buffers free again
+    cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in);
+    if (t_host) cudaMemcpyAsync(m->pipe_t[slot], t_host + done * out, sizeof(float) * n * out, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(ev_in[slot], s_in);
+    cudaStreamWaitEvent(s_cmp, ev_in[slot], 0);
+    rc = p3d_model_forward(m, m->pipe_x[slot], m->pipe_y[slot], n, s_cmp);
+    if (rc != P3D_OK) break;
+    if (t_host) rc = sqerr_accumulate(m->pipe_y[slot], m->pipe_t[slot], static_cast<size_t>(n) * out, m->pipe_loss, s_cmp);
+    cudaEventRecord(ev_cmp[slot], s_cmp);
+    cudaStreamWaitEvent(s_out, ev_cmp[slot], 0);
+    cudaMemcpyAsync(y_host + done * out, m->pipe_y[slot], sizeof(float) * n * out, cudaMemcpyDeviceToHost, s_out);
+    cudaEventRecord(ev_out[slot], s_out);
+    done += n;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+  for (int i = 0; i < 3; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_cmp[i]); cudaEventDestroy(ev_out[i]); }
+  if (rc != P3D_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    set_error("step_eval_host: %s", cudaGetErrorString(e));
+    return P3D_ERR_CUDA;
+  }
+  if (t_host && loss_host) {
+    double acc = 0;
+    P3D_CUDA(cudaMemcpy(&acc, m->pipe_loss, sizeof(double), cudaMemcpyDeviceToHost));
+    *loss_host = static_cast<float>(acc / (static_cast<double>(B) * out));
+  }
+  return P3D_OK;
+}
+
+int p3d_debug_umma_gemm(const void* A, const void* W, float* C, int N, int K, void* stream) {
+  P3D_REQUIRE(A && W && C, "debug_umma_gemm: null argument");
+  return tc::debug_umma_gemm(A, W, C, N, K, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

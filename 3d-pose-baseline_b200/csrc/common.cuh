@@ -1,0 +1,158 @@
+// Shared host-side plumbing for libp3d: error reporting, launch accounting, model state.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/p3d.h"
+
+namespace p3d {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define P3D_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::p3d::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return P3D_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define P3D_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    ::p3d::count_launch();                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::p3d::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return P3D_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define P3D_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::p3d::set_error(__VA_ARGS__);    \
+      return P3D_ERR_ARG;               \
+    }                                   \
+  } while (0)
+
+#define P3D_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != P3D_OK) return rc__; \
+  } while (0)
+
+constexpr float kBnEps = 1e-3f;       // tf.layers.batch_normalization default
+constexpr float kBnMomentum = 0.99f;  // idem
+constexpr int kIn = 32;               // HUMAN_2D_SIZE (linear_model.py:60)
+
+// One Linear(+BN) stage of the network, in graph order: w1 | (w2_i, w3_i)* | w4.
+struct Layer {
+  int K = 0, N = 0;
+  bool has_bn = false;   // hidden layers when cfg.batch_norm
+  bool hidden = true;    // false for the output layer (no BN/ReLU/dropout)
+  // offsets (in floats) into the flat trainable buffer theta / grad / adam_m / adam_v
+  size_t off_w = 0, off_b = 0, off_gamma = 0, off_beta = 0;
+  // offsets into the flat non-trainable buffer (moving_mean | moving_variance)
+  size_t off_mm = 0, off_mv = 0;
+  // packed inference weights: row offset into wt_bf16 / bias_fold
+  int row_off = 0;
+  // fp32 folded weights [K,N] offset into wfold
+  size_t off_wfold = 0;
+  std::string wname, bname, bnscope;
+};
+
+struct NamedParam {
+  std::string name;
+  float* ptr;     // device
+  size_t numel;
+  bool affects_inference;
+};
+
+struct TrainWorkspace {
+  int64_t cap_B = 0;
+  float* z = nullptr;       // [nhidden][B][L] pre-BN activations
+  float* h = nullptr;       // [nhidden][B][L] post-dropout(+residual) activations
+  float* dh = nullptr;      // [B][L] gradient wrt current layer output
+  float* dz = nullptr;      // [B][L]
+  float* dres = nullptr;    // [B][L] residual-path gradient
+  uint8_t* maskbuf = nullptr;  // [nhidden][B][L] dropout keep-masks
+  float* dy = nullptr;      // [B][out]
+  double* stats = nullptr;  // [nhidden][2][L] sum, sumsq (double) then mean,var
+  float* mean = nullptr;    // [nhidden][L]
+  float* rstd = nullptr;    // [nhidden][L]
+  double* red = nullptr;    // [nhidden][2][L] backward sums (dgamma, dbeta) + misc scalars
+  float* scal = nullptr;    // small device scalars: loss, lr, clip dots...
+};
+
+namespace simt {
+struct Epilogue {
+  const float* bias = nullptr;        // [N] added to every row
+  const float* res = nullptr;         // [M,N] (ldc) added after the activation
+  int relu = 0;
+  const float* alpha_dev = nullptr;   // optional device scalar multiplying the product (clip scale)
+  float alpha = 1.f;
+  float beta = 0.f;                   // C = alpha*AB + beta*C before bias/activation
+};
+// C[M,N] = epi(alpha * op(A)[M,K] op(B)[K,N]);  op(A)[m,k] = ta ? A[k*lda+m] : A[m*lda+k],
+// op(B)[k,n] = tb ? B[n*ldb+k] : B[k*ldb+n]
+int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+          int ldc, const Epilogue& e, cudaStream_t st);
+}  // namespace simt
+int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st);
+
+}  // namespace p3d
+
+struct p3d_model {
+  p3d_cfg cfg;
+  int out_size = 48;
+  int L = 1024;
+  std::vector<p3d::Layer> layers;
+  std::vector<p3d::NamedParam> params;
+  // flat parameter storage
+  size_t n_train = 0, n_moving = 0;
+  float* theta = nullptr;
+  float* grad = nullptr;
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  float* moving = nullptr;
+  int64_t global_step = 0;
+  // inference pack
+  bool pack_valid = false;
+  int rows_total = 0;      // sum of N over layers
+  int kpad = 0;            // row pitch (elements) of wt_bf16 = max(L,64)
+  __nv_bfloat16* wt_bf16 = nullptr;  // [rows_total][kpad], K-major, BN+clip folded
+  float* bias_fold = nullptr;        // [rows_total]
+  float* wfold = nullptr;            // fp32 folded [K,N] per layer, concatenated
+  double* norm2 = nullptr;           // [nlayers] ||W||_F^2
+  // forward scratch
+  int num_sms = 0;
+  __nv_bfloat16* act_scratch = nullptr;  // [2][grid*128][L] bf16 (tcgen05 path)
+  int act_grid = 0;
+  __nv_bfloat16* xb = nullptr;           // packed input [cap][64]
+  int64_t xb_cap = 0;
+  float* f32_a = nullptr;                // fp32-path activations [3][cap][L]
+  int64_t f32_cap = 0;
+  // host-step pipeline
+  cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
+  float* pipe_x[3] = {nullptr, nullptr, nullptr};
+  float* pipe_t[3] = {nullptr, nullptr, nullptr};
+  float* pipe_y[3] = {nullptr, nullptr, nullptr};
+  float* pipe_hx[3] = {nullptr, nullptr, nullptr};   // pinned staging (used when caller memory is pageable)
+  float* pipe_hy[3] = {nullptr, nullptr, nullptr};
+  float* pipe_ht[3] = {nullptr, nullptr, nullptr};
+  double* pipe_loss = nullptr;                        // device accumulator (sum of squared errors)
+  int64_t pipe_chunk = 0;
+  // training
+  p3d::TrainWorkspace tw;
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};

@@ -1,0 +1,343 @@
+// Camera-frame preprocessing kernels (K4): HBM-bound, coalesced, staged through shared memory.
+//   cameras.project_point_radial / world_to_camera_frame / camera_to_world_frame  (src/cameras.py:13-90)
+//   data_utils.project_to_cameras + transform_world_to_camera + postprocess_3d + normalize_data
+//                                                   (src/data_utils.py:233-280,339-364,474-494)
+//   data_utils.normalize_data / unNormalizeData     (src/data_utils.py:260-311)
+#include "common.cuh"
+#include "math_hd.h"
+
+namespace p3d {
+namespace geo {
+
+// H36M joints with a name (data_utils.py:19-39); 2D drops Neck/Nose(14), 3D drops Hip(0)
+// (and Spine(12), Neck/Nose(14) when predict_14) - data_utils.py:214-228.
+__constant__ int kJoints2D[16] = {0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27};
+__constant__ int kJoints3D16[16] = {1, 2, 3, 6, 7, 8, 12, 13, 14, 15, 17, 18, 19, 25, 26, 27};
+__constant__ int kJoints3D14[14] = {1, 2, 3, 6, 7, 8, 13, 15, 17, 18, 19, 25, 26, 27};
+static const int hJoints2D[16] = {0, 1, 2, 3, 6, 7, 8, 12, 13, 15, 17, 18, 19, 25, 26, 27};
+static const int hJoints3D16[16] = {1, 2, 3, 6, 7, 8, 12, 13, 14, 15, 17, 18, 19, 25, 26, 27};
+static const int hJoints3D14[14] = {1, 2, 3, 6, 7, 8, 13, 15, 17, 18, 19, 25, 26, 27};
+
+template <typename T>
+static CamT<T> to_cam(const p3d_camera& c) {
+  CamT<T> o;
+  for (int i = 0; i < 9; ++i) o.R[i] = static_cast<T>(c.R[i]);
+  for (int i = 0; i < 3; ++i) { o.Tr[i] = static_cast<T>(c.T[i]); o.k[i] = static_cast<T>(c.k[i]); }
+  for (int i = 0; i < 2; ++i) { o.f[i] = static_cast<T>(c.f[i]); o.c[i] = static_cast<T>(c.c[i]); o.p[i] = static_cast<T>(c.p[i]); }
+  return o;
+}
+
+// ------------------------------------------------------------------ faithful elementwise forms
+template <typename T>
+__global__ void project_point_radial_kernel(const T* __restrict__ P, const CamT<T> cam, T* __restrict__ proj,
+                                            T* __restrict__ D, T* __restrict__ radial, T* __restrict__ tang,
+                                            T* __restrict__ r2o, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    T u, v, d, ra, ta, r2;
+    project_point(cam, P[3 * i], P[3 * i + 1], P[3 * i + 2], u, v, d, ra, ta, r2);
+    proj[2 * i] = u; proj[2 * i + 1] = v;
+    if (D) D[i] = d;
+    if (radial) radial[i] = ra;
+    if (tang) tang[i] = ta;
+    if (r2o) r2o[i] = r2;
+  }
+}
+
+template <bool INVERSE>
+__global__ void rigid_kernel(const double* __restrict__ P, const CamT<double> cam, double* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double a, b, c;
+    if (INVERSE) cam_to_world(cam, P[3 * i], P[3 * i + 1], P[3 * i + 2], a, b, c);
+    else world_to_cam(cam, P[3 * i], P[3 * i + 1], P[3 * i + 2], a, b, c);
+    out[3 * i] = a; out[3 * i + 1] = b; out[3 * i + 2] = c;
+  }
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+// ------------------------------------------------------------------ fused project + normalise
+constexpr int MAXCAMS = 8;
+constexpr int PPB = 16;   // poses per block (16 poses x 16 joints = 256 threads)
+
+struct FusedArgs {
+  CamT<float> cam[MAXCAMS];
+  float mean2[32], istd2[32];   // gathered to the used dims
+  float mean3[48], istd3[48];
+  int ncams;
+  int out3;        // 48 or 42
+  int nj3;         // 16 or 14
+  int predict_14;
+};
+
+__global__ void __launch_bounds__(256) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
+                                                               float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
+  __shared__ __align__(16) float sw[PPB * 96];
+  __shared__ __align__(16) float s2[PPB * 32];
+  __shared__ __align__(16) float s3[PPB * 48];
+  const int tid = threadIdx.x;
+  const int lp = tid >> 4, j = tid & 15;   // local pose, joint slot
+  const long long ntiles = (N + PPB - 1) / PPB;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * PPB;
+    const int np = static_cast<int>((N - p0 < PPB) ? (N - p0) : PPB);
+    // coalesced stage-in of np*96 floats (rows are 384 B => float4 aligned)
+    const float4* src = reinterpret_cast<const float4*>(world + p0 * 96);
+    for (int i = tid; i < np * 24; i += 256) reinterpret_cast<float4*>(sw)[i] = __ldg(src + i);
+    __syncthreads();
+    const bool live = lp < np;
+    const float* w = sw + lp * 96;
+    for (int c = 0; c < a.ncams; ++c) {
+      if (live && x2d) {
+        const int jj = kJoints2D[j];
+        float u, v, d, ra, ta, r2;
+        project_point(a.cam[c], w[jj * 3], w[jj * 3 + 1], w[jj * 3 + 2], u, v, d, ra, ta, r2);
+        s2[lp * 32 + 2 * j] = (u - a.mean2[2 * j]) * a.istd2[2 * j];
+        s2[lp * 32 + 2 * j + 1] = (v - a.mean2[2 * j + 1]) * a.istd2[2 * j + 1];
+      }
+      if (live && y3d && j < a.nj3) {
+        const int jj = a.predict_14 ? kJoints3D14[j] : kJoints3D16[j];
+        float X0, X1, X2, H0, H1, H2;
+        world_to_cam(a.cam[c], w[jj * 3], w[jj * 3 + 1], w[jj * 3 + 2], X0, X1, X2);
+        world_to_cam(a.cam[c], w[0], w[1], w[2], H0, H1, H2);     // root (hip) for postprocess_3d
+        s3[lp * a.out3 + 3 * j] = ((X0 - H0) - a.mean3[3 * j]) * a.istd3[3 * j];
+        s3[lp * a.out3 + 3 * j + 1] = ((X1 - H1) - a.mean3[3 * j + 1]) * a.istd3[3 * j + 1];
+        s3[lp * a.out3 + 3 * j + 2] = ((X2 - H2) - a.mean3[3 * j + 2]) * a.istd3[3 * j + 2];
+      }
+      __syncthreads();
+      if (x2d) {
+        float4* dst = reinterpret_cast<float4*>(x2d + (static_cast<long long>(c) * N + p0) * 32);
+        for (int i = tid; i < np * 8; i += 256) dst[i] = reinterpret_cast<const float4*>(s2)[i];
+      }
+      if (y3d) {
+        float* dst = y3d + (static_cast<long long>(c) * N + p0) * a.out3;
+        const int tot = np * a.out3;
+        if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (tot % 4 == 0)) {
+          for (int i = tid; i < tot / 4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s3)[i];
+        } else {
+          for (int i = tid; i < tot; i += 256) dst[i] = s3[i];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ normalise / un-normalise (f64, one array)
+struct NormArgs {
+  double mean[96], stdv[96];
+  short use[96];     // normalize: use[d] = source column of output d ; unnormalize: use[j] = input column of full dim j or -1
+  int din, dout;
+};
+
+__global__ void normalize_kernel(const double* __restrict__ in, const __grid_constant__ NormArgs a, double* __restrict__ out, long long N) {
+  const long long total = N * a.dout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / a.dout;
+    const int d = static_cast<int>(i - r * a.dout);
+    const int s = a.use[d];
+    out[i] = (in[r * a.din + s] - a.mean[s]) / a.stdv[s];
+  }
+}
+
+__global__ void unnormalize_kernel(const double* __restrict__ in, const __grid_constant__ NormArgs a, double* __restrict__ out, long long N) {
+  const long long total = N * a.dout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / a.dout;
+    const int j = static_cast<int>(i - r * a.dout);
+    const int s = a.use[j];
+    // the reference scatters into a float32 matrix first (data_utils.py:299-303)
+    const double v = (s >= 0) ? static_cast<double>(static_cast<float>(in[r * a.din + s])) : 0.0;
+    out[i] = v * a.stdv[j] + a.mean[j];
+  }
+}
+
+
+// ------------------------------------------------------------------ column statistics / root centring (f64)
+// data_utils.normalization_stats (src/data_utils.py:211-212): column mean and POPULATION std.
+// pass 0 accumulates sum(x), pass 1 accumulates sum((x-mean)^2) - two passes keep fp64 accuracy.
+__global__ void colstat_pass_kernel(const double* __restrict__ data, long long N, int D, const double* __restrict__ mean_or_null,
+                                    double invN, double* __restrict__ acc) {
+  __shared__ double sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.y) * 1024;
+  const long long r1 = (r0 + 1024 < N) ? r0 + 1024 : N;
+  double s = 0;
+  if (c < D) {
+    const double mu = mean_or_null ? mean_or_null[c] * invN : 0.0;
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) { const double v = data[r * D + c] - mu; s += mean_or_null ? v * v : v; }
+  }
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    for (int i = 1; i < 8; ++i) s += sh[i][threadIdx.x];
+    atomicAdd(acc + c, s);
+  }
+}
+__global__ void colstat_finish_kernel(const double* sum, const double* ssq, double invN, int D, double* mean, double* stdv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < D) { mean[c] = sum[c] * invN; stdv[c] = sqrt(ssq[c] * invN); }
+}
+// data_utils.postprocess_3d (src/data_utils.py:474-494): subtract the root joint from every joint
+__global__ void root_center_kernel(const double* __restrict__ in, double* __restrict__ out, double* __restrict__ roots, long long N, int D) {
+  const long long total = N * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / D;
+    const int c = static_cast<int>(i - r * D);
+    const double root = in[r * D + (c % 3)];
+    if (roots && c < 3) roots[r * 3 + c] = root;
+    out[i] = in[i] - root;
+  }
+}
+
+static int use_table(int dim, int predict_14, int* use, int* nuse) {
+  int n = 0;
+  if (dim == 2) {
+    for (int j = 0; j < 16; ++j) { use[n++] = hJoints2D[j] * 2; use[n++] = hJoints2D[j] * 2 + 1; }
+  } else if (dim == 3) {
+    const int nj = predict_14 ? 14 : 16;
+    const int* jt = predict_14 ? hJoints3D14 : hJoints3D16;
+    for (int j = 0; j < nj; ++j) { use[n++] = jt[j] * 3; use[n++] = jt[j] * 3 + 1; use[n++] = jt[j] * 3 + 2; }
+  } else {
+    set_error("dim must be 2 or 3");
+    return P3D_ERR_ARG;
+  }
+  *nuse = n;
+  return P3D_OK;
+}
+
+}  // namespace geo
+}  // namespace p3d
+
+using namespace p3d;
+using namespace p3d::geo;
+
+extern "C" {
+
+int p3d_project_point_radial_f64(const double* P, const p3d_camera* cam, double* proj, double* D, double* radial,
+                                 double* tan_, double* r2, int64_t npts, void* stream) {
+  P3D_REQUIRE(P && cam && proj && npts >= 0, "project_point_radial: null argument");
+  if (npts == 0) return P3D_OK;
+  project_point_radial_kernel<double><<<grid_for(npts), 256, 0, (cudaStream_t)stream>>>(P, to_cam<double>(*cam), proj, D, radial, tan_, r2, npts);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_project_point_radial_f32(const float* P, const p3d_camera* cam, float* proj, float* D, float* radial,
+                                 float* tan_, float* r2, int64_t npts, void* stream) {
+  P3D_REQUIRE(P && cam && proj && npts >= 0, "project_point_radial: null argument");
+  if (npts == 0) return P3D_OK;
+  project_point_radial_kernel<float><<<grid_for(npts), 256, 0, (cudaStream_t)stream>>>(P, to_cam<float>(*cam), proj, D, radial, tan_, r2, npts);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_world_to_camera_f64(const double* P, const p3d_camera* cam, double* out, int64_t npts, void* stream) {
+  P3D_REQUIRE(P && cam && out && npts >= 0, "world_to_camera: null argument");
+  if (npts == 0) return P3D_OK;
+  rigid_kernel<false><<<grid_for(npts), 256, 0, (cudaStream_t)stream>>>(P, to_cam<double>(*cam), out, npts);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_camera_to_world_f64(const double* P, const p3d_camera* cam, double* out, int64_t npts, void* stream) {
+  P3D_REQUIRE(P && cam && out && npts >= 0, "camera_to_world: null argument");
+  if (npts == 0) return P3D_OK;
+  rigid_kernel<true><<<grid_for(npts), 256, 0, (cudaStream_t)stream>>>(P, to_cam<double>(*cam), out, npts);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams, const double* mean2d, const double* std2d,
+                          const double* mean3d, const double* std3d, int predict_14, float* x2d, float* y3d, int64_t N,
+                          void* stream) {
+  P3D_REQUIRE(world && cams && ncams >= 1 && ncams <= MAXCAMS, "project_normalize: need 1..%d cameras", MAXCAMS);
+  P3D_REQUIRE(x2d || y3d, "project_normalize: no output requested");
+  P3D_REQUIRE(!x2d || (mean2d && std2d), "project_normalize: 2D statistics missing");
+  P3D_REQUIRE(!y3d || (mean3d && std3d), "project_normalize: 3D statistics missing");
+  if (N == 0) return P3D_OK;
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ncams = ncams;
+  for (int c = 0; c < ncams; ++c) a.cam[c] = to_cam<float>(cams[c]);
+  int use[96], n;
+  if (x2d) {
+    P3D_TRY(use_table(2, 0, use, &n));
+    for (int d = 0; d < n; ++d) { a.mean2[d] = (float)mean2d[use[d]]; a.istd2[d] = (float)(1.0 / std2d[use[d]]); }
+  }
+  a.predict_14 = predict_14 ? 1 : 0;
+  a.nj3 = predict_14 ? 14 : 16;
+  a.out3 = a.nj3 * 3;
+  if (y3d) {
+    P3D_TRY(use_table(3, predict_14, use, &n));
+    for (int d = 0; d < n; ++d) { a.mean3[d] = (float)mean3d[use[d]]; a.istd3[d] = (float)(1.0 / std3d[use[d]]); }
+  }
+  long long ntiles = (N + PPB - 1) / PPB;
+  int grid = ntiles < 148 * 8 ? (int)ntiles : 148 * 8;
+  project_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(world, a, x2d, y3d, N);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_normalize_f64(const double* in, const double* mean, const double* stdv, int dim, int predict_14, double* out,
+                      int64_t N, void* stream) {
+  P3D_REQUIRE(in && mean && stdv && out, "normalize: null argument");
+  NormArgs a;
+  int use[96], n;
+  P3D_TRY(use_table(dim, predict_14, use, &n));
+  a.din = dim == 2 ? 64 : 96; a.dout = n;
+  for (int j = 0; j < a.din; ++j) { a.mean[j] = mean[j]; a.stdv[j] = stdv[j]; }
+  for (int d = 0; d < n; ++d) a.use[d] = (short)use[d];
+  if (N == 0) return P3D_OK;
+  normalize_kernel<<<grid_for(N * a.dout), 256, 0, (cudaStream_t)stream>>>(in, a, out, N);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_unnormalize_f64(const double* in, const double* mean, const double* stdv, int dim, int predict_14, double* out,
+                        int64_t N, void* stream) {
+  P3D_REQUIRE(in && mean && stdv && out, "unnormalize: null argument");
+  NormArgs a;
+  int use[96], n;
+  P3D_TRY(use_table(dim, predict_14, use, &n));
+  a.dout = dim == 2 ? 64 : 96; a.din = n;
+  for (int j = 0; j < a.dout; ++j) { a.mean[j] = mean[j]; a.stdv[j] = stdv[j]; a.use[j] = -1; }
+  for (int d = 0; d < n; ++d) a.use[use[d]] = (short)d;
+  if (N == 0) return P3D_OK;
+  unnormalize_kernel<<<grid_for(N * a.dout), 256, 0, (cudaStream_t)stream>>>(in, a, out, N);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_column_stats_f64(const double* data, int64_t N, int D, double* mean, double* stdv, double* work /*[2*D]*/, void* stream) {
+  P3D_REQUIRE(data && mean && stdv && work && N >= 1 && D >= 1, "column_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  P3D_CUDA(cudaMemsetAsync(work, 0, sizeof(double) * 2 * D, st));
+  dim3 grid((D + 31) / 32, (unsigned)((N + 1023) / 1024)), block(32, 8);
+  colstat_pass_kernel<<<grid, block, 0, st>>>(data, N, D, nullptr, 1.0 / N, work);
+  P3D_LAUNCH_CHECK();
+  colstat_pass_kernel<<<grid, block, 0, st>>>(data, N, D, work, 1.0 / N, work + D);
+  P3D_LAUNCH_CHECK();
+  colstat_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(work, work + D, 1.0 / N, D, mean, stdv);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_root_center_f64(const double* in, double* out, double* roots_or_null, int64_t N, int D, void* stream) {
+  P3D_REQUIRE(in && out && N >= 0 && D >= 3 && D % 3 == 0, "root_center: bad argument");
+  if (N == 0) return P3D_OK;
+  P3D_REQUIRE(in != out, "root_center: in-place is not supported");
+  root_center_kernel<<<grid_for(N * D), 256, 0, (cudaStream_t)stream>>>(in, out, roots_or_null, N, D);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+}  // extern "C"

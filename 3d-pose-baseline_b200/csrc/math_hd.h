@@ -1,0 +1,151 @@
+// Host/device math shared by the geometry and evaluation kernels.  Header-only and free of CUDA
+// types so that tests/hostcheck can compile the very same code with g++ and compare it with the
+// oracle on the CPU (test infrastructure only - the product always runs these on the GPU).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define P3D_HD __host__ __device__ __forceinline__
+#else
+#define P3D_HD inline
+#endif
+
+namespace p3d {
+
+template <typename T>
+struct CamT {
+  T R[9], Tr[3], f[2], c[2], k[3], p[2];
+};
+
+// cameras.world_to_camera_frame (src/cameras.py:55-72): X = R (P - T)
+template <typename T>
+P3D_HD void world_to_cam(const CamT<T>& cam, T px, T py, T pz, T& X0, T& X1, T& X2) {
+  const T dx = px - cam.Tr[0], dy = py - cam.Tr[1], dz = pz - cam.Tr[2];
+  X0 = cam.R[0] * dx + cam.R[1] * dy + cam.R[2] * dz;
+  X1 = cam.R[3] * dx + cam.R[4] * dy + cam.R[5] * dz;
+  X2 = cam.R[6] * dx + cam.R[7] * dy + cam.R[8] * dz;
+}
+
+// cameras.camera_to_world_frame (src/cameras.py:74-90): P = R^T X + T
+template <typename T>
+P3D_HD void cam_to_world(const CamT<T>& cam, T x, T y, T z, T& P0, T& P1, T& P2) {
+  P0 = cam.R[0] * x + cam.R[3] * y + cam.R[6] * z + cam.Tr[0];
+  P1 = cam.R[1] * x + cam.R[4] * y + cam.R[7] * z + cam.Tr[1];
+  P2 = cam.R[2] * x + cam.R[5] * y + cam.R[8] * z + cam.Tr[2];
+}
+
+// cameras.project_point_radial (src/cameras.py:39-51) for one point.
+// tan pairs p[0] with y and p[1] with x; the additive term is [p[1]; p[0]] * r2 (:44-46).
+template <typename T>
+P3D_HD void project_point(const CamT<T>& cam, T px, T py, T pz, T& u, T& v, T& D, T& radial, T& tang, T& r2) {
+  T X0, X1, X2;
+  world_to_cam(cam, px, py, pz, X0, X1, X2);
+  const T x = X0 / X2, y = X1 / X2;
+  r2 = x * x + y * y;
+  radial = T(1) + cam.k[0] * r2 + cam.k[1] * (r2 * r2) + cam.k[2] * (r2 * r2 * r2);
+  tang = cam.p[0] * y + cam.p[1] * x;
+  const T s = radial + tang;
+  u = cam.f[0] * (x * s + cam.p[1] * r2) + cam.c[0];
+  v = cam.f[1] * (y * s + cam.p[0] * r2) + cam.c[1];
+  D = X2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optimal rotation of procrustes.compute_similarity_transform (src/procrustes.py:38-50).
+// Given A = X0^T Y0 (3x3, row-major, any positive scaling), returns T = V diag(1,1,det) U^T where
+// A = U S V^T, i.e. the reflection-corrected rotation the reference builds (:45-48), and
+// tr = s0 + s1 + det*s2 = trace(T A) (the reference's traceTA before normalisation by |X0||Y0|).
+//
+// Method: cyclic Jacobi eigen-decomposition of the symmetric A^T A -> V; U's first two columns from
+// A v_i / s_i (Gram-Schmidt), third columns as cross products, which yields exactly
+// V diag(1,1,sign det(VU^T)) U^T without ever forming a possibly ill-defined third singular vector.
+P3D_HD void jacobi_rot(double app, double aqq, double apq, double& c, double& s) {
+  if (apq == 0.0) { c = 1.0; s = 0.0; return; }
+  const double theta = (aqq - app) / (2.0 * apq);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  c = 1.0 / sqrt(t * t + 1.0);
+  s = t * c;
+}
+
+P3D_HD void kabsch_rotation(const double A[9], double T[9], double& tr) {
+  // S = A^T A
+  double S[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) S[i][j] = A[0 * 3 + i] * A[0 * 3 + j] + A[1 * 3 + i] * A[1 * 3 + j] + A[2 * 3 + i] * A[2 * 3 + j];
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
+    const double diag = fabs(S[0][0]) + fabs(S[1][1]) + fabs(S[2][2]);
+    if (off <= 1e-17 * diag) break;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 3; ++r) {
+      const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;   // (0,1), (0,2), (1,2)
+      double c, s;
+      jacobi_rot(S[p][p], S[q][q], S[p][q], c, s);
+      // S <- J^T S J with J = [[c, s], [-s, c]] on (p,q);  V <- V J
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < 3; ++k) {
+        const double skp = S[k][p], skq = S[k][q];
+        S[k][p] = c * skp - s * skq;
+        S[k][q] = s * skp + c * skq;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < 3; ++k) {
+        const double spk = S[p][k], sqk = S[q][k];
+        S[p][k] = c * spk - s * sqk;
+        S[q][k] = s * spk + c * sqk;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < 3; ++k) {
+        const double vkp = V[k][p], vkq = V[k][q];
+        V[k][p] = c * vkp - s * vkq;
+        V[k][q] = s * vkp + c * vkq;
+      }
+    }
+  }
+  // two largest eigenpairs by compare-and-swap of (eigenvalue, column) with constant indices
+  double l0 = S[0][0], l1 = S[1][1], l2 = S[2][2];
+#define P3D_CSWAP(la, lb, ca, cb)                                        \
+  if (la < lb) {                                                         \
+    double t_ = la; la = lb; lb = t_;                                    \
+    for (int k_ = 0; k_ < 3; ++k_) { t_ = V[k_][ca]; V[k_][ca] = V[k_][cb]; V[k_][cb] = t_; } \
+  }
+  P3D_CSWAP(l0, l1, 0, 1)
+  P3D_CSWAP(l0, l2, 0, 2)
+  P3D_CSWAP(l1, l2, 1, 2)
+#undef P3D_CSWAP
+  (void)l0; (void)l1; (void)l2;
+  double v1[3] = {V[0][0], V[1][0], V[2][0]};
+  double v2[3] = {V[0][1], V[1][1], V[2][1]};
+  double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+  // u1 = A v1 / |A v1| ; u2 = A v2 orthogonalised against u1 ; u3 = u1 x u2
+  double u1[3], u2[3];
+  for (int i = 0; i < 3; ++i) {
+    u1[i] = A[i * 3 + 0] * v1[0] + A[i * 3 + 1] * v1[1] + A[i * 3 + 2] * v1[2];
+    u2[i] = A[i * 3 + 0] * v2[0] + A[i * 3 + 1] * v2[1] + A[i * 3 + 2] * v2[2];
+  }
+  const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  for (int i = 0; i < 3; ++i) u1[i] /= n1;
+  const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+  for (int i = 0; i < 3; ++i) u2[i] -= d12 * u1[i];
+  const double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+  for (int i = 0; i < 3; ++i) u2[i] /= n2;
+  const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+  // T = V' U'^T : T[i][j] = v1[i]u1[j] + v2[i]u2[j] + v3[i]u3[j]
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) T[i * 3 + j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];
+  // tr = trace(T A)
+  tr = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) tr += T[i * 3 + j] * A[j * 3 + i];
+}
+
+}  // namespace p3d

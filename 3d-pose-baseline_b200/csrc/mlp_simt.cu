@@ -1,0 +1,235 @@
+// FP32 (FFMA) kernels: the "fp32 mode" forward (<=1e-4 of the fp64 oracle), the small-batch
+// (latency) forward and the generic SGEMM the training step is built from.
+// Same graph as mlp_tc.cu: src/linear_model.py:102-125,154-201.
+#include "common.cuh"
+
+namespace p3d {
+namespace simt {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+
+// C[M,N] = epi(alpha * op(A)[M,K] op(B)[K,N]);  op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k],
+// op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n].  256 threads, 64x64 tile, 4x4 per thread.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                    const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                    int ldc, const Epilogue e) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = static_cast<long long>(blockIdx.y) * TM;
+  const int n0 = blockIdx.x * TN;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each a 4x4 micro tile
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    // ---- A tile -> As[k][m]
+    if (!TA) {
+      const int mm = tid >> 2, kk = (tid & 3) * 4;
+      const long long m = m0 + mm;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + kk + j;
+        As[kk + j][mm] = (m < M && k < K) ? A[m * lda + k] : 0.f;
+      }
+    } else {
+      const int kk = tid >> 4, mm = (tid & 15) * 4;
+      const int k = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long m = m0 + mm + j;
+        As[kk][mm + j] = (m < M && k < K) ? A[static_cast<long long>(k) * lda + m] : 0.f;
+      }
+    }
+    // ---- B tile -> Bs[k][n]
+    if (!TB) {
+      const int kk = tid >> 4, nn = (tid & 15) * 4;
+      const int k = k0 + kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + nn + j;
+        Bs[kk][nn + j] = (n < N && k < K) ? B[static_cast<long long>(k) * ldb + n] : 0.f;
+      }
+    } else {
+      const int nn = tid >> 2, kk = (tid & 3) * 4;
+      const int n = n0 + nn;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + kk + j;
+        Bs[kk + j][nn] = (n < N && k < K) ? B[static_cast<long long>(n) * ldb + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float alpha = e.alpha * (e.alpha_dev ? *e.alpha_dev : 1.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (e.beta != 0.f) v += e.beta * C[m * ldc + n];
+      if (e.bias) v += e.bias[n];
+      if (e.relu) v = fmaxf(v, 0.f);
+      if (e.res) v += e.res[m * ldc + n];
+      C[m * ldc + n] = v;
+    }
+  }
+}
+
+int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+          int ldc, const Epilogue& e, cudaStream_t st) {
+  if (M == 0 || N == 0) return P3D_OK;
+  dim3 grid((N + TN - 1) / TN, static_cast<unsigned>((M + TM - 1) / TM));
+  P3D_REQUIRE(grid.y <= 65535u || true, "sgemm: M too large");
+  // gridDim.y is limited to 65535: process in slabs of rows
+  const int64_t slab = 65535ll * TM;
+  for (int64_t r0 = 0; r0 < M; r0 += slab) {
+    const int64_t mr = (M - r0 < slab) ? (M - r0) : slab;
+    dim3 g((N + TN - 1) / TN, static_cast<unsigned>((mr + TM - 1) / TM));
+    const float* Ar = ta ? A + r0 : A + r0 * lda;
+    float* Cr = C + r0 * ldc;
+    Epilogue er = e;
+    if (er.res) er.res = e.res + r0 * ldc;
+    if (!ta && !tb) sgemm_kernel<false, false><<<g, 256, 0, st>>>((int)mr, N, K, Ar, lda, B, ldb, Cr, ldc, er);
+    else if (!ta && tb) sgemm_kernel<false, true><<<g, 256, 0, st>>>((int)mr, N, K, Ar, lda, B, ldb, Cr, ldc, er);
+    else if (ta && !tb) sgemm_kernel<true, false><<<g, 256, 0, st>>>((int)mr, N, K, Ar, lda, B, ldb, Cr, ldc, er);
+    else sgemm_kernel<true, true><<<g, 256, 0, st>>>((int)mr, N, K, Ar, lda, B, ldb, Cr, ldc, er);
+    P3D_LAUNCH_CHECK();
+  }
+  return P3D_OK;
+}
+
+// fp32-mode inference through the folded fp32 weights; activations in three [cap,L] fp32 buffers
+int forward_fp32(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
+  const int L = m->L;
+  if (m->f32_cap < B) {
+    if (m->f32_a) cudaFree(m->f32_a);
+    m->f32_a = nullptr; m->f32_cap = 0;
+    P3D_CUDA(cudaMalloc(&m->f32_a, sizeof(float) * 2ull * B * L));
+    m->f32_cap = B;
+  }
+  float* P = m->f32_a;
+  float* Q = m->f32_a + static_cast<size_t>(m->f32_cap) * L;
+  const int nl = static_cast<int>(m->layers.size());
+  for (int l = 0; l < nl; ++l) {
+    const Layer& ly = m->layers[l];
+    Epilogue e;
+    e.bias = m->bias_fold + ly.row_off;
+    const float* W = m->wfold + ly.off_wfold;
+    if (l == nl - 1) {
+      P3D_TRY(sgemm(false, false, B, ly.N, ly.K, P, L, W, ly.N, y, ly.N, e, st));
+    } else if (l == 0) {
+      e.relu = 1;
+      P3D_TRY(sgemm(false, false, B, ly.N, ly.K, x, kIn, W, ly.N, P, L, e, st));
+    } else if (l & 1) {
+      e.relu = 1;
+      P3D_TRY(sgemm(false, false, B, ly.N, ly.K, P, L, W, ly.N, Q, L, e, st));
+    } else {
+      e.relu = 1;
+      if (m->cfg.residual) e.res = P;       // in-place: each element is read (res) then written by one thread
+      P3D_TRY(sgemm(false, false, B, ly.N, ly.K, Q, L, W, ly.N, P, L, e, st));
+    }
+  }
+  return P3D_OK;
+}
+
+// ----------------------------------------------------------------------------- small batch
+// Latency path (the batch-1 loop of src/openpose_3dpose_sandbox_realtime.py:50-168): one launch per
+// layer, one warp per output feature, bf16 K-major weights streamed once, fp32 activations.
+// Handles up to SB_ROWS rows per launch.
+constexpr int SB_ROWS = 8;
+
+template <int ROWS>
+__global__ void __launch_bounds__(256) small_batch_layer_kernel(const float* __restrict__ hin, int ldin, int K,
+                                                                const __nv_bfloat16* __restrict__ wt, int kpad,
+                                                                const float* __restrict__ bias, int N, int relu,
+                                                                const float* res, float* hout, int ldout, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const __nv_bfloat16* wrow = wt + static_cast<size_t>(warp) * kpad;
+  float acc[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wrow + k));
+    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[2 * i] = __low2float(w2[i]); w[2 * i + 1] = __high2float(w2[i]); }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (r < rows) {
+        const float4 a = *reinterpret_cast<const float4*>(hin + static_cast<size_t>(r) * ldin + k);
+        const float4 b = *reinterpret_cast<const float4*>(hin + static_cast<size_t>(r) * ldin + k + 4);
+        acc[r] = fmaf(a.x, w[0], acc[r]); acc[r] = fmaf(a.y, w[1], acc[r]);
+        acc[r] = fmaf(a.z, w[2], acc[r]); acc[r] = fmaf(a.w, w[3], acc[r]);
+        acc[r] = fmaf(b.x, w[4], acc[r]); acc[r] = fmaf(b.y, w[5], acc[r]);
+        acc[r] = fmaf(b.z, w[6], acc[r]); acc[r] = fmaf(b.w, w[7], acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float v = acc[r];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && r < rows) {
+      v += bias[warp];
+      if (relu) v = fmaxf(v, 0.f);
+      if (res) v += res[static_cast<size_t>(r) * ldout + warp];
+      hout[static_cast<size_t>(r) * ldout + warp] = v;
+    }
+  }
+}
+
+int forward_small(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
+  const int L = m->L;
+  if (m->f32_cap < SB_ROWS) {
+    if (m->f32_a) cudaFree(m->f32_a);
+    m->f32_a = nullptr; m->f32_cap = 0;
+    P3D_CUDA(cudaMalloc(&m->f32_a, sizeof(float) * 2ull * SB_ROWS * L));
+    m->f32_cap = SB_ROWS;
+  }
+  float* P = m->f32_a;
+  float* Q = m->f32_a + static_cast<size_t>(m->f32_cap) * L;
+  const int nl = static_cast<int>(m->layers.size());
+  for (int64_t r0 = 0; r0 < B; r0 += SB_ROWS) {
+    const int rows = static_cast<int>(B - r0 < SB_ROWS ? B - r0 : SB_ROWS);
+    for (int l = 0; l < nl; ++l) {
+      const Layer& ly = m->layers[l];
+      const __nv_bfloat16* wt = m->wt_bf16 + static_cast<size_t>(ly.row_off) * m->kpad;
+      const float* bias = m->bias_fold + ly.row_off;
+      const float* hin; int ldin; float* hout; int ldout; const float* res = nullptr; int relu = 1;
+      if (l == 0) { hin = x + r0 * kIn; ldin = kIn; hout = P; ldout = L; }
+      else if (l == nl - 1) { hin = P; ldin = L; hout = y + r0 * m->out_size; ldout = m->out_size; relu = 0; }
+      else if (l & 1) { hin = P; ldin = L; hout = Q; ldout = L; }
+      else { hin = Q; ldin = L; hout = P; ldout = L; if (m->cfg.residual) res = P; }
+      const int blocks = (ly.N * 32 + 255) / 256;
+      if (rows == 1)
+        small_batch_layer_kernel<1><<<blocks, 256, 0, st>>>(hin, ldin, ly.K, wt, m->kpad, bias, ly.N, relu, res, hout, ldout, rows);
+      else
+        small_batch_layer_kernel<SB_ROWS><<<blocks, 256, 0, st>>>(hin, ldin, ly.K, wt, m->kpad, bias, ly.N, relu, res, hout, ldout, rows);
+      P3D_LAUNCH_CHECK();
+    }
+  }
+  return P3D_OK;
+}
+
+}  // namespace simt
+}  // namespace p3d

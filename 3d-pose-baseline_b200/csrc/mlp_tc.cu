@@ -1,0 +1,368 @@
+// Fused LinearModel inference on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the op-by-op TensorFlow graph of src/linear_model.py:102-125,154-201 at inference
+// (isTraining=False): x[B,32] -> Linear+BN+ReLU -> num_layers x (two_linear + residual) -> Linear.
+// clip_by_norm and the moving-statistics BatchNorm are folded into W',b' by mlp_prep.cu, so every
+// stage is  h' = relu(h W' + b') (+ residual)  and the last one  y = h W' + b'.
+//
+// One persistent CTA per SM walks 128-pose row tiles through ALL layers:
+//   warp 0 (1 thread)  TMA producer : A tile [128 x 64] bf16 of the current activations and the
+//                                     matching W' tile [256 x 64] into a 4-stage smem ring (SW128)
+//   warp 1 (1 thread)  MMA issuer   : tcgen05.mma 128x256x16, fp32 accumulators in TMEM
+//                                     (2 x 256 columns, double buffered against the epilogue)
+//   warp 2             TMEM allocator
+//   warps 4-7          epilogue     : tcgen05.ld -> +bias -> ReLU -> (+residual) -> bf16 -> the
+//                                     CTA's private activation tile (L2 resident), or fp32 y
+// The activation tile of a CTA (2 x [128 x L] bf16) lives in a per-CTA global scratch that never
+// leaves L2; only x (128 B/pose) and y (192 B/pose) are compulsory HBM traffic.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace p3d {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int NTHREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + 4 * BN * 4 + 256;
+
+struct Params {
+  int L;           // linear_size (multiple of 256)
+  int nlayers;     // 2*num_layers + 2
+  int out_n;       // output width padded to a multiple of 16 (48)
+  int out_valid;   // 48 or 42
+  int residual;
+  int ntiles;
+  long long B;
+  long long act_half_rows;   // gridDim.x * 128 : row offset of buffer Q inside the scratch
+  const float* bias;         // folded bias, indexed by packed weight row
+  __nv_bfloat16* act;        // scratch base (buffer P), [2][grid*128][L]
+  float* y;                  // [B][out_valid]
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_act,
+                      const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wout,
+                      const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  float* sBias = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * BN);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* layer_done = tempty + 2;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_act); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_wout);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(layer_done, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int L = p.L;
+  const int nlayers = p.nlayers;
+  const int nk_hidden = L / BK;
+  const int nchunks_hidden = L / BN;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0; uint32_t ld_waits = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int l = 0; l < nlayers; ++l) {
+        const bool first = (l == 0), last = (l == nlayers - 1);
+        if (!first) {   // activations of layer l-1 must be complete and visible to the async proxy
+          mbar_wait(layer_done, ld_waits & 1, 100 + l); ++ld_waits;
+          fence_proxy_async();
+        }
+        const int nk = first ? 1 : nk_hidden;
+        const int nchunks = last ? 1 : nchunks_hidden;
+        const CUtensorMap* tmA = first ? &tm_x : &tm_act;
+        const int a_row = first ? tile * BM
+                                : static_cast<int>(((l & 1) ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
+        const uint32_t bytes = A_BYTES + (last ? p.out_n * BK * 2 : B_BYTES);
+        for (int c = 0; c < nchunks; ++c) {
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&empty[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
+            if (last) tma_load_2d(sB + stage * B_BYTES, &tm_wout, &full[stage], ks * BK, 0);
+            else      tma_load_2d(sB + stage * B_BYTES, &tm_w, &full[stage], ks * BK, l * L + c * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    int stage = 0; uint32_t phase = 0; uint32_t q = 0;
+    const uint32_t idesc_hidden = umma_idesc_bf16_f32(BM, BN);
+    const uint32_t idesc_out = umma_idesc_bf16_f32(BM, p.out_n);
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int l = 0; l < nlayers; ++l) {
+        const bool first = (l == 0), last = (l == nlayers - 1);
+        const int nk = first ? 1 : nk_hidden;
+        const int nchunks = last ? 1 : nchunks_hidden;
+        const uint32_t idesc = last ? idesc_out : idesc_hidden;
+        for (int c = 0; c < nchunks; ++c, ++q) {
+          const uint32_t acc = q & 1, aphase = (q >> 1) & 1;
+          mbar_wait(&tempty[acc], aphase ^ 1, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int ks = 0; ks < nk; ++ks) {
+            mbar_wait(&full[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                           (ks | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (128 threads = 128 rows)
+    const int ew = warp - 4;                 // == warp % 4 : the TMEM lane quadrant this warp may read
+    const int row = ew * 32 + lane;
+    float* myBias = sBias + ew * BN;
+    uint32_t q = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int l = 0; l < nlayers; ++l) {
+        const bool last = (l == nlayers - 1);
+        const int nchunks = last ? 1 : nchunks_hidden;
+        for (int c = 0; c < nchunks; ++c, ++q) {
+          const uint32_t acc = q & 1, aphase = (q >> 1) & 1;
+          const int ncols = last ? p.out_n : BN;
+          const int wrow0 = last ? (nlayers - 1) * L : l * L + c * BN;
+          __syncwarp();
+          for (int j = lane; j < ncols; j += 32) myBias[j] = __ldg(p.bias + wrow0 + j);
+          __syncwarp();
+          mbar_wait(&tfull[acc], aphase, 4);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+          if (!last) {
+            const bool to_p = (l == 0) || ((l & 1) == 0);
+            const bool add_res = p.residual && l >= 2 && ((l & 1) == 0);
+            __nv_bfloat16* drow = p.act + ((to_p ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM + row) * L + c * BN;
+#pragma unroll 1
+            for (int g = 0; g < BN / 32; ++g) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr + g * 32, v);
+              uint4 rr[4];
+              if (add_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(drow + g * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rr[i] = rp[i];
+              }
+              tmem_ld_wait();
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a0 = fmaxf(__uint_as_float(v[2 * j]) + myBias[g * 32 + 2 * j], 0.f);
+                float a1 = fmaxf(__uint_as_float(v[2 * j + 1]) + myBias[g * 32 + 2 * j + 1], 0.f);
+                if (add_res) {
+                  const uint32_t rw = reinterpret_cast<const uint32_t*>(rr)[j];
+                  __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw);
+                  a0 += __low2float(r2);
+                  a1 += __high2float(r2);
+                }
+                o[j] = pack_bf16x2(a0, a1);
+              }
+              uint4* dp = reinterpret_cast<uint4*>(drow + g * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dp[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+          } else {
+            const long long grow = static_cast<long long>(tile) * BM + row;
+            for (int g = 0; g < p.out_n / 16; ++g) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(taddr + g * 16, v);
+              tmem_ld_wait();
+              if (grow < p.B) {
+                float* yp = p.y + grow * p.out_valid + g * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const int col = g * 16 + j;
+                  if (col + 1 < p.out_valid) {
+                    float2 o2 = make_float2(__uint_as_float(v[j]) + myBias[col], __uint_as_float(v[j + 1]) + myBias[col + 1]);
+                    *reinterpret_cast<float2*>(yp + j) = o2;
+                  } else if (col < p.out_valid) {
+                    yp[j] = __uint_as_float(v[j]) + myBias[col];
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          if (!last && c == nchunks - 1) { __threadfence(); fence_proxy_async(); }
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&tempty[acc]);
+            if (!last && c == nchunks - 1) mbar_arrive(layer_done);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ----------------------------------------------------------------------------- debug GEMM
+// C[128,N] = A[128,K] W[N,K]^T with one CTA, one smem stage, fully serialised: exercises the TMA
+// tensor maps, the UMMA smem/instruction descriptors and the TMEM load layout in isolation.
+__global__ void __launch_bounds__(128, 1)
+umma_gemm_debug_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                       float* C, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + A_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + B_BYTES);
+  uint64_t* bar_mma = bar_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar_full, 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16_f32(128, N);
+    for (int ks = 0; ks < K / BK; ++ks) {
+      mbar_arrive_expect_tx(bar_full, A_BYTES + N * BK * 2);
+      tma_load_2d(sA, &tm_a, bar_full, ks * BK, 0);
+      tma_load_2d(sB, &tm_w, bar_full, ks * BK, 0);
+      mbar_wait(bar_full, ks & 1, 10);
+      tc_fence_after();
+      for (int k = 0; k < BK / 16; ++k)
+        umma_bf16_ss(tmem_base, umma_desc_k_sw128(smem_u32(sA) + k * 32), umma_desc_k_sw128(smem_u32(sB) + k * 32),
+                     idesc, (ks | k) != 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+      mbar_wait(bar_mma, ks & 1, 11);
+    }
+  }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int g = 0; g < N / 16; ++g) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 16, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) C[row * N + g * 16 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows][pitch_elems] tensor, box = [box_rows][64 cols], 128B swizzle
+static int make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return P3D_ERR_CUDA; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return P3D_ERR_CUDA; }
+  return P3D_OK;
+}
+
+int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cudaStream_t st) {
+  const int L = m->L;
+  P3D_REQUIRE(L % BN == 0, "bf16 tensor-core path needs linear_size %% 256 == 0 (got %d)", L);
+  const int ntiles = static_cast<int>((B + BM - 1) / BM);
+  const int grid = ntiles < m->num_sms ? ntiles : m->num_sms;
+  // per-CTA activation scratch, sized for a full grid once
+  if (m->act_grid < m->num_sms) {
+    if (m->act_scratch) cudaFree(m->act_scratch);
+    P3D_CUDA(cudaMalloc(&m->act_scratch, sizeof(__nv_bfloat16) * 2ull * m->num_sms * BM * L));
+    m->act_grid = m->num_sms;
+  }
+  const int nlayers = static_cast<int>(m->layers.size());
+  const int out_n = (m->out_size + 15) / 16 * 16;
+  CUtensorMap tm_x, tm_act, tm_w, tm_wout;
+  P3D_TRY(make_tmap(&tm_x, xb, static_cast<uint64_t>(B), 64, 64, BM));
+  P3D_TRY(make_tmap(&tm_act, m->act_scratch, 2ull * grid * BM, L, L, BM));
+  P3D_TRY(make_tmap(&tm_w, m->wt_bf16, static_cast<uint64_t>(nlayers - 1) * L, m->kpad, m->kpad, BN));
+  P3D_TRY(make_tmap(&tm_wout, m->wt_bf16 + static_cast<size_t>(nlayers - 1) * L * m->kpad, out_n, m->kpad, m->kpad, out_n));
+  Params p;
+  p.L = L; p.nlayers = nlayers; p.out_n = out_n; p.out_valid = m->out_size; p.residual = m->cfg.residual;
+  p.ntiles = ntiles; p.B = B; p.act_half_rows = static_cast<long long>(grid) * BM;
+  p.bias = m->bias_fold; p.act = m->act_scratch; p.y = y;
+  static bool attr_set = false;
+  if (!attr_set) {
+    P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  mlp_forward_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_x, tm_act, tm_w, tm_wout, p);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int debug_umma_gemm(const void* A, const void* W, float* C, int N, int K, cudaStream_t st) {
+  P3D_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64, "debug gemm: bad N=%d K=%d", N, K);
+  CUtensorMap tm_a, tm_w;
+  P3D_TRY(make_tmap(&tm_a, A, 128, K, K, 128));
+  P3D_TRY(make_tmap(&tm_w, W, N, K, K, N));
+  const int smem = 1024 + A_BYTES + B_BYTES + 64;
+  P3D_CUDA(cudaFuncSetAttribute(umma_gemm_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_gemm_debug_kernel<<<1, 128, smem, st>>>(tm_a, tm_w, C, N, K);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+}  // namespace tc
+}  // namespace p3d

@@ -1,0 +1,319 @@
+"""Drop-in for the reference's `linear_model.LinearModel` (src/linear_model.py:31-300) on B200.
+
+Same constructor flags, same `step()` / `get_all_batches()` contract; the TensorFlow graph and session
+are replaced by libp3d.so (hand-written sm_100a CUDA).  There is no TensorFlow, Triton or CPU path.
+
+Differences that are visible to a caller, all additive:
+  * `session` is accepted and ignored (there is no tf.Session).
+  * keyword-only extras: `mode` ('bf16' tensor-core path, or 'fp32'), `device`, `seed`, `dist`.
+  * `step()` also accepts torch CUDA tensors (fp32) and then returns torch tensors without any host copy.
+  * summaries are small `Summary(tag, value)` tuples instead of serialized protobufs.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+Summary = collections.namedtuple("Summary", ["tag", "value"])
+
+
+class _Evaluable:
+    """Stands in for a tf.Variable/Tensor that callers `.eval()` (predict_3dpose.py:228,288)."""
+
+    def __init__(self, getter):
+        self._getter = getter
+
+    def eval(self, session=None):
+        return self._getter()
+
+    def __float__(self):
+        return float(self._getter())
+
+    def __int__(self):
+        return int(self._getter())
+
+
+class _NullWriter:
+    """train_writer/test_writer placeholders (linear_model.py:81-82): summaries are returned, not logged."""
+
+    def __init__(self, path):
+        self.path = path
+        self.events = []
+
+    def add_summary(self, summary, step=None):
+        self.events.append((step, summary))
+
+    def add_graph(self, graph):
+        pass
+
+
+def kaiming(shape, rng: np.random.RandomState, dtype=np.float32):
+    """linear_model.py:17-29: truncated_normal(shape) * sqrt(2/shape[0]); samples beyond 2 sigma re-drawn."""
+    v = rng.standard_normal(int(np.prod(shape)))
+    bad = np.abs(v) > 2.0
+    while bad.any():
+        v[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(v) > 2.0
+    return (v.reshape(shape) * math.sqrt(2.0 / float(shape[0]))).astype(dtype)
+
+
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous row block of `rank` when n_rows poses are split over `world` GPUs."""
+    base, rem = divmod(n_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class LinearModel(object):
+    """A simple Linear+RELU model (linear_model.py:31)."""
+
+    def __init__(self, linear_size, num_layers, residual, batch_norm, max_norm, batch_size, learning_rate,
+                 summaries_dir=None, predict_14=False, dtype=np.float32, *, mode="bf16", device=0, seed=None,
+                 dist=None):
+        self.HUMAN_2D_SIZE = 16 * 2                                  # linear_model.py:60
+        self.HUMAN_3D_SIZE = 14 * 3 if predict_14 else 16 * 3         # :69
+        self.input_size = self.HUMAN_2D_SIZE
+        self.output_size = self.HUMAN_3D_SIZE
+        self.linear_size = int(linear_size)
+        self.num_layers = int(num_layers)
+        self.residual, self.batch_norm, self.max_norm = bool(residual), bool(batch_norm), bool(max_norm)
+        self.batch_size = int(batch_size)
+        self.predict_14 = bool(predict_14)
+        self.mode = mode
+        self.device = int(device)
+        self._lr0 = float(learning_rate)
+        self._seed = int(seed) if seed is not None else int.from_bytes(os.urandom(4), "little")
+        self._handle = None
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("mode must be 'bf16' or 'fp32'")
+        sd = summaries_dir or ""
+        self.train_writer = _NullWriter(os.path.join(sd, "train"))
+        self.test_writer = _NullWriter(os.path.join(sd, "test"))
+
+        cfg = _lib.Cfg(self.linear_size, self.num_layers, int(self.residual), int(self.batch_norm),
+                       int(self.max_norm), int(self.predict_14),
+                       _lib.MODE_BF16 if mode == "bf16" else _lib.MODE_FP32, self.device, self._lr0)
+        h = C.c_void_p()
+        check(lib.p3d_model_create(C.byref(cfg), C.byref(h)))
+        self._handle = h
+        self.global_step = _Evaluable(lambda: int(lib.p3d_model_global_step(self._handle)))
+        self.learning_rate = _Evaluable(self._decayed_lr)
+        self._names = self._query_names()
+        self._init_variables(np.random.RandomState(self._seed))
+        # data parallel (one process per GPU, torch.distributed for the rendezvous only)
+        self.rank, self.world = 0, 1
+        if dist is not None:
+            self._attach_dist(dist)
+
+    # ------------------------------------------------------------------ variables
+    def _query_names(self):
+        out = collections.OrderedDict()
+        n = lib.p3d_model_param_count(self._handle)
+        buf = C.create_string_buffer(256)
+        numel = C.c_size_t()
+        for i in range(n):
+            check(lib.p3d_model_param_name(self._handle, i, buf, 256, C.byref(numel)))
+            out[buf.value.decode()] = int(numel.value)
+        return out
+
+    def variable_shapes(self):
+        """TF variable name -> shape, weights [in,out] (what tf.train.Saver would hold)."""
+        L, shapes = self.linear_size, collections.OrderedDict()
+        for name, numel in self._names.items():
+            base = name.replace("/Adam_1", "").replace("/Adam", "").replace("/gradient", "")
+            leaf = base.rsplit("/", 1)[-1]
+            if leaf == "w1":
+                shapes[name] = (self.input_size, L)
+            elif leaf == "w4":
+                shapes[name] = (L, self.output_size)
+            elif leaf.startswith("w"):
+                shapes[name] = (L, L)
+            elif name == "global_step":
+                shapes[name] = ()
+            else:
+                shapes[name] = (numel,)
+        return shapes
+
+    def _init_variables(self, rng):
+        """kaiming for every weight AND bias (linear_model.py:106-107,121-122,176-188); BN at TF defaults."""
+        for name, shape in self.variable_shapes().items():
+            leaf = name.rsplit("/", 1)[-1]
+            if "Adam" in name or name == "global_step" or name.endswith("/gradient"):
+                continue
+            if leaf[0] in "wb" and "batch_normalization" not in name:
+                self.set_variable(name, kaiming(shape, rng))
+
+    def set_variable(self, name, value):
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float32)).reshape(-1)
+        check(lib.p3d_model_set_param_host(self._handle, name.encode(), _lib.np_ptr(a), a.size))
+
+    def get_variable(self, name):
+        shape = self.variable_shapes()[name]
+        a = np.empty(self._names[name], dtype=np.float32)
+        check(lib.p3d_model_get_param_host(self._handle, name.encode(), _lib.np_ptr(a), a.size))
+        return a.reshape(shape) if shape != () else a[0]
+
+    def get_variables(self, include_optimizer=False):
+        return {n: self.get_variable(n) for n in self._names
+                if not n.endswith("/gradient") and (include_optimizer or ("Adam" not in n and n != "global_step"))}
+
+    def get_gradients(self):
+        """Gradients of the last training step by variable name (model.gradients, linear_model.py:143-144)."""
+        return {n[:-len("/gradient")]: self.get_variable(n) for n in self._names if n.endswith("/gradient")}
+
+    def set_variables(self, values):
+        for n, v in values.items():
+            self.set_variable(n, v)
+
+    # tf.train.Saver stand-in (linear_model.py:151; predict_3dpose.py:158-186,328): one .npz keyed by TF names
+    def save(self, path):
+        np.savez(path, **{k.replace("/", "|"): v for k, v in self.get_variables(include_optimizer=True).items()})
+
+    def restore(self, path):
+        if not os.path.exists(path):
+            raise ValueError("Asked to load checkpoint {0}, but it does not seem to exist".format(path))
+        with np.load(path) as z:
+            for k in z.files:
+                self.set_variable(k.replace("|", "/"), z[k])
+
+    def _decayed_lr(self):
+        """tf.train.exponential_decay(lr, global_step, 100000, 0.96) (linear_model.py:86-90)."""
+        return np.float32(self._lr0) * np.float32(0.96) ** np.float32(int(self.global_step) / 100000.0)
+
+    # ------------------------------------------------------------------ distributed
+    def _attach_dist(self, dist):
+        torch = _lib.require_cuda()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world == 1:
+            return
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            check(lib.p3d_nccl_unique_id(_lib.np_ptr(ident)))
+        t = torch.from_numpy(ident).cuda(self.device) if dist.get_backend() == "nccl" else torch.from_numpy(ident)
+        dist.broadcast(t, src=0)
+        ident = t.cpu().numpy().copy()
+        # identical initial variables on every rank
+        for name in self._names:
+            if name == "global_step" or name.endswith("/gradient"):
+                continue
+            v = torch.from_numpy(np.asarray(self.get_variable(name), dtype=np.float32).copy())
+            if dist.get_backend() == "nccl":
+                v = v.cuda(self.device)
+            dist.broadcast(v, src=0)
+            self.set_variable(name, v.cpu().numpy())
+        check(lib.p3d_model_attach_nccl(self._handle, _lib.np_ptr(ident), self.rank, self.world))
+        self._dist = dist
+
+    # ------------------------------------------------------------------ step
+    def step(self, session, encoder_inputs, decoder_outputs, dropout_keep_prob, isTraining=True, *,
+             dropout_mask=None):
+        """Run a step of the model feeding the given inputs (linear_model.py:203-245).
+
+        Returns (loss, loss_summary, learning_rate_summary, outputs) when isTraining else
+        (loss, loss_summary, outputs).  NumPy in -> NumPy out; torch CUDA tensors in -> torch out."""
+        torch = _lib.require_cuda()
+        is_torch = hasattr(encoder_inputs, "is_cuda")
+        if is_torch:
+            x, t = encoder_inputs, decoder_outputs
+            if not (x.is_cuda and t.is_cuda and x.dtype == torch.float32 and t.dtype == torch.float32):
+                raise ValueError("torch inputs must be float32 CUDA tensors")
+            x, t = x.contiguous(), t.contiguous()
+        else:
+            x = np.ascontiguousarray(np.asarray(encoder_inputs, dtype=np.float32))   # the TF feed casts fp64 -> fp32
+            t = np.ascontiguousarray(np.asarray(decoder_outputs, dtype=np.float32))
+        if x.ndim != 2 or x.shape[1] != self.input_size:
+            raise ValueError("encoder_inputs must be [B,%d]" % self.input_size)
+        if t.ndim != 2 or t.shape[1] != self.output_size or t.shape[0] != x.shape[0]:
+            raise ValueError("decoder_outputs must be [B,%d]" % self.output_size)
+        B = int(x.shape[0])
+
+        if not isTraining:
+            if is_torch:
+                with torch.cuda.device(self.device):
+                    y = torch.empty((B, self.output_size), dtype=torch.float32, device=x.device)
+                    loss = torch.zeros((), dtype=torch.float32, device=x.device)
+                    st = _lib.current_stream()
+                    check(lib.p3d_model_forward(self._handle, x.data_ptr(), y.data_ptr(), B, st))
+                    if B:
+                        check(lib.p3d_model_mse(self._handle, y.data_ptr(), t.data_ptr(), B, loss.data_ptr(), st))
+                return loss, Summary("loss/loss", loss), y
+            y = np.empty((B, self.output_size), dtype=np.float32)
+            loss = C.c_float(0.0)
+            check(lib.p3d_model_step_eval_host(self._handle, _lib.np_ptr(x), _lib.np_ptr(t), _lib.np_ptr(y),
+                                               C.byref(loss), B))
+            return np.float32(loss.value), Summary("loss/loss", np.float32(loss.value)), y
+
+        # ---- training
+        keep = float(dropout_keep_prob)
+        with torch.cuda.device(self.device):
+            dev = torch.device("cuda", self.device)
+            xd = x if is_torch else torch.from_numpy(x).to(dev)
+            td = t if is_torch else torch.from_numpy(t).to(dev)
+            gB, row0 = B, 0
+            if self.world > 1:          # every rank is handed the global batch; it trains on its row block
+                lo, hi = shard_rows(B, self.rank, self.world)
+                xd, td, row0 = xd[lo:hi].contiguous(), td[lo:hi].contiguous(), lo
+            Bl = int(xd.shape[0])
+            y = torch.empty((Bl, self.output_size), dtype=torch.float32, device=dev)
+            scal = torch.zeros(2, dtype=torch.float32, device=dev)
+            mask_ptr = None
+            if dropout_mask is not None:      # tests inject the keep-mask: uint8 [nhidden][B][L]
+                md = torch.as_tensor(np.ascontiguousarray(dropout_mask, dtype=np.uint8)).to(dev)
+                if self.world > 1:
+                    md = md[:, row0:row0 + Bl].contiguous()
+                mask_ptr = md.data_ptr()
+            check(lib.p3d_model_train_step(self._handle, xd.data_ptr(), td.data_ptr(), Bl, keep,
+                                           C.c_uint64(self._seed & 0xFFFFFFFFFFFFFFFF), mask_ptr, gB, row0,
+                                           scal.data_ptr(), scal.data_ptr() + 4, y.data_ptr(), _lib.current_stream()))
+            if self.world > 1:
+                parts = [torch.empty((shard_rows(B, r, self.world)[1] - shard_rows(B, r, self.world)[0],
+                                      self.output_size), dtype=torch.float32, device=dev) for r in range(self.world)]
+                self._dist.all_gather(parts, y)
+                y = torch.cat(parts, 0)
+            if is_torch:
+                return scal[0], Summary("loss/loss", scal[0]), Summary("learning_rate/learning_rate", scal[1]), y
+            s = scal.cpu().numpy()
+            return (np.float32(s[0]), Summary("loss/loss", np.float32(s[0])),
+                    Summary("learning_rate/learning_rate", np.float32(s[1])), y.cpu().numpy())
+
+    # ------------------------------------------------------------------ batching (host side, linear_model.py:247-300)
+    def get_all_batches(self, data_x, data_y, camera_frame, training=True):
+        """Obtain a list of all the batches, randomly permuted when training (linear_model.py:247-300)."""
+        n = sum(v.shape[0] for v in data_x.values())
+        encoder_inputs = np.zeros((n, self.input_size), dtype=float)
+        decoder_outputs = np.zeros((n, self.output_size), dtype=float)
+        idx = 0
+        for key2d in data_x.keys():
+            (subj, b, fname) = key2d
+            key3d = key2d if camera_frame else (subj, b, "{0}.h5".format(fname.split(".")[0]))
+            key3d = (subj, b, fname[:-3]) if fname.endswith("-sh") and camera_frame else key3d
+            n2d = data_x[key2d].shape[0]
+            encoder_inputs[idx:idx + n2d, :] = data_x[key2d]
+            decoder_outputs[idx:idx + n2d, :] = data_y[key3d]
+            idx += n2d
+        if training:
+            perm = np.random.permutation(n)
+            encoder_inputs, decoder_outputs = encoder_inputs[perm, :], decoder_outputs[perm, :]
+        n_extra = n % self.batch_size
+        if n_extra > 0:
+            encoder_inputs, decoder_outputs = encoder_inputs[:-n_extra, :], decoder_outputs[:-n_extra, :]
+        n_batches = n // self.batch_size
+        return np.split(encoder_inputs, n_batches), np.split(decoder_outputs, n_batches)
+
+    def close(self):
+        if self._handle is not None:
+            lib.p3d_model_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,172 @@
+/* p3d.h - C ABI of libp3d.so: the B200 (sm_100a) implementation of 3d-pose-baseline's hot path.
+ *
+ * The reference (EsauPR/3d-pose-baseline) is pure Python: it has no FFI/plugin layer, every device
+ * op runs inside TensorFlow and every geometry op inside NumPy.  The drop-in boundary is therefore
+ * the reference's Python surface (mirrored in 3d-pose-baseline_b200/p3d/*.py); this header is the
+ * C ABI that mirror binds through ctypes.  Each entry cites the reference interface it replaces
+ * (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - every call returns 0 on success, <0 on error; p3d_last_error() gives a thread-local message.
+ *   - pointers are DEVICE pointers unless the name ends in _host.  The caller owns every buffer it
+ *     passes; the library keeps no caller pointer after return.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream unless they take/return host data.
+ *   - handles are not thread-safe; distinct handles may be used from distinct threads.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with P3D_ERR_CUDA.
+ */
+#ifndef P3D_H_
+#define P3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_OK 0
+#define P3D_ERR_ARG (-1)
+#define P3D_ERR_CUDA (-2)
+#define P3D_ERR_STATE (-3)
+#define P3D_ERR_NCCL (-4)
+
+#define P3D_MODE_BF16 0 /* tcgen05 bf16 x bf16 -> fp32 accumulate (headline path) */
+#define P3D_MODE_FP32 1 /* fp32 FFMA path, <=1e-4 relative to the fp64 oracle */
+
+const char* p3d_last_error(void);
+int p3d_version(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t p3d_launch_count(void);
+
+/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+int p3d_host_alloc(void** out_host, size_t bytes);
+int p3d_host_free(void* host);
+
+/* ---------------------------------------------------------------- LinearModel -----------------
+ * linear_model.LinearModel.__init__ (src/linear_model.py:34-151): same flags. */
+typedef struct p3d_model p3d_model;
+typedef struct {
+  int linear_size; /* src/linear_model.py:35 */
+  int num_layers;  /* :36 number of two_linear blocks */
+  int residual;    /* :37 */
+  int batch_norm;  /* :38 */
+  int max_norm;    /* :39 tf.clip_by_norm(w,1): whole-matrix Frobenius clip inside the graph */
+  int predict_14;  /* :43 output width 42 instead of 48 */
+  int mode;        /* P3D_MODE_* */
+  int device;      /* CUDA ordinal */
+  float learning_rate; /* :41 */
+} p3d_cfg;
+
+int p3d_model_create(const p3d_cfg* cfg, p3d_model** out);
+void p3d_model_destroy(p3d_model* m);
+
+/* Variables by their TensorFlow names (what tf.train.Saver stores, src/linear_model.py:151):
+ * "linear_model/w1", "linear_model/b1", "linear_model/batch_normalization/{gamma,beta,moving_mean,
+ * moving_variance}", "linear_model/two_linear_<i>/{w2_<i>,b2_<i>,batch_normalization1<i>/...,w3_<i>,
+ * b3_<i>,batch_normalization2<i>/...}", "linear_model/w4", "linear_model/b4"; optimizer state as
+ * "<var>/Adam" (m) and "<var>/Adam_1" (v); "global_step" (as float).  Weights are [in,out] row-major. */
+int p3d_model_set_param_host(p3d_model* m, const char* tf_name, const float* host, size_t n);
+int p3d_model_get_param_host(p3d_model* m, const char* tf_name, float* host, size_t n);
+int p3d_model_param_count(p3d_model* m);
+int p3d_model_param_name(p3d_model* m, int index, char* out, size_t cap, size_t* numel);
+
+/* Fold clip_by_norm + moving-statistics BN into per-layer W',b' and pack them for the forward
+ * kernels (src/linear_model.py:108-112,178-193,123).  Called lazily by forward if params changed. */
+int p3d_model_prepare_inference(p3d_model* m, void* stream);
+
+/* model.step(..., isTraining=False) forward (src/linear_model.py:237-245): y[B,out] = f(x[B,32]).
+ * x, y fp32 row-major on the device; any B >= 1. */
+int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* stream);
+/* mean((y-t)^2) over all B*out elements (src/linear_model.py:129); loss is a DEVICE float. */
+int p3d_model_mse(p3d_model* m, const float* y, const float* t, int64_t B, float* loss, void* stream);
+/* the same step with HOST buffers (what a NumPy caller of step() passes): chunked, pipelined
+ * H2D -> forward -> D2H inside.  x_host/t_host/y_host may be pageable or pinned.  t_host may be NULL
+ * (loss_host then receives 0).  Synchronous. */
+int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_host, float* y_host,
+                             float* loss_host, int64_t B);
+
+/* model.step(..., isTraining=True) (src/linear_model.py:226-235): forward with batch statistics and
+ * dropout, MSE, backward, BN moving-average update, TF-Adam with exponential lr decay; y receives the
+ * pre-update outputs, loss/lr_used are DEVICE floats.  mask_or_null: optional uint8 [nhidden][B][L]
+ * dropout keep-mask (1 = keep) injected for tests; otherwise a Philox4x32-10 mask is generated from
+ * (seed, global_step, layer, global_row0 + row, col).  global_B/row0 describe this rank's shard when
+ * data-parallel (global_B = B, row0 = 0 on one GPU). */
+int p3d_model_train_step(p3d_model* m, const float* x, const float* t, int64_t B, float keep_prob,
+                         uint64_t seed, const uint8_t* mask_or_null, int64_t global_B, int64_t row0,
+                         float* loss, float* lr_used, float* y, void* stream);
+/* Data parallel: a NCCL communicator owned by the library (SyncBN statistics + one gradient
+ * all-reduce per step).  id_host = 128-byte ncclUniqueId made by rank 0 and broadcast by the caller. */
+int p3d_nccl_unique_id(uint8_t* id_host /*[128]*/);
+int p3d_model_attach_nccl(p3d_model* m, const uint8_t* id_host, int rank, int world);
+int64_t p3d_model_global_step(p3d_model* m);
+
+/* ---------------------------------------------------------------- cameras ---------------------
+ * One H36M camera as loaded by cameras.load_camera_params (src/cameras.py:92-120). */
+typedef struct {
+  double R[9]; /* row-major 3x3 */
+  double T[3];
+  double f[2];
+  double c[2];
+  double k[3];
+  double p[2];
+} p3d_camera;
+
+/* cameras.project_point_radial (src/cameras.py:13-53).  P[npts,3] -> proj[npts,2], and optionally
+ * D, radial, tan, r2 [npts] (NULL = not wanted).  f64 variant = reference precision. */
+int p3d_project_point_radial_f64(const double* P, const p3d_camera* cam_host, double* proj, double* D,
+                                 double* radial, double* tan_, double* r2, int64_t npts, void* stream);
+int p3d_project_point_radial_f32(const float* P, const p3d_camera* cam_host, float* proj, float* D,
+                                 float* radial, float* tan_, float* r2, int64_t npts, void* stream);
+/* cameras.world_to_camera_frame / camera_to_world_frame (src/cameras.py:55-90) */
+int p3d_world_to_camera_f64(const double* P, const p3d_camera* cam_host, double* out, int64_t npts, void* stream);
+int p3d_camera_to_world_f64(const double* P, const p3d_camera* cam_host, double* out, int64_t npts, void* stream);
+
+/* Fused camera_frame preprocessing for ncams (<=8) cameras:
+ *   2D: data_utils.project_to_cameras (src/data_utils.py:339-364) + normalize_data (:260-280)
+ *   3D: transform_world_to_camera (:233-257) + postprocess_3d (:474-494) + normalize_data
+ * world[N,96] fp32 -> x2d[ncams,N,32] and/or y3d[ncams,N,48 or 42] fp32 (either may be NULL).
+ * mean/std are full-width (64 / 96) host vectors; the dims_to_use tables are built in. */
+int p3d_project_normalize(const float* world, const p3d_camera* cams_host, int ncams, const double* mean2d_host,
+                          const double* std2d_host, const double* mean3d_host, const double* std3d_host,
+                          int predict_14, float* x2d, float* y3d, int64_t N, void* stream);
+
+/* data_utils.normalize_data / unNormalizeData for one array (src/data_utils.py:260-311).
+ * dim = 2 or 3.  normalize: in[N,64|96] -> out[N,32|48|42];  unnormalize: the inverse, ignored
+ * dims come out as the mean.  f64 I/O like the reference (unnormalize rounds its input to fp32 first,
+ * as the reference does at :299-303). */
+int p3d_normalize_f64(const double* in, const double* mean_host, const double* std_host, int dim, int predict_14,
+                      double* out, int64_t N, void* stream);
+int p3d_unnormalize_f64(const double* in, const double* mean_host, const double* std_host, int dim, int predict_14,
+                        double* out, int64_t N, void* stream);
+
+/* data_utils.normalization_stats (src/data_utils.py:211-212): column mean and population std of
+ * data[N,D] (f64).  work = 2*D device doubles of scratch. */
+int p3d_column_stats_f64(const double* data, int64_t N, int D, double* mean, double* stdv, double* work, void* stream);
+/* data_utils.postprocess_3d (src/data_utils.py:474-494) for one array: out = in - tile(in[:, :3]);
+ * roots_or_null[N,3] receives the root positions.  Out of place. */
+int p3d_root_center_f64(const double* in, double* out, double* roots_or_null, int64_t N, int D, void* stream);
+
+/* ---------------------------------------------------------------- evaluation ------------------
+ * predict_3dpose.evaluate_batches arithmetic (src/predict_3dpose.py:399-442) + per-pose
+ * procrustes.compute_similarity_transform(gt, out, compute_optimal_scale=True) (src/procrustes.py:2-63).
+ * pred_n, gt_n: normalised [N,48|42] fp32.  dists_or_null[N,J] (J=17|14) per-joint errors in mm;
+ * joint_sum[J] DEVICE doubles are ACCUMULATED into (caller zeroes them), so that joint_err =
+ * joint_sum/N and total_err = sum(joint_sum)/(N*J). */
+int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* mean3d_host, const double* std3d_host,
+                         int predict_14, int use_procrustes, int64_t N, float* dists_or_null, double* joint_sum,
+                         void* stream);
+/* Batched procrustes.compute_similarity_transform on raw poses X,Y[N,J,3] f64 (J<=17):
+ * d[N], Z[N,J,3], T[N,9], b[N], c[N,3]; any output may be NULL. */
+int p3d_similarity_transform_f64(const double* X, const double* Y, int J, int compute_optimal_scale, int64_t N,
+                                 double* d, double* Z, double* T, double* b, double* c, void* stream);
+
+/* ---------------------------------------------------------------- debug / self-test -----------
+ * One-CTA tcgen05 GEMM: C[128,N] = A[128,K] * W[N,K]^T, A/W bf16 row-major (K contiguous),
+ * K % 64 == 0, N % 16 == 0, N <= 256.  Exercises TMA + UMMA descriptors + TMEM load in isolation. */
+int p3d_debug_umma_gemm(const void* A_bf16, const void* W_bf16, float* C, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_H_ */

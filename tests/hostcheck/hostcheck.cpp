@@ -1,0 +1,32 @@
+// TEST INFRASTRUCTURE: compiles the host/device math header of the CUDA kernels with g++ so that the
+// exact device arithmetic (projection, Kabsch/Jacobi rotation) can be checked against the oracle on a
+// machine without a GPU.  Never linked into the product.
+#include "../../3d-pose-baseline_b200/csrc/math_hd.h"
+
+extern "C" {
+
+void hc_kabsch(const double* A, double* T, double* tr, int n) {
+  for (int i = 0; i < n; ++i) p3d::kabsch_rotation(A + 9 * i, T + 9 * i, tr[i]);
+}
+
+// cam = R[9] T[3] f[2] c[2] k[3] p[2] ; out = u v D radial tan r2 per point
+void hc_project_f64(const double* P, const double* cam, double* out, int n) {
+  p3d::CamT<double> c;
+  for (int i = 0; i < 9; ++i) c.R[i] = cam[i];
+  for (int i = 0; i < 3; ++i) { c.Tr[i] = cam[9 + i]; c.k[i] = cam[16 + i]; }
+  for (int i = 0; i < 2; ++i) { c.f[i] = cam[12 + i]; c.c[i] = cam[14 + i]; c.p[i] = cam[19 + i]; }
+  for (int i = 0; i < n; ++i)
+    p3d::project_point(c, P[3 * i], P[3 * i + 1], P[3 * i + 2], out[6 * i], out[6 * i + 1], out[6 * i + 2], out[6 * i + 3],
+                       out[6 * i + 4], out[6 * i + 5]);
+}
+
+void hc_project_f32(const float* P, const double* cam, float* out, int n) {
+  p3d::CamT<float> c;
+  for (int i = 0; i < 9; ++i) c.R[i] = (float)cam[i];
+  for (int i = 0; i < 3; ++i) { c.Tr[i] = (float)cam[9 + i]; c.k[i] = (float)cam[16 + i]; }
+  for (int i = 0; i < 2; ++i) { c.f[i] = (float)cam[12 + i]; c.c[i] = (float)cam[14 + i]; c.p[i] = (float)cam[19 + i]; }
+  for (int i = 0; i < n; ++i)
+    p3d::project_point(c, P[3 * i], P[3 * i + 1], P[3 * i + 2], out[6 * i], out[6 * i + 1], out[6 * i + 2], out[6 * i + 3],
+                       out[6 * i + 4], out[6 * i + 5]);
+}
+}

@@ -1,0 +1,100 @@
+"""Parity of the Procrustes / MPJPE kernels with golden vectors from the reference
+(procrustes.compute_similarity_transform + the evaluate_batches arithmetic, tests/golden/procrustes.npz)
+and with the oracle.  Tolerance (north_star): Procrustes-aligned MPJPE within 1e-3 mm."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_ref as G
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def proc(golden_dir):
+    return np.load(os.path.join(golden_dir, "procrustes.npz"))
+
+
+def test_similarity_transform_golden(proc):
+    from p3d import procrustes
+    X, Y = proc["X"], proc["Y"]
+    d, Z, T, b, c = procrustes.compute_similarity_transform(X, Y, compute_optimal_scale=True)
+    np.testing.assert_allclose(d, proc["proc_d"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(Z, proc["proc_Z"], rtol=1e-8, atol=1e-7)
+    np.testing.assert_allclose(T, proc["proc_T"], atol=1e-9)
+    np.testing.assert_allclose(b, proc["proc_b"], rtol=1e-9)
+    np.testing.assert_allclose(c, proc["proc_c"], rtol=1e-8, atol=1e-7)
+    d, Z, T, b, c = procrustes.compute_similarity_transform(X, Y, compute_optimal_scale=False)
+    np.testing.assert_allclose(d, proc["ns_d"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(Z, proc["ns_Z"], rtol=1e-8, atol=1e-7)
+    np.testing.assert_allclose(c, proc["ns_c"], rtol=1e-8, atol=1e-7)
+    # the reference's single-pose call form (predict_3dpose.py:418)
+    d1, Z1, T1, b1, c1 = procrustes.compute_similarity_transform(X[5], Y[5], compute_optimal_scale=True)
+    assert Z1.shape == (17, 3) and T1.shape == (3, 3) and isinstance(b1, float)
+    np.testing.assert_allclose(T1, proc["proc_T"][5], atol=1e-9)      # the reflected pose
+    assert abs(np.linalg.det(T1) - 1) < 1e-9
+
+
+def test_mpjpe_golden(proc):
+    from p3d import evaluate
+    args = (proc["pred_n"], proc["gt_n"].astype(np.float32), proc["mean3d"], proc["std3d"])
+    # the golden ground truth is float64-normalised; the kernel reads fp32: re-derive the reference on the fp32 copy
+    use, ign = proc["use3d"], proc["ignore3d"]
+    gt32 = proc["gt_n"].astype(np.float32)
+    for use_proc in (False, True):
+        ref = G.mpjpe(proc["pred_n"], gt32, proc["mean3d"], proc["std3d"], ign, use, procrustes=use_proc)
+        tot, joint, dists = evaluate.mpjpe(*args, procrustes=use_proc, return_dists=True)
+        np.testing.assert_allclose(dists.cpu().numpy(), ref, atol=1e-3)
+        assert abs(tot - ref.mean()) < 1e-3 and np.abs(joint - ref.mean(0)).max() < 1e-3
+        # against the reference-generated golden distances (gt normalised in fp64 there): same bound
+        gold = proc["dists_procrustes"] if use_proc else proc["dists_plain"]
+        assert np.abs(dists.cpu().numpy() - gold).max() < 2e-3
+        assert abs(tot - gold.mean()) < 1e-3
+
+
+def test_mpjpe_large_against_oracle_and_predict_14():
+    from p3d import evaluate
+    N = 20011                                     # ragged last block (128 poses per block)
+    gt96, pr96 = synth.eval_pairs(N, seed=21)
+    rng = np.random.RandomState(2)
+    mean = rng.normal(0, 50, 96); mean[:3] = 0
+    std = rng.uniform(50, 200, 96)
+    for p14 in (False, True):
+        use, ign = G.dims_to_use(3, p14)
+        gt_n = ((gt96[:, use] - mean[use]) / std[use]).astype(np.float32)
+        pr_n = ((pr96[:, use] - mean[use]) / std[use]).astype(np.float32)
+        for use_proc in (True, False):
+            ref = G.mpjpe(pr_n, gt_n, mean, std, ign, use, procrustes=use_proc, predict_14=p14)
+            tot, joint, dists = evaluate.mpjpe(torch.from_numpy(pr_n).cuda(), torch.from_numpy(gt_n).cuda(), mean, std,
+                                               procrustes=use_proc, predict_14=p14, return_dists=True)
+            assert np.abs(dists.cpu().numpy() - ref).max() < 1e-3
+            assert abs(tot - ref.mean()) < 1e-3 and np.abs(joint - ref.mean(0)).max() < 1e-3
+
+
+def test_procrustes_properties_at_full_size():
+    """2^20 poses x 4 cameras is out of the oracle's reach: use invariances instead.
+    (i) a similarity-transformed copy of the ground truth aligns to ~0 error;
+    (ii) the aligned error is invariant to a similarity transform of the prediction;
+    (iii) aligned error <= unaligned error."""
+    from p3d import evaluate
+    N = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(1)
+    gt = torch.randn((N, 48), device="cuda", generator=g)
+    pred = gt + 0.2 * torch.randn((N, 48), device="cuda", generator=g)
+    mean = np.zeros(96); std = np.full(96, 100.0)
+    tot_a, joint_a = evaluate.mpjpe(pred, gt, mean, std, procrustes=True)
+    tot_u, _ = evaluate.mpjpe(pred, gt, mean, std, procrustes=False)
+    assert tot_a <= tot_u and np.isfinite(tot_a) and joint_a.shape == (17,)
+    # rotate + scale + translate every pose (incl. the implicit hip at 0 -> translation moves it: use
+    # rotation + scale about the hip only, the hip being part of the 17-joint error)
+    th = 0.7
+    R = torch.tensor([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], device="cuda", dtype=torch.float32)
+    pred_t = (1.3 * pred.view(N, 16, 3) @ R).reshape(N, 48).contiguous()
+    tot_t, joint_t = evaluate.mpjpe(pred_t, gt, mean, std, procrustes=True)
+    assert abs(tot_t - tot_a) < 1e-3 and np.abs(joint_t - joint_a).max() < 2e-3
+    gt_t = (0.8 * gt.view(N, 16, 3) @ R).reshape(N, 48).contiguous()
+    tot_0, _ = evaluate.mpjpe(gt_t, gt, mean, std, procrustes=True)
+    assert tot_0 < 1e-3

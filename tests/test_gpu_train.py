@@ -1,0 +1,169 @@
+"""Parity of the CUDA training step (model.step(isTraining=True), src/linear_model.py:129-145,203-235)
+with the fp64 oracle: forward with batch statistics + dropout, loss, gradients through clip_by_norm /
+BN / ReLU / dropout / residual, BN moving averages, TF-Adam + lr decay.
+
+The kernels compute in fp32: after a few steps the variables agree with the fp64 oracle to ~1e-4
+relative to each tensor's scale (Adam's m/sqrt(v) normalisation amplifies fp32 rounding of tiny
+gradients, so biases that feed a BatchNorm - whose true gradient is exactly 0, SURVEY appendix A.4 -
+are pinned to "do not move at all")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlp_ref as M
+from oracle import synth
+from helpers import make_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol, name):
+    scale = max(np.abs(b).max(), 1e-6)
+    err = np.abs(np.asarray(a, np.float64) - b).max()
+    assert err <= rtol * scale, (name, err, scale)
+
+
+CFGS = [M.Config(1024, 2, True, True, True), M.Config(256, 2, True, True, False), M.Config(128, 1, False, True, True),
+        M.Config(64, 2, True, False, False), M.Config(128, 0, True, True, True)]
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=lambda c: f"L{c.linear_size}n{c.num_layers}r{int(c.residual)}b{int(c.batch_norm)}m{int(c.max_norm)}")
+def test_train_steps_match_oracle_with_injected_masks(cfg):
+    B, keep, lr0, steps = 64, 0.5, 1e-3, 3
+    m, p = make_model(cfg, seed=21, bn="fresh", mode="fp32", lr=lr0)
+    st = M.AdamState()
+    nh = 2 * cfg.num_layers + 1
+    rng = np.random.RandomState(0)
+    for s in range(steps):
+        x, t = synth.mlp_inputs(B, seed=50 + s)
+        masks = (rng.uniform(size=(nh, B, cfg.linear_size)) < keep).astype(np.uint8)
+        loss, _, lr_sum, y = m.step(None, x, t, keep, isTraining=True, dropout_mask=masks)
+        rloss, rlr, ry = M.train_step(p, st, x.astype(np.float64), t.astype(np.float64), cfg, lr0, keep_prob=keep,
+                                      masks=list(masks))
+        assert abs(float(loss) - rloss) <= 2e-4 * max(1.0, rloss), (s, float(loss), rloss)
+        assert abs(float(lr_sum.value) - rlr) <= 1e-6 * rlr
+        _close(y, ry, 2e-4, f"outputs step {s}")
+    assert int(m.global_step) == steps
+    got = m.get_variables(include_optimizer=True)
+    for name in M.trainable_names(cfg.linear_size, cfg.num_layers, cfg.batch_norm):
+        leaf = name.rsplit("/", 1)[-1]
+        if cfg.batch_norm and leaf[0] == "b" and leaf != "b4" and "batch_normalization" not in name:
+            # bias feeding a BN layer: zero gradient, Adam must leave it bit-identical
+            assert np.array_equal(got[name], p[name].astype(np.float32)), name
+            continue
+        # Every element moved by ~lr per step.  Adam's m/(sqrt(v)+eps) turns fp32 rounding of near-zero
+        # gradients into O(lr) differences on a few elements, so: 99.5% of the elements within 2% of
+        # the total movement, and nothing further off than the movement itself.
+        err = np.abs(got[name].astype(np.float64) - p[name])
+        move = lr0 * steps
+        assert np.quantile(err, 0.995) <= 0.02 * move + 1e-6 * np.abs(p[name]).max(), (name, np.quantile(err, 0.995))
+        assert err.max() <= 2.2 * move, (name, err.max())
+    if cfg.batch_norm:
+        for name in p:
+            if name.endswith(("moving_mean", "moving_variance")):
+                _close(got[name], p[name], 1e-4, name)
+    m.close()
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=lambda c: f"L{c.linear_size}n{c.num_layers}r{int(c.residual)}b{int(c.batch_norm)}m{int(c.max_norm)}")
+def test_gradients_match_oracle(cfg):
+    """model.gradients (linear_model.py:143-144) after one step == the oracle's backward pass at the
+    pre-update variables: 2e-4 of each tensor's largest gradient."""
+    B, keep = 64, 0.5
+    m, p = make_model(cfg, seed=31, bn="trained", mode="fp32", lr=1e-3)
+    nh = 2 * cfg.num_layers + 1
+    x, t = synth.mlp_inputs(B, seed=77)
+    masks = (np.random.RandomState(4).uniform(size=(nh, B, cfg.linear_size)) < keep).astype(np.uint8)
+    m.step(None, x, t, keep, isTraining=True, dropout_mask=masks)
+    got = m.get_gradients()
+    y, cache = M.forward(p, x.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True)
+    grads = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cache, y)
+    for name, g in grads.items():
+        scale = np.abs(g).max()
+        if scale < 1e-12:                 # biases in front of a BN layer: exactly zero
+            assert np.abs(got[name]).max() == 0.0, name
+            continue
+        assert np.abs(got[name].astype(np.float64) - g).max() <= 2e-4 * scale, (name, np.abs(got[name] - g).max(), scale)
+    m.close()
+
+
+def test_gradients_via_single_step_sgd_like_probe():
+    """One step from zero Adam state moves every variable by -alpha*sign(g) (|m|/sqrt(v) = 1 up to eps):
+    the sign pattern of the update must equal the sign of the oracle gradient wherever |g| is not tiny."""
+    cfg = M.Config(256, 1, True, True, True)
+    m, p = make_model(cfg, seed=5, bn="fresh", mode="fp32", lr=1e-3)
+    x, t = synth.mlp_inputs(64, seed=3)
+    before = m.get_variables()
+    m.step(None, x, t, 1.0, isTraining=True)
+    after = m.get_variables()
+    y, cache = M.forward(p, x.astype(np.float64), cfg, training=True, want_cache=True)
+    grads = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cache, y)
+    for name in ("linear_model/w1", "linear_model/two_linear_0/w2_0", "linear_model/w4", "linear_model/b4",
+                 "linear_model/batch_normalization/gamma", "linear_model/two_linear_0/batch_normalization20/beta"):
+        g = grads[name]
+        big = np.abs(g) > 1e-3 * np.abs(g).max()
+        delta = after[name].astype(np.float64) - before[name]
+        assert np.array_equal(np.sign(delta[big]), -np.sign(g[big])), name
+        assert np.allclose(np.abs(delta[big]), 1e-3, rtol=2e-2), name
+    m.close()
+
+
+def test_generated_dropout_mask_is_the_documented_philox_stream():
+    """Without an injected mask the kernel draws floor(keep + u) from Philox4x32-10 keyed by
+    (seed; global_row, col/4, layer, global_step): the oracle generates the same mask, so a full
+    training step must agree; and the step is reproducible for a fixed seed."""
+    cfg = M.Config(128, 1, True, True, False)
+    B, keep = 32, 0.5
+    x, t = synth.mlp_inputs(B, seed=8)
+    outs = []
+    for _ in range(2):
+        m, p = make_model(cfg, seed=77, bn="fresh", mode="fp32", lr=1e-3)
+        loss, _, _, y = m.step(None, x, t, keep, isTraining=True)
+        outs.append((float(loss), y))
+        seed = m._seed
+        m.close()
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+    masks = [M.dropout_mask_philox(seed, 0, li, B, cfg.linear_size, keep) for li in range(3)]
+    st = M.AdamState()
+    rloss, _, ry = M.train_step(p, st, x.astype(np.float64), t.astype(np.float64), cfg, 1e-3, keep_prob=keep, masks=masks)
+    assert abs(outs[0][0] - rloss) <= 2e-4 * max(1.0, rloss)
+    _close(outs[0][1], ry, 2e-4, "outputs")
+    frac = np.mean([mk.mean() for mk in masks])
+    assert 0.45 < frac < 0.55
+
+
+def test_training_reduces_loss_and_inference_uses_moving_stats():
+    cfg = M.Config(1024, 2, True, True, True)
+    m, _ = make_model(cfg, seed=9, bn="fresh", mode="bf16", lr=1e-3)
+    rng = np.random.RandomState(0)
+    W = rng.standard_normal((32, 48)).astype(np.float32) * 0.3
+    x = rng.standard_normal((4096, 32)).astype(np.float32)
+    t = x @ W
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda()
+    first = None
+    for it in range(60):
+        idx = torch.randint(0, 4096, (256,), device="cuda")
+        loss, _, _, _ = m.step(None, xd[idx], td[idx], 0.9, isTraining=True)
+        first = first if first is not None else float(loss)
+    assert float(loss) < 0.5 * first
+    # eval path works right after training (weights re-folded with the updated moving statistics)
+    l_eval, _, y = m.step(None, xd, td, 1.0, isTraining=False)
+    assert torch.isfinite(y).all() and float(l_eval) < first
+    m.close()
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    cfg = M.Config(128, 1, True, True, True)
+    m, _ = make_model(cfg, seed=1, bn="fresh", mode="fp32")
+    x, t = synth.mlp_inputs(64, seed=1)
+    m.step(None, x, t, 0.8, isTraining=True)
+    path = str(tmp_path / "checkpoint-1.npz")
+    m.save(path)
+    _, _, y_a = m.step(None, x, t, 1.0, isTraining=False)
+    m2, _ = make_model(cfg, seed=99, bn="fresh", mode="fp32")
+    m2.restore(path)
+    _, _, y_b = m2.step(None, x, t, 1.0, isTraining=False)
+    assert np.array_equal(y_a, y_b) and int(m2.global_step) == 1
+    with pytest.raises(ValueError):
+        m2.restore(str(tmp_path / "checkpoint-2.npz"))
+    m.close(); m2.close()
