@@ -69,6 +69,32 @@ int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cuda
   return P3D_OK;
 }
 
+namespace prof {
+static bool g_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pending;
+static double g_ms = 0.0;
+static long long g_n = 0;
+bool enabled() { return g_on; }
+void begin(cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if (cudaEventCreate(e0) != cudaSuccess || cudaEventCreate(e1) != cudaSuccess) { *e0 = *e1 = nullptr; return; }
+  cudaEventRecord(*e0, st);
+}
+void end(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaEventRecord(e1, st);
+  g_pending.emplace_back(e0, e1);
+}
+static void drain() {
+  for (auto& pr : g_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      g_ms += ms; g_n += 1;
+    }
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  g_pending.clear();
+}
+}  // namespace prof
+
 static NamedParam* find_param(p3d_model* m, const char* name) {
   for (auto& p : m->params)
     if (p.name == name) return &p;
@@ -84,6 +110,19 @@ extern "C" {
 const char* p3d_last_error(void) { return g_err; }
 int p3d_version(void) { return 100; }
 int64_t p3d_launch_count(void) { return launch_counter()->load(); }
+
+int p3d_profile_enable(int on) {
+  prof::drain();
+  prof::g_on = on != 0;
+  prof::g_ms = 0.0; prof::g_n = 0;
+  return P3D_OK;
+}
+int p3d_profile_read(double* ms_total, int64_t* launches) {
+  prof::drain();
+  if (ms_total) *ms_total = prof::g_ms;
+  if (launches) *launches = prof::g_n;
+  return P3D_OK;
+}
 
 int p3d_host_alloc(void** out, size_t bytes) {
   P3D_REQUIRE(out, "host_alloc: null out");

@@ -93,6 +93,14 @@ struct TrainWorkspace {
   float* scal = nullptr;    // small device scalars: loss, lr, clip dots...
 };
 
+// Optional per-launch CUDA-event timing of the dominant kernel (bench.py's roofline figure):
+// events are recorded on the launching stream right around the kernel.
+namespace prof {
+bool enabled();
+void begin(cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1);
+void end(cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
+}  // namespace prof
+
 namespace simt {
 struct Epilogue {
   const float* bias = nullptr;        // [N] added to every row

@@ -347,8 +347,11 @@ int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cud
     P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (prof::enabled()) prof::begin(st, &e0, &e1);
   mlp_forward_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_x, tm_act, tm_w, tm_wout, p);
   P3D_LAUNCH_CHECK();
+  if (e0) prof::end(st, e0, e1);
   return P3D_OK;
 }
 

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "p3d_last_error": (c_char_p, []),
     "p3d_version": (c_int, []),
     "p3d_launch_count": (c_int64, []),
+    "p3d_profile_enable": (c_int, [c_int]),
+    "p3d_profile_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_int64)]),
     "p3d_host_alloc": (c_int, [C.POINTER(c_void_p), c_size_t]),
     "p3d_host_free": (c_int, [c_void_p]),
     "p3d_model_create": (c_int, [C.POINTER(Cfg), C.POINTER(c_void_p)]),

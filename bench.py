@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 hot path (BASELINE.json: "poses/sec (fused MLP inference,
+bf16) at 1/2/4/8 B200; batch-1 p50 latency").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mlp|preprocess|eval|train]
+
+One "step" = one pass of LinearModel(1024, 2, residual, batch_norm, max_norm) inference over one
+batch of 2^20 synthetic poses per GPU (configs[1]).  N > 1 is launched by torch.distributed.run, one
+process per GPU; the pose batch is sharded by rows (weak scaling: 2^20 poses per GPU), there is no
+data-path collective, timing is CUDA events, max over ranks.  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's own CPU implementation of the path.  TensorFlow is not
+installable here (no network), so this is the NumPy restatement of linear_model.py's graph
+(oracle/mlp_ref.py, "port"), fp32, all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "3d-pose-baseline_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "poses/sec (fused MLP inference, bf16)"
+UNIT = "poses/s"
+L, NL, IN, OUT = 1024, 2, 32, 48
+FLOP_PER_POSE = 2 * (IN * L + 2 * NL * L * L + L * OUT)       # 8,552,448
+B_PER_GPU = 1 << 20
+WORKLOAD = "LinearModel(linear_size=1024,num_layers=2,residual,batch_norm,max_norm) inference, batch 2^20 poses/GPU"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.stop_flag = [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_port_rate(sample, threads, repeats=1):
+    """poses/s of the CPU restatement of the reference graph (fp32, op by op like the TF graph)."""
+    from oracle import mlp_ref as M
+    from oracle import synth
+    cfg = M.Config(L, NL, True, True, True)
+    p = {k: v.astype(np.float32) for k, v in M.init_params(L, NL, seed=1, bn="trained").items()}
+    x, _ = synth.mlp_inputs(sample, seed=0)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        y = M.forward(p, x, cfg, training=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert y.dtype == np.float32 and np.isfinite(y).all()
+    return sample / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    rate0, _ = cpu_port_rate(4096, threads)
+    # size the per-step sample so that the whole run stays within ~2 minutes
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    sample = int(min(B_PER_GPU, max(4096, (rate0 * budget) // 4096 * 4096)))
+    from oracle import mlp_ref as M
+    from oracle import synth
+    cfg = M.Config(L, NL, True, True, True)
+    p = {k: v.astype(np.float32) for k, v in M.init_params(L, NL, seed=1, bn="trained").items()}
+    x, _ = synth.mlp_inputs(sample, seed=0)
+    for _ in range(args.warmup):
+        M.forward(p, x, cfg, training=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        M.forward(p, x, cfg, training=False)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "TensorFlow not installable (no network): NumPy restatement of the "
+                   "reference graph (oracle/mlp_ref.py) on the host cores; each step = a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} poses per step (of 2^20), fp32, NumPy/BLAS with {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def pinned_array(lib, shape, dtype=np.float32):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    rc = lib.p3d_host_alloc(C.byref(ptr), max(n, 16))
+    if rc != 0:
+        raise RuntimeError("p3d_host_alloc failed")
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_byte)), shape=(max(n, 16),))[:n].view(dtype).reshape(shape)
+    return arr, ptr
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: libp3d has no CPU fallback"}))
+        return 2
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from p3d import LinearModel, _lib
+    lib = _lib.lib
+    peaks = load_peaks()
+
+    # random-init weights (the model's own kaiming init) + non-trivial BN statistics so that the folding is real
+    model = LinearModel(L, NL, True, True, True, 64, 1e-3, mode="bf16", device=local_rank, seed=1)
+    rng = np.random.RandomState(2)
+    for name, shape in model.variable_shapes().items():
+        leaf = name.rsplit("/", 1)[-1]
+        if "Adam" in name or name.endswith("/gradient"):
+            continue
+        if leaf == "gamma":
+            model.set_variable(name, rng.uniform(0.5, 1.5, shape))
+        elif leaf == "beta":
+            model.set_variable(name, rng.normal(0, 0.1, shape))
+        elif leaf == "moving_mean":
+            model.set_variable(name, rng.normal(0, 0.5, shape))
+        elif leaf == "moving_variance":
+            model.set_variable(name, rng.uniform(0.5, 2.0, shape))
+
+    B = B_PER_GPU
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn((B, IN), device=dev, generator=g)
+    t = torch.zeros((B, OUT), device=dev)
+    y = torch.empty((B, OUT), device=dev)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        _lib.check(lib.p3d_model_forward(model._handle, x.data_ptr(), y.data_ptr(), B, sptr))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    # ---- device-resident timing (value): K steps between two events, max over ranks
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    lib.p3d_profile_enable(1)
+    launches0 = lib.p3d_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = int(lib.p3d_launch_count() - launches0)
+    kms, kn = C.c_double(), C.c_int64()
+    lib.p3d_profile_read(C.byref(kms), C.byref(kn))
+    lib.p3d_profile_enable(0)
+    clocks = sampler.summary() if sampler else None
+    el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end: model.step() with pinned HOST buffers, H2D of x and decoder_outputs + D2H of y inside
+    xh, xh_ptr = pinned_array(lib, (B, IN))
+    th, th_ptr = pinned_array(lib, (B, OUT))
+    xh[:] = x.cpu().numpy()
+    th[:] = 0.0
+    e2e_steps = max(2, min(args.steps, 5))
+    model.step(None, xh, th, 1.0, isTraining=False)           # warm (allocates the pipeline buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        loss, _, yh = model.step(None, xh, th, 1.0, isTraining=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2 = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(e2.item())
+    ok = bool(np.isfinite(yh[:1024]).all()) and bool(np.allclose(yh[:4096], y[:4096].cpu().numpy(), atol=1e-5))
+
+    # ---- batch-1 latency (p50) of the same model: CUDA events per call + host wall clock
+    lat = None
+    if rank == 0:
+        x1, t1 = x[:1].contiguous(), t[:1].contiguous()
+        y1 = torch.empty((1, OUT), device=dev)
+        for _ in range(200):
+            _lib.check(lib.p3d_model_forward(model._handle, x1.data_ptr(), y1.data_ptr(), 1, sptr))
+        torch.cuda.synchronize()
+        ev, wall = [], []
+        for _ in range(2000):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            a.record(stream)
+            _lib.check(lib.p3d_model_forward(model._handle, x1.data_ptr(), y1.data_ptr(), 1, sptr))
+            b.record(stream)
+            b.synchronize()
+            wall.append((time.perf_counter() - w0) * 1e6)
+            ev.append(a.elapsed_time(b) * 1e3)
+        lat = {"p50_us_device": statistics.median(ev), "p50_us_wall": statistics.median(wall),
+               "p99_us_wall": sorted(wall)[int(0.99 * len(wall))], "iters": 2000}
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r0, _ = cpu_port_rate(4096, threads)
+        sample = int(min(B, max(4096, (r0 * 15.0) // 4096 * 4096)))          # ~15 s of CPU work
+        rate, secs = cpu_port_rate(sample, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} of 2^20 poses, fp32 NumPy restatement of the TF graph, {secs:.1f} s"}
+
+    if rank == 0:
+        k_ms = kms.value / max(1, kn.value)
+        achieved = B * FLOP_PER_POSE / (k_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "sharding": f"rows, {world} x 2^20, no collective",
+                       "l2": "x (134 MB) + y (201 MB) per step exceed the 126 MB L2; no flush needed",
+                       "weights": "random init (kaiming), BN statistics non-trivial and folded"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                         "peak_source": peaks["source"] + " burst bf16 (MEASURED_PEAKS.json)",
+                         "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
+                         "kernel": "mlp_forward_tc_kernel", "kernel_ms": k_ms, "kernel_launches": int(kn.value),
+                         "flop_per_launch": B * FLOP_PER_POSE},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (IN + OUT) * 4,
+                    "d2h_bytes_per_step": B * OUT * 4 + 4, "steps": e2e_steps, "outputs_match_device_path": ok,
+                    "api": "LinearModel.step(None, x_pinned, dec_out_pinned, 1.0, isTraining=False)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "latency_batch1": lat,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    lib.p3d_host_free(xh_ptr)
+    lib.p3d_host_free(th_ptr)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -39,6 +39,12 @@ int p3d_version(void);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t p3d_launch_count(void);
 
+/* Per-launch CUDA-event timing of the dominant kernel (the fused tcgen05 forward), recorded on the
+ * launching stream.  enable(1) resets the counters; read() waits for the recorded events and returns
+ * the summed device time and the number of launches since enable. */
+int p3d_profile_enable(int on);
+int p3d_profile_read(double* ms_total, int64_t* launches);
+
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 int p3d_host_alloc(void** out_host, size_t bytes);
 int p3d_host_free(void* host);

@@ -104,7 +104,9 @@ def test_gradients_via_single_step_sgd_like_probe():
         big = np.abs(g) > 1e-3 * np.abs(g).max()
         delta = after[name].astype(np.float64) - before[name]
         assert np.array_equal(np.sign(delta[big]), -np.sign(g[big])), name
-        assert np.allclose(np.abs(delta[big]), 1e-3, rtol=2e-2), name
+        alpha = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+        expect = -alpha * 0.1 * g / (np.sqrt(0.001 * g * g) + 1e-8)         # TF-Adam, first step, eps included
+        assert np.allclose(delta[big], expect[big], rtol=2e-2, atol=2e-6), name
     m.close()
 
 
