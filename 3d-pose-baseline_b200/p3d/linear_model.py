@@ -213,11 +213,13 @@ class LinearModel(object):
 
     # ------------------------------------------------------------------ step
     def step(self, session, encoder_inputs, decoder_outputs, dropout_keep_prob, isTraining=True, *,
-             dropout_mask=None):
+             dropout_mask=None, out=None):
         """Run a step of the model feeding the given inputs (linear_model.py:203-245).
 
         Returns (loss, loss_summary, learning_rate_summary, outputs) when isTraining else
-        (loss, loss_summary, outputs).  NumPy in -> NumPy out; torch CUDA tensors in -> torch out."""
+        (loss, loss_summary, outputs).  NumPy in -> NumPy out; torch CUDA tensors in -> torch out.
+        `out`: optional preallocated fp32 [B,out] NumPy array for the evaluation outputs (e.g. pinned
+        memory from p3d_host_alloc, which lets the device->host copy overlap the compute)."""
         torch = _lib.require_cuda()
         is_torch = hasattr(encoder_inputs, "is_cuda")
         if is_torch:
@@ -244,7 +246,12 @@ class LinearModel(object):
                     if B:
                         check(lib.p3d_model_mse(self._handle, y.data_ptr(), t.data_ptr(), B, loss.data_ptr(), st))
                 return loss, Summary("loss/loss", loss), y
-            y = np.empty((B, self.output_size), dtype=np.float32)
+            if out is not None:
+                if out.shape != (B, self.output_size) or out.dtype != np.float32 or not out.flags.c_contiguous:
+                    raise ValueError("out must be a C-contiguous float32 [B,%d] array" % self.output_size)
+                y = out
+            else:
+                y = np.empty((B, self.output_size), dtype=np.float32)
             loss = C.c_float(0.0)
             check(lib.p3d_model_step_eval_host(self._handle, _lib.np_ptr(x), _lib.np_ptr(t), _lib.np_ptr(y),
                                                C.byref(loss), B))

@@ -19,14 +19,20 @@ from helpers import bf16_round, emulate_bf16_forward, make_model, rowwise_rel
 pytestmark = pytest.mark.gpu
 
 
-def assert_matches_emulation(y, emu, rms):
+def assert_matches_emulation(y, emu, rms, ref=None):
     """The kernel and the emulation round at the same points but accumulate in different precision, so
-    an activation sitting on a bf16 rounding boundary can flip by one bf16 ulp (0.4 % of ITS value) and
-    move a few outputs by ~1e-2 rms.  Hence: 99 % of the outputs within 2e-3 rms, none beyond 3e-2 rms.
-    A wrong tile / column / residual gives O(1) errors on whole rows and fails both."""
+    an activation sitting on a bf16 rounding boundary can flip by one bf16 ulp (0.4 % of ITS value); the
+    flips compound over the layers into a heavy tail while the MEDIAN difference stays ~1e-6 rms
+    (measured on B200: tools/diag_mlp.py).  A wrong tile / column / residual / dropped K slice shifts
+    the median by O(1e-2) and fails.  With `ref` (fp64 oracle) the kernel must also be as accurate as
+    the emulation is."""
     err = np.abs(np.asarray(y, np.float64) - emu)
-    assert np.quantile(err, 0.99) <= 2e-3 * rms + 1e-5, (np.quantile(err, 0.99), rms)
-    assert err.max() <= 3e-2 * rms + 1e-5, (err.max(), rms)
+    assert np.median(err) <= 1e-3 * rms + 1e-6, (np.median(err), rms)
+    assert np.quantile(err, 0.99) <= 2e-2 * rms + 1e-5, (np.quantile(err, 0.99), rms)
+    if ref is not None:
+        ek, ee = np.abs(np.asarray(y, np.float64) - ref), np.abs(emu - ref)
+        for qv in (0.5, 0.9, 0.99):
+            assert np.quantile(ek, qv) <= 1.25 * np.quantile(ee, qv) + 1e-5 * rms, (qv, np.quantile(ek, qv), np.quantile(ee, qv))
 
 
 def _bf16_bits(a):
@@ -72,7 +78,7 @@ def test_bf16_forward_matches_oracle(cfg, B):
     emu = emulate_bf16_forward(p, x, cfg)
     assert y.shape == (B, 48) and y.dtype == np.float32
     rms = np.sqrt(np.mean(ref ** 2))
-    assert_matches_emulation(y, emu, rms)
+    assert_matches_emulation(y, emu, rms, ref)
     rel = rowwise_rel(y, ref)
     assert rel.max() <= 1e-2, rel.max()
     assert abs(float(loss) - M.loss_fn(y.astype(np.float64), t.astype(np.float64))) <= 1e-4 * max(1.0, float(loss))
@@ -90,7 +96,7 @@ def test_bf16_forward_ragged_batches(B):
     ref = M.forward(p, x.astype(np.float64), cfg, training=False)
     emu = emulate_bf16_forward(p, x, cfg, small_batch=(B <= 16))
     rms = np.sqrt(np.mean(ref ** 2))
-    assert_matches_emulation(y, emu, rms)
+    assert_matches_emulation(y, emu, rms, ref)
     assert rowwise_rel(y, ref).max() <= 1e-2
     m.close()
 
