@@ -6,15 +6,19 @@
 // stage is  h' = relu(h W' + b') (+ residual)  and the last one  y = h W' + b'.
 //
 // One persistent CTA per SM walks 128-pose row tiles through ALL layers:
-//   warp 0 (1 thread)  TMA producer : A tile [128 x 64] bf16 of the current activations and the
-//                                     matching W' tile [256 x 64] into a 4-stage smem ring (SW128)
-//   warp 1 (1 thread)  MMA issuer   : tcgen05.mma 128x256x16, fp32 accumulators in TMEM
-//                                     (2 x 256 columns, double buffered against the epilogue)
-//   warp 2             TMEM allocator
-//   warps 4-7          epilogue     : tcgen05.ld -> +bias -> ReLU -> (+residual) -> bf16 -> the
-//                                     CTA's private activation tile (L2 resident), or fp32 y
-// The activation tile of a CTA (2 x [128 x L] bf16) lives in a per-CTA global scratch that never
-// leaves L2; only x (128 B/pose) and y (192 B/pose) are compulsory HBM traffic.
+//   warp 0   TMA producer : A tile [128 x 64] bf16 of the current activations and the matching
+//                           W' tile [256 x 64] into a 4-stage smem ring (128B swizzle)
+//   warp 1   MMA issuer   : tcgen05.mma 128x256x16 (one elected lane, warp-uniform operands), fp32
+//                           accumulators in TMEM, 2 x 256 columns double buffered against the epilogue
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue    : tcgen05.ld -> +bias -> ReLU -> bf16 -> swizzled smem tile -> TMA store
+//                           (cp.reduce.async.bulk .add when the block's residual is added: the L2
+//                           performs  P += tile  so the residual is never re-read by the SM), or fp32 y
+// Layers are chained through per-256-column "chunk done" mbarriers: the producer may load the K
+// slices of layer l+1 that depend only on finished chunks of layer l, so the tensor pipe does not
+// drain while the last chunk's epilogue runs.
+// The activation tile of a CTA (2 x [128 x L] bf16) lives in a per-CTA global scratch that stays in
+// L2; only x (128 B/pose) and y (192 B/pose) are compulsory HBM traffic.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,9 +33,12 @@ constexpr int BK = 64;
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int OUT_BYTES = BM * 64 * 2; // 16 KB staging tile [128 rows x 64 cols] bf16
 constexpr int NTHREADS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + 4 * BN * 4 + 256;
+constexpr int MAX_CHUNKS = 16;         // linear_size <= 4096
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + BN * 4 + 512;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 
 struct Params {
   int L;           // linear_size (multiple of 256)
@@ -43,13 +50,19 @@ struct Params {
   long long B;
   long long act_half_rows;   // gridDim.x * 128 : row offset of buffer Q inside the scratch
   const float* bias;         // folded bias, indexed by packed weight row
-  __nv_bfloat16* act;        // scratch base (buffer P), [2][grid*128][L]
   float* y;                  // [B][out_valid]
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// descriptor for (1024B-aligned tile base + byte offset inside the first 128B row)
+__device__ __forceinline__ uint64_t desc_at(uint32_t smem_addr) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version=1 | SWIZZLE_128B
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);    // start address | LBO (unused) = 1
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -60,14 +73,15 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  float* sBias = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * BN);
+  uint8_t* sOut = sB + STAGES * B_BYTES;                       // 1024-aligned (all sizes are multiples of 1 KB)
+  float* sBias = reinterpret_cast<float*>(sOut + OUT_BYTES);   // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint64_t* layer_done = tempty + 2;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_done + 1);
+  uint64_t* chunk_done = tempty + 2;     // [MAX_CHUNKS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_done + MAX_CHUNKS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,7 +90,7 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_act); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_wout);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-    mbar_init(layer_done, 4);
+    for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(&chunk_done[c], 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -90,16 +104,12 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   const int nk_hidden = L / BK;
   const int nchunks_hidden = L / BN;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
-    int stage = 0; uint32_t phase = 0; uint32_t ld_waits = 0;
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop)
+    int stage = 0; uint32_t phase = 0; uint32_t dep_layers = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int l = 0; l < nlayers; ++l) {
         const bool first = (l == 0), last = (l == nlayers - 1);
-        if (!first) {   // activations of layer l-1 must be complete and visible to the async proxy
-          mbar_wait(layer_done, ld_waits & 1, 100 + l); ++ld_waits;
-          fence_proxy_async();
-        }
         const int nk = first ? 1 : nk_hidden;
         const int nchunks = last ? 1 : nchunks_hidden;
         const CUtensorMap* tmA = first ? &tm_x : &tm_act;
@@ -108,21 +118,31 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const uint32_t bytes = A_BYTES + (last ? p.out_n * BK * 2 : B_BYTES);
         for (int c = 0; c < nchunks; ++c) {
           for (int ks = 0; ks < nk; ++ks) {
+            if (!first && c == 0 && (ks & 3) == 0) {
+              // K slice ks reads columns [64ks, 64ks+64) = chunk ks/4 of the previous layer
+              mbar_wait(&chunk_done[ks >> 2], dep_layers & 1, 100 + l);
+              fence_proxy_async();
+            }
             mbar_wait(&empty[stage], phase ^ 1, 1);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
-            if (last) tma_load_2d(sB + stage * B_BYTES, &tm_wout, &full[stage], ks * BK, 0);
-            else      tma_load_2d(sB + stage * B_BYTES, &tm_w, &full[stage], ks * BK, l * L + c * BN);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
+              if (last) tma_load_2d(sB + stage * B_BYTES, &tm_wout, &full[stage], ks * BK, 0);
+              else      tma_load_2d(sB + stage * B_BYTES, &tm_w, &full[stage], ks * BK, l * L + c * BN);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+        if (!first) ++dep_layers;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     int stage = 0; uint32_t phase = 0; uint32_t q = 0;
     const uint32_t idesc_hidden = umma_idesc_bf16_f32(BM, BN);
     const uint32_t idesc_out = umma_idesc_bf16_f32(BM, p.out_n);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int l = 0; l < nlayers; ++l) {
         const bool first = (l == 0), last = (l == nlayers - 1);
@@ -137,17 +157,18 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           for (int ks = 0; ks < nk; ++ks) {
             mbar_wait(&full[stage], phase, 3);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+            if (elect_one()) {
+              const uint64_t ad = desc_at(a_base + stage * A_BYTES);
+              const uint64_t bd = desc_at(b_base + stage * B_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                           (ks | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)      // +32 B per K=16 slice -> +2 in the (addr >> 4) field
+                umma_bf16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+              umma_commit(&empty[stage]);            // frees the smem slot once these MMAs have read it
+              if (ks == nk - 1) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
             }
-            umma_commit(&empty[stage]);   // frees the smem slot once these MMAs have read it
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull[acc]);       // accumulator complete -> epilogue
         }
       }
     }
@@ -155,7 +176,8 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     // ------------------------------------------------------------ epilogue (128 threads = 128 rows)
     const int ew = warp - 4;                 // == warp % 4 : the TMEM lane quadrant this warp may read
     const int row = ew * 32 + lane;
-    float* myBias = sBias + ew * BN;
+    const bool t0 = (threadIdx.x == 128);    // issues the TMA stores
+    uint8_t* my_out = sOut + row * 128;
     uint32_t q = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int l = 0; l < nlayers; ++l) {
@@ -163,46 +185,60 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int nchunks = last ? 1 : nchunks_hidden;
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t acc = q & 1, aphase = (q >> 1) & 1;
-          const int ncols = last ? p.out_n : BN;
           const int wrow0 = last ? (nlayers - 1) * L : l * L + c * BN;
-          __syncwarp();
-          for (int j = lane; j < ncols; j += 32) myBias[j] = __ldg(p.bias + wrow0 + j);
-          __syncwarp();
+          // bias of this chunk -> smem (the previous chunk's readers are past their last named barrier)
+          sBias[row] = __ldg(p.bias + wrow0 + row);
+          if (!last) sBias[row + 128] = __ldg(p.bias + wrow0 + row + 128);
+          named_bar_sync(1, 128);
           mbar_wait(&tfull[acc], aphase, 4);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
           if (!last) {
             const bool to_p = (l == 0) || ((l & 1) == 0);
             const bool add_res = p.residual && l >= 2 && ((l & 1) == 0);
-            __nv_bfloat16* drow = p.act + ((to_p ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM + row) * L + c * BN;
+            const int drow = static_cast<int>((to_p ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
 #pragma unroll 1
-            for (int g = 0; g < BN / 32; ++g) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(taddr + g * 32, v);
-              uint4 rr[4];
-              if (add_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(drow + g * 32);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rr[i] = rp[i];
-              }
+            for (int s = 0; s < BN / 64; ++s) {
+              uint32_t v0[32], v1[32];
+              tmem_ld_32x32b_x32(taddr + s * 64, v0);
+              tmem_ld_32x32b_x32(taddr + s * 64 + 32, v1);
               tmem_ld_wait();
-              uint32_t o[16];
+              if (s == BN / 64 - 1) {          // accumulator drained: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+              }
+              uint32_t o[32];
+              const float* bs = sBias + s * 64;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float a0 = fmaxf(__uint_as_float(v[2 * j]) + myBias[g * 32 + 2 * j], 0.f);
-                float a1 = fmaxf(__uint_as_float(v[2 * j + 1]) + myBias[g * 32 + 2 * j + 1], 0.f);
-                if (add_res) {
-                  const uint32_t rw = reinterpret_cast<const uint32_t*>(rr)[j];
-                  __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw);
-                  a0 += __low2float(r2);
-                  a1 += __high2float(r2);
-                }
-                o[j] = pack_bf16x2(a0, a1);
+                o[j] = pack_bf16x2(fmaxf(__uint_as_float(v0[2 * j]) + bs[2 * j], 0.f),
+                                   fmaxf(__uint_as_float(v0[2 * j + 1]) + bs[2 * j + 1], 0.f));
+                o[16 + j] = pack_bf16x2(fmaxf(__uint_as_float(v1[2 * j]) + bs[32 + 2 * j], 0.f),
+                                        fmaxf(__uint_as_float(v1[2 * j + 1]) + bs[32 + 2 * j + 1], 0.f));
               }
-              uint4* dp = reinterpret_cast<uint4*>(drow + g * 32);
+              if (t0) tma_store_wait_read<0>();      // the previous store has finished reading the staging tile
+              __syncwarp();
+              named_bar_sync(1, 128);
+              // row `row` = 128 B = 8 x 16 B chunks at chunk index (j ^ (row & 7)): the SWIZZLE_128B layout
 #pragma unroll
-              for (int i = 0; i < 4; ++i) dp[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(my_out + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              fence_proxy_async_smem();
+              named_bar_sync(1, 128);
+              if (t0) {
+                if (add_res) tma_reduce_add_2d(&tm_act, sOut, c * BN + s * 64, drow);   // P += relu(.)  (residual)
+                else         tma_store_2d(&tm_act, sOut, c * BN + s * 64, drow);
+                tma_store_commit();
+              }
+              __syncwarp();
             }
+            if (t0) {                           // chunk c of this layer is complete in global memory
+              tma_store_wait<0>();
+              fence_proxy_async();
+              mbar_arrive(&chunk_done[c]);
+            }
+            __syncwarp();
           } else {
             const long long grow = static_cast<long long>(tile) * BM + row;
             for (int g = 0; g < p.out_n / 16; ++g) {
@@ -215,21 +251,17 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 for (int j = 0; j < 16; j += 2) {
                   const int col = g * 16 + j;
                   if (col + 1 < p.out_valid) {
-                    float2 o2 = make_float2(__uint_as_float(v[j]) + myBias[col], __uint_as_float(v[j + 1]) + myBias[col + 1]);
+                    float2 o2 = make_float2(__uint_as_float(v[j]) + sBias[col], __uint_as_float(v[j + 1]) + sBias[col + 1]);
                     *reinterpret_cast<float2*>(yp + j) = o2;
                   } else if (col < p.out_valid) {
-                    yp[j] = __uint_as_float(v[j]) + myBias[col];
+                    yp[j] = __uint_as_float(v[j]) + sBias[col];
                   }
                 }
               }
             }
-          }
-          tc_fence_before();
-          if (!last && c == nchunks - 1) { __threadfence(); fence_proxy_async(); }
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&tempty[acc]);
-            if (!last && c == nchunks - 1) mbar_arrive(layer_done);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
         }
       }
@@ -341,7 +373,7 @@ int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cud
   Params p;
   p.L = L; p.nlayers = nlayers; p.out_n = out_n; p.out_valid = m->out_size; p.residual = m->cfg.residual;
   p.ntiles = ntiles; p.B = B; p.act_half_rows = static_cast<long long>(grid) * BM;
-  p.bias = m->bias_fold; p.act = m->act_scratch; p.y = y;
+  p.bias = m->bias_fold; p.y = y;
   static bool attr_set = false;
   if (!attr_set) {
     P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

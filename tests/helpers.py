@@ -14,7 +14,8 @@ def bf16_round(a):
 
 def emulate_bf16_forward(p, x, cfg, small_batch=False):
     """What the tcgen05 kernel computes, restated in NumPy: folded weights rounded to bf16, the input
-    and every hidden activation (after bias+ReLU+residual) rounded to bf16, fp32 accumulation (here
+    and every hidden activation rounded to bf16 after bias+ReLU and again after the residual add (the
+    residual is added by the L2 through a bf16 TMA reduce-add), fp32 accumulation (here
     float64 - the difference is far below the bf16 rounding).  small_batch: the latency path keeps
     activations in fp32 (only the weights are bf16)."""
     folded = M.fold_inference(p, cfg)
@@ -27,12 +28,14 @@ def emulate_bf16_forward(p, x, cfg, small_batch=False):
         if li == last:
             return z
         r = np.maximum(z, 0)
+        if not small_batch:
+            r = bf16_round(r).astype(np.float64)          # the epilogue stores relu(.) as bf16 ...
         if li == 0 or li % 2 == 1:
             h = r
         else:
-            h = (res + r) if cfg.residual else r
-        if not small_batch:
-            h = bf16_round(h).astype(np.float64)
+            h = (res + r) if cfg.residual else r          # ... and the L2 adds the residual (TMA reduce-add)
+            if not small_batch:
+                h = bf16_round(h).astype(np.float64)
         if li == 0 or li % 2 == 0:
             res = h
 

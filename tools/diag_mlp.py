@@ -28,6 +28,7 @@ def emulate(p, x, cfg, act_round=bf16_round, w_round=bf16_round, acc=np.float64)
         if li == last:
             return z, hs
         r = np.maximum(z, 0)
+        r = act_round(r).astype(acc)
         h = r if (li == 0 or li % 2 == 1) else ((res + r) if cfg.residual else r)
         h = act_round(h).astype(acc)
         hs.append(h)
