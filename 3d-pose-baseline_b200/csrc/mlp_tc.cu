@@ -19,6 +19,8 @@
 // drain while the last chunk's epilogue runs.
 // The activation tile of a CTA (2 x [128 x L] bf16) lives in a per-CTA global scratch that stays in
 // L2; only x (128 B/pose) and y (192 B/pose) are compulsory HBM traffic.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,15 +32,23 @@ using namespace ptx;
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int OUT_BYTES = BM * 64 * 2; // 16 KB staging tile [128 rows x 64 cols] bf16
 constexpr int NTHREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_CHUNKS = 16;         // linear_size <= 4096
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + BN * 4 + 512;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
+
+// CG = 1: one CTA per 128-pose tile, W' tile [256 x 64] per stage (48 KB/stage, 4 stages).
+// CG = 2: a CTA PAIR (cta_group::2) per 256-pose tile; each CTA stages its own A [128 x 64] and HALF
+//         of the W' tile [128 x 64] (32 KB/stage, 6 stages) - the pair's tensor cores share the halves,
+//         which cuts the L2->SM operand traffic per FLOP by a third (the measured limiter at CG = 1).
+template <int CG> struct Tile {
+  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + BN * 4 + 512;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
+};
 
 struct Params {
   int L;           // linear_size (multiple of 256)
@@ -46,7 +56,7 @@ struct Params {
   int out_n;       // output width padded to a multiple of 16 (48)
   int out_valid;   // 48 or 42
   int residual;
-  int ntiles;
+  int ntiles;      // 128-row tiles
   long long B;
   long long act_half_rows;   // gridDim.x * 128 : row offset of buffer Q inside the scratch
   const float* bias;         // folded bias, indexed by packed weight row
@@ -65,10 +75,14 @@ __device__ __forceinline__ uint64_t desc_at(uint32_t smem_addr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_act,
                       const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wout,
                       const Params p) {
+  using T = Tile<CG>;
+  constexpr int STAGES = T::STAGES;
+  constexpr int B_BYTES = T::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -76,26 +90,33 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   uint8_t* sOut = sB + STAGES * B_BYTES;                       // 1024-aligned (all sizes are multiples of 1 KB)
   float* sBias = reinterpret_cast<float*>(sOut + OUT_BYTES);   // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
-  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* full = bars;                 // [STAGES]   (CG = 2: only the leader CTA's are used)
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* tempty = tfull + 2;          // [2]        (CG = 2: only the leader CTA's are used)
   uint64_t* chunk_done = tempty + 2;     // [MAX_CHUNKS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_done + MAX_CHUNKS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const int group_id = blockIdx.x / CG, ngroups = gridDim.x / CG;
+  const int ngtiles = (p.ntiles + CG - 1) / CG;     // tiles of 128*CG rows
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_act); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_wout);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * CG); }
     for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(&chunk_done[c], 1);
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 2) {
+    if (CG == 2) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -107,7 +128,8 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop)
     int stage = 0; uint32_t phase = 0; uint32_t dep_layers = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int gt = group_id; gt < ngtiles; gt += ngroups) {
+      const int tile = gt * CG + static_cast<int>(rank);
       for (int l = 0; l < nlayers; ++l) {
         const bool first = (l == 0), last = (l == nlayers - 1);
         const int nk = first ? 1 : nk_hidden;
@@ -115,20 +137,28 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const CUtensorMap* tmA = first ? &tm_x : &tm_act;
         const int a_row = first ? tile * BM
                                 : static_cast<int>(((l & 1) ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
-        const uint32_t bytes = A_BYTES + (last ? p.out_n * BK * 2 : B_BYTES);
+        const int b_rows = last ? p.out_n / CG : T::B_ROWS;
+        const uint32_t bytes = A_BYTES + b_rows * BK * 2;
         for (int c = 0; c < nchunks; ++c) {
+          const int b_row = (last ? 0 : l * L + c * BN) + static_cast<int>(rank) * b_rows;
           for (int ks = 0; ks < nk; ++ks) {
             if (!first && c == 0 && (ks & 3) == 0) {
-              // K slice ks reads columns [64ks, 64ks+64) = chunk ks/4 of the previous layer
+              // K slice ks reads columns [64ks, 64ks+64) = chunk ks/4 of the previous layer (this CTA's rows)
               mbar_wait(&chunk_done[ks >> 2], dep_layers & 1, 100 + l);
               fence_proxy_async();
             }
             mbar_wait(&empty[stage], phase ^ 1, 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full[stage], bytes);
-              tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
-              if (last) tma_load_2d(sB + stage * B_BYTES, &tm_wout, &full[stage], ks * BK, 0);
-              else      tma_load_2d(sB + stage * B_BYTES, &tm_w, &full[stage], ks * BK, l * L + c * BN);
+              if (CG == 1) {
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
+                tma_load_2d(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row);
+              } else {
+                // both CTAs' bytes are accounted on the leader's barrier
+                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+                tma_load_2d_2sm(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
+                tma_load_2d_2sm(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -137,13 +167,13 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (!first) ++dep_layers;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     int stage = 0; uint32_t phase = 0; uint32_t q = 0;
-    const uint32_t idesc_hidden = umma_idesc_bf16_f32(BM, BN);
-    const uint32_t idesc_out = umma_idesc_bf16_f32(BM, p.out_n);
+    const uint32_t idesc_hidden = umma_idesc_bf16_f32(BM * CG, BN);
+    const uint32_t idesc_out = umma_idesc_bf16_f32(BM * CG, p.out_n);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int gt = group_id; gt < ngtiles; gt += ngroups) {
       for (int l = 0; l < nlayers; ++l) {
         const bool first = (l == 0), last = (l == nlayers - 1);
         const int nk = first ? 1 : nk_hidden;
@@ -161,10 +191,17 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
               const uint64_t ad = desc_at(a_base + stage * A_BYTES);
               const uint64_t bd = desc_at(b_base + stage * B_BYTES);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)      // +32 B per K=16 slice -> +2 in the (addr >> 4) field
-                umma_bf16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
-              umma_commit(&empty[stage]);            // frees the smem slot once these MMAs have read it
-              if (ks == nk - 1) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+              for (int k = 0; k < BK / 16; ++k) {    // +32 B per K=16 slice -> +2 in the (addr >> 4) field
+                if (CG == 1) umma_bf16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                else         umma_bf16_ss_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+              }
+              if (CG == 1) {
+                umma_commit(&empty[stage]);                   // frees the smem slot once these MMAs have read it
+                if (ks == nk - 1) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+              } else {
+                umma_commit_2sm(&empty[stage], 0x3);          // ... in both CTAs of the pair
+                if (ks == nk - 1) umma_commit_2sm(&tfull[acc], 0x3);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -173,13 +210,14 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads = 128 rows)
+    // ------------------------------------------------------------ epilogue (128 threads = this CTA's 128 rows)
     const int ew = warp - 4;                 // == warp % 4 : the TMEM lane quadrant this warp may read
     const int row = ew * 32 + lane;
     const bool t0 = (threadIdx.x == 128);    // issues the TMA stores
     uint8_t* my_out = sOut + row * 128;
     uint32_t q = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int gt = group_id; gt < ngtiles; gt += ngroups) {
+      const int tile = gt * CG + static_cast<int>(rank);
       for (int l = 0; l < nlayers; ++l) {
         const bool last = (l == nlayers - 1);
         const int nchunks = last ? 1 : nchunks_hidden;
@@ -203,10 +241,10 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
               tmem_ld_32x32b_x32(taddr + s * 64, v0);
               tmem_ld_32x32b_x32(taddr + s * 64 + 32, v1);
               tmem_ld_wait();
-              if (s == BN / 64 - 1) {          // accumulator drained: hand it back to the MMA warp
+              if (s == BN / 64 - 1) {          // accumulator drained: hand it back to the MMA warp (of the leader CTA)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) { if (CG == 1) mbar_arrive(&tempty[acc]); else mbar_arrive_cluster(&tempty[acc], 0); }
               }
               uint32_t o[32];
               const float* bs = sBias + s * 64;
@@ -261,7 +299,7 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (CG == 1) mbar_arrive(&tempty[acc]); else mbar_arrive_cluster(&tempty[acc], 0); }
           }
         }
       }
@@ -269,13 +307,17 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ----------------------------------------------------------------------------- debug GEMM
 // C[128,N] = A[128,K] W[N,K]^T with one CTA, one smem stage, fully serialised: exercises the TMA
 // tensor maps, the UMMA smem/instruction descriptors and the TMEM load layout in isolation.
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB (debug kernel: full W tile in one CTA)
 __global__ void __launch_bounds__(128, 1)
 umma_gemm_debug_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                        float* C, int N, int K) {
@@ -352,39 +394,59 @@ static int make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return P3D_OK;
 }
 
-int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cudaStream_t st) {
+template <int CG>
+static int launch_forward(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cudaStream_t st) {
+  using T = Tile<CG>;
   const int L = m->L;
-  P3D_REQUIRE(L % BN == 0, "bf16 tensor-core path needs linear_size %% 256 == 0 (got %d)", L);
   const int ntiles = static_cast<int>((B + BM - 1) / BM);
-  const int grid = ntiles < m->num_sms ? ntiles : m->num_sms;
-  // per-CTA activation scratch, sized for a full grid once
-  if (m->act_grid < m->num_sms) {
-    if (m->act_scratch) cudaFree(m->act_scratch);
-    P3D_CUDA(cudaMalloc(&m->act_scratch, sizeof(__nv_bfloat16) * 2ull * m->num_sms * BM * L));
-    m->act_grid = m->num_sms;
-  }
+  const int ngtiles = (ntiles + CG - 1) / CG;
+  const int max_groups = m->num_sms / CG;
+  const int grid = CG * (ngtiles < max_groups ? ngtiles : max_groups);
   const int nlayers = static_cast<int>(m->layers.size());
   const int out_n = (m->out_size + 15) / 16 * 16;
   CUtensorMap tm_x, tm_act, tm_w, tm_wout;
   P3D_TRY(make_tmap(&tm_x, xb, static_cast<uint64_t>(B), 64, 64, BM));
   P3D_TRY(make_tmap(&tm_act, m->act_scratch, 2ull * grid * BM, L, L, BM));
-  P3D_TRY(make_tmap(&tm_w, m->wt_bf16, static_cast<uint64_t>(nlayers - 1) * L, m->kpad, m->kpad, BN));
-  P3D_TRY(make_tmap(&tm_wout, m->wt_bf16 + static_cast<size_t>(nlayers - 1) * L * m->kpad, out_n, m->kpad, m->kpad, out_n));
+  P3D_TRY(make_tmap(&tm_w, m->wt_bf16, static_cast<uint64_t>(nlayers - 1) * L, m->kpad, m->kpad, T::B_ROWS));
+  P3D_TRY(make_tmap(&tm_wout, m->wt_bf16 + static_cast<size_t>(nlayers - 1) * L * m->kpad, out_n, m->kpad, m->kpad, out_n / CG));
   Params p;
   p.L = L; p.nlayers = nlayers; p.out_n = out_n; p.out_valid = m->out_size; p.residual = m->cfg.residual;
   p.ntiles = ntiles; p.B = B; p.act_half_rows = static_cast<long long>(grid) * BM;
   p.bias = m->bias_fold; p.y = y;
   static bool attr_set = false;
   if (!attr_set) {
-    P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     attr_set = true;
   }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = T::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (prof::enabled()) prof::begin(st, &e0, &e1);
-  mlp_forward_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tm_x, tm_act, tm_w, tm_wout, p);
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, mlp_forward_tc_kernel<CG>, tm_x, tm_act, tm_w, tm_wout, p));
   P3D_LAUNCH_CHECK();
   if (e0) prof::end(st, e0, e1);
   return P3D_OK;
+}
+
+int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cudaStream_t st) {
+  const int L = m->L;
+  P3D_REQUIRE(L % BN == 0 && L / BN <= MAX_CHUNKS, "bf16 tensor-core path needs linear_size %% 256 == 0 and <= 4096 (got %d)", L);
+  // per-CTA activation scratch, sized for a full grid once
+  if (m->act_grid < m->num_sms) {
+    if (m->act_scratch) cudaFree(m->act_scratch);
+    P3D_CUDA(cudaMalloc(&m->act_scratch, sizeof(__nv_bfloat16) * 2ull * m->num_sms * BM * L));
+    m->act_grid = m->num_sms;
+  }
+  static int cg = -1;
+  if (cg < 0) {
+    const char* e = getenv("P3D_TC_CG");       // 1 = single-CTA tiles, 2 = CTA pairs (default)
+    cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cg == 1 ? launch_forward<1>(m, xb, y, B, st) : launch_forward<2>(m, xb, y, B, st);
 }
 
 int debug_umma_gemm(const void* A, const void* W, float* C, int N, int K, cudaStream_t st) {
