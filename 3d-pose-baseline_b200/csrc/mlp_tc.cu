@@ -36,7 +36,7 @@ constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int OUT_BYTES = BM * 64 * 2; // 16 KB staging tile [128 rows x 64 cols] bf16
 constexpr int NTHREADS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_CHUNKS = 16;         // linear_size <= 4096
+constexpr int MAX_SLABS = 64;          // 64-column slabs per layer: linear_size <= 4096
 
 // CG = 1: one CTA per 128-pose tile, W' tile [256 x 64] per stage (48 KB/stage, 4 stages).
 // CG = 2: a CTA PAIR (cta_group::2) per 256-pose tile; each CTA stages its own A [128 x 64] and HALF
@@ -44,9 +44,10 @@ constexpr int MAX_CHUNKS = 16;         // linear_size <= 4096
 //         which cuts the L2->SM operand traffic per FLOP by a third (the measured limiter at CG = 1).
 template <int CG> struct Tile {
   static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int BAR_BYTES = 1024;       // mbarriers + tmem slot
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + BN * 4 + 512;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + 2 * BN * 4 + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -88,14 +89,16 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sOut = sB + STAGES * B_BYTES;                       // 1024-aligned (all sizes are multiples of 1 KB)
-  float* sBias = reinterpret_cast<float*>(sOut + OUT_BYTES);   // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+  float* sBiasAll = reinterpret_cast<float*>(sOut + OUT_BYTES);   // [2][256], double buffered per chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBiasAll + 2 * BN);
   uint64_t* full = bars;                 // [STAGES]   (CG = 2: only the leader CTA's are used)
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]        (CG = 2: only the leader CTA's are used)
-  uint64_t* chunk_done = tempty + 2;     // [MAX_CHUNKS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_done + MAX_CHUNKS);
+  uint64_t* stg_full = tempty + 2;       // [1] staging tile written by the 4 epilogue warps
+  uint64_t* stg_free = stg_full + 1;     // [1] staging tile read out by the TMA store
+  uint64_t* slab_done = stg_free + 1;    // [MAX_SLABS] 64-column slab of the current layer is complete in global memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_done + MAX_SLABS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,7 +111,8 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_act); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_wout);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * CG); }
-    for (int c = 0; c < MAX_CHUNKS; ++c) mbar_init(&chunk_done[c], 1);
+    mbar_init(stg_full, 4); mbar_init(stg_free, 1);
+    for (int c = 0; c < MAX_SLABS; ++c) mbar_init(&slab_done[c], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -142,22 +146,20 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int c = 0; c < nchunks; ++c) {
           const int b_row = (last ? 0 : l * L + c * BN) + static_cast<int>(rank) * b_rows;
           for (int ks = 0; ks < nk; ++ks) {
-            if (!first && c == 0 && (ks & 3) == 0) {
-              // K slice ks reads columns [64ks, 64ks+64) = chunk ks/4 of the previous layer (this CTA's rows)
-              mbar_wait(&chunk_done[ks >> 2], dep_layers & 1, 100 + l);
-              fence_proxy_async();
-            }
+            // K slice ks reads columns [64ks, 64ks+64) = slab ks of the previous layer (this CTA's rows), written
+            // by TMA stores (async proxy, completed before the arrive): no proxy fence needed
+            if (!first && c == 0) mbar_wait(&slab_done[ks], dep_layers & 1, 100 + l);
             mbar_wait(&empty[stage], phase ^ 1, 1);
             if (elect_one()) {
               if (CG == 1) {
                 mbar_arrive_expect_tx(&full[stage], bytes);
-                tma_load_2d(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
-                tma_load_2d(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row);
+                tma_load_2d_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
+                tma_load_2d_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
               } else {
                 // both CTAs' bytes are accounted on the leader's barrier
                 if (leader) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
-                tma_load_2d_2sm(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row);
-                tma_load_2d_2sm(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row);
+                tma_load_2d_2sm_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
+                tma_load_2d_2sm_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
               }
             }
             __syncwarp();
@@ -209,13 +211,38 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ TMA store warp: staging tile -> this CTA's activation rows
+    // One lane owns the bulk async-groups: it frees the staging tile as soon as the store has READ it and
+    // publishes "slab done" (to the producer of the next layer) when the store has fully completed.
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int gt = group_id; gt < ngtiles; gt += ngroups) {
+        for (int l = 0; l < nlayers - 1; ++l) {
+          const bool to_p = (l == 0) || ((l & 1) == 0);
+          const bool add_res = p.residual && l >= 2 && ((l & 1) == 0);
+          const int drow = static_cast<int>((to_p ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
+          const int nsl = L / 64;
+          for (int sl = 0; sl < nsl; ++sl, ++n) {
+            mbar_wait(stg_full, n & 1, 6);
+            if (add_res) tma_reduce_add_2d_hint(&tm_act, sOut, sl * 64, drow, kEvictLast);   // P += relu(.)  (residual, added in the L2)
+            else         tma_store_2d_hint(&tm_act, sOut, sl * 64, drow, kEvictLast);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(stg_free);
+            if (sl > 0) { tma_store_wait<1>(); mbar_arrive(&slab_done[sl - 1]); }
+          }
+          tma_store_wait<0>();
+          mbar_arrive(&slab_done[nsl - 1]);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (128 threads = this CTA's 128 rows)
     const int ew = warp - 4;                 // == warp % 4 : the TMEM lane quadrant this warp may read
     const int row = ew * 32 + lane;
-    const bool t0 = (threadIdx.x == 128);    // issues the TMA stores
     uint8_t* my_out = sOut + row * 128;
-    uint32_t q = 0;
+    uint32_t q = 0, nslab = 0;
     for (int gt = group_id; gt < ngtiles; gt += ngroups) {
       const int tile = gt * CG + static_cast<int>(rank);
       for (int l = 0; l < nlayers; ++l) {
@@ -224,7 +251,9 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         for (int c = 0; c < nchunks; ++c, ++q) {
           const uint32_t acc = q & 1, aphase = (q >> 1) & 1;
           const int wrow0 = last ? (nlayers - 1) * L : l * L + c * BN;
-          // bias of this chunk -> smem (the previous chunk's readers are past their last named barrier)
+          // bias of this chunk -> smem.  Double buffered: a fast warp may stage chunk q+1 while a slow one still
+          // reads chunk q; the named barrier below keeps everybody within one chunk of each other.
+          float* sBias = sBiasAll + (q & 1) * BN;
           sBias[row] = __ldg(p.bias + wrow0 + row);
           if (!last) sBias[row + 128] = __ldg(p.bias + wrow0 + row + 128);
           named_bar_sync(1, 128);
@@ -232,9 +261,6 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
           if (!last) {
-            const bool to_p = (l == 0) || ((l & 1) == 0);
-            const bool add_res = p.residual && l >= 2 && ((l & 1) == 0);
-            const int drow = static_cast<int>((to_p ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
 #pragma unroll 1
             for (int s = 0; s < BN / 64; ++s) {
               uint32_t v0[32], v1[32];
@@ -255,28 +281,16 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 o[16 + j] = pack_bf16x2(fmaxf(__uint_as_float(v1[2 * j]) + bs[32 + 2 * j], 0.f),
                                         fmaxf(__uint_as_float(v1[2 * j + 1]) + bs[32 + 2 * j + 1], 0.f));
               }
-              if (t0) tma_store_wait_read<0>();      // the previous store has finished reading the staging tile
-              __syncwarp();
-              named_bar_sync(1, 128);
+              mbar_wait(stg_free, (nslab & 1) ^ 1, 5);    // the store warp has read the previous slab out of the staging tile
               // row `row` = 128 B = 8 x 16 B chunks at chunk index (j ^ (row & 7)): the SWIZZLE_128B layout
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<uint4*>(my_out + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
               fence_proxy_async_smem();
-              named_bar_sync(1, 128);
-              if (t0) {
-                if (add_res) tma_reduce_add_2d(&tm_act, sOut, c * BN + s * 64, drow);   // P += relu(.)  (residual)
-                else         tma_store_2d(&tm_act, sOut, c * BN + s * 64, drow);
-                tma_store_commit();
-              }
               __syncwarp();
+              if (lane == 0) mbar_arrive(stg_full);
+              ++nslab;
             }
-            if (t0) {                           // chunk c of this layer is complete in global memory
-              tma_store_wait<0>();
-              fence_proxy_async();
-              mbar_arrive(&chunk_done[c]);
-            }
-            __syncwarp();
           } else {
             const long long grow = static_cast<long long>(tile) * BM + row;
             for (int g = 0; g < p.out_n / 16; ++g) {
@@ -290,9 +304,9 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                   const int col = g * 16 + j;
                   if (col + 1 < p.out_valid) {
                     float2 o2 = make_float2(__uint_as_float(v[j]) + sBias[col], __uint_as_float(v[j + 1]) + sBias[col + 1]);
-                    *reinterpret_cast<float2*>(yp + j) = o2;
+                    __stcs(reinterpret_cast<float2*>(yp + j), o2);
                   } else if (col < p.out_valid) {
-                    yp[j] = __uint_as_float(v[j]) + sBias[col];
+                    __stcs(yp + j, __uint_as_float(v[j]) + sBias[col]);
                   }
                 }
               }
@@ -434,7 +448,7 @@ static int launch_forward(p3d_model* m, const __nv_bfloat16* xb, float* y, int64
 
 int forward_bf16(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t B, cudaStream_t st) {
   const int L = m->L;
-  P3D_REQUIRE(L % BN == 0 && L / BN <= MAX_CHUNKS, "bf16 tensor-core path needs linear_size %% 256 == 0 and <= 4096 (got %d)", L);
+  P3D_REQUIRE(L % BN == 0 && L / 64 <= MAX_SLABS, "bf16 tensor-core path needs linear_size %% 256 == 0 and <= 4096 (got %d)", L);
   // per-CTA activation scratch, sized for a full grid once
   if (m->act_grid < m->num_sms) {
     if (m->act_scratch) cudaFree(m->act_scratch);
