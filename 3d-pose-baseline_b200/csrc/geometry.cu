@@ -78,10 +78,19 @@ struct FusedArgs {
 __global__ void __launch_bounds__(256) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
                                                                float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
   __shared__ __align__(16) float sw[PPB * 96];
-  __shared__ __align__(16) float s2[PPB * 32];
-  __shared__ __align__(16) float s3[PPB * 48];
+  __shared__ __align__(16) float s3[MAXCAMS * PPB * 48];
   const int tid = threadIdx.x;
   const int lp = tid >> 4, j = tid & 15;   // local pose, joint slot
+  // per-thread constants (indexing the tables with a per-lane index inside the loop would serialise
+  // the constant cache 16 ways)
+  const int j2 = kJoints2D[j];
+  const bool has3 = j < a.nj3;
+  const int j3 = has3 ? (a.predict_14 ? kJoints3D14[j] : kJoints3D16[j]) : 0;
+  const float m2x = a.mean2[2 * j], m2y = a.mean2[2 * j + 1], i2x = a.istd2[2 * j], i2y = a.istd2[2 * j + 1];
+  float m3[3], i3[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { m3[d] = has3 ? a.mean3[3 * j + d] : 0.f; i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; }
+  const int out3 = a.out3;
   const long long ntiles = (N + PPB - 1) / PPB;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long p0 = tile * PPB;
@@ -89,41 +98,44 @@ __global__ void __launch_bounds__(256) project_normalize_kernel(const float* __r
     // coalesced stage-in of np*96 floats (rows are 384 B => float4 aligned)
     const float4* src = reinterpret_cast<const float4*>(world + p0 * 96);
     for (int i = tid; i < np * 24; i += 256) reinterpret_cast<float4*>(sw)[i] = __ldg(src + i);
-    __syncthreads();
+    __syncthreads();                       // also orders the previous tile's reads of s3 before this tile's writes
     const bool live = lp < np;
-    const float* w = sw + lp * 96;
-    for (int c = 0; c < a.ncams; ++c) {
-      if (live && x2d) {
-        const int jj = kJoints2D[j];
-        float u, v, d, ra, ta, r2;
-        project_point(a.cam[c], w[jj * 3], w[jj * 3 + 1], w[jj * 3 + 2], u, v, d, ra, ta, r2);
-        s2[lp * 32 + 2 * j] = (u - a.mean2[2 * j]) * a.istd2[2 * j];
-        s2[lp * 32 + 2 * j + 1] = (v - a.mean2[2 * j + 1]) * a.istd2[2 * j + 1];
-      }
-      if (live && y3d && j < a.nj3) {
-        const int jj = a.predict_14 ? kJoints3D14[j] : kJoints3D16[j];
-        float X0, X1, X2, H0, H1, H2;
-        world_to_cam(a.cam[c], w[jj * 3], w[jj * 3 + 1], w[jj * 3 + 2], X0, X1, X2);
-        world_to_cam(a.cam[c], w[0], w[1], w[2], H0, H1, H2);     // root (hip) for postprocess_3d
-        s3[lp * a.out3 + 3 * j] = ((X0 - H0) - a.mean3[3 * j]) * a.istd3[3 * j];
-        s3[lp * a.out3 + 3 * j + 1] = ((X1 - H1) - a.mean3[3 * j + 1]) * a.istd3[3 * j + 1];
-        s3[lp * a.out3 + 3 * j + 2] = ((X2 - H2) - a.mean3[3 * j + 2]) * a.istd3[3 * j + 2];
-      }
-      __syncthreads();
-      if (x2d) {
-        float4* dst = reinterpret_cast<float4*>(x2d + (static_cast<long long>(c) * N + p0) * 32);
-        for (int i = tid; i < np * 8; i += 256) dst[i] = reinterpret_cast<const float4*>(s2)[i];
-      }
-      if (y3d) {
-        float* dst = y3d + (static_cast<long long>(c) * N + p0) * a.out3;
-        const int tot = np * a.out3;
-        if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (tot % 4 == 0)) {
-          for (int i = tid; i < tot / 4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s3)[i];
-        } else {
-          for (int i = tid; i < tot; i += 256) dst[i] = s3[i];
+    if (live) {
+      const float* w = sw + lp * 96;
+      const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
+      const float qx = w[j3 * 3], qy = w[j3 * 3 + 1], qz = w[j3 * 3 + 2];
+      const float hx = w[0], hy = w[1], hz = w[2];
+      for (int c = 0; c < a.ncams; ++c) {
+        if (x2d) {
+          float u, v, d, ra, ta, r2;
+          project_point(a.cam[c], px, py, pz, u, v, d, ra, ta, r2);
+          // a warp = 2 poses x 16 joints writes 256 contiguous bytes
+          __stcs(reinterpret_cast<float2*>(x2d + (static_cast<long long>(c) * N + p0 + lp) * 32) + j,
+                 make_float2((u - m2x) * i2x, (v - m2y) * i2y));
+        }
+        if (y3d && has3) {
+          float X0, X1, X2, H0, H1, H2;
+          world_to_cam(a.cam[c], qx, qy, qz, X0, X1, X2);
+          world_to_cam(a.cam[c], hx, hy, hz, H0, H1, H2);     // root (hip) for postprocess_3d
+          float* o = s3 + (c * PPB + lp) * out3 + 3 * j;
+          o[0] = ((X0 - H0) - m3[0]) * i3[0];
+          o[1] = ((X1 - H1) - m3[1]) * i3[1];
+          o[2] = ((X2 - H2) - m3[2]) * i3[2];
         }
       }
-      __syncthreads();
+    }
+    __syncthreads();                       // sw fully consumed; s3 complete
+    if (y3d) {
+      const int tot = np * out3;
+      for (int c = 0; c < a.ncams; ++c) {
+        float* dst = y3d + (static_cast<long long>(c) * N + p0) * out3;
+        const float* srcs = s3 + c * PPB * out3;
+        if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (tot % 4 == 0)) {
+          for (int i = tid; i < tot / 4; i += 256) __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(srcs)[i]);
+        } else {
+          for (int i = tid; i < tot; i += 256) __stcs(dst + i, srcs[i]);
+        }
+      }
     }
   }
 }
@@ -281,7 +293,7 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
     for (int d = 0; d < n; ++d) { a.mean3[d] = (float)mean3d[use[d]]; a.istd3[d] = (float)(1.0 / std3d[use[d]]); }
   }
   long long ntiles = (N + PPB - 1) / PPB;
-  int grid = ntiles < 148 * 8 ? (int)ntiles : 148 * 8;
+  int grid = ntiles < 148 * 16 ? (int)ntiles : 148 * 16;
   project_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(world, a, x2d, y3d, N);
   P3D_LAUNCH_CHECK();
   return P3D_OK;

@@ -66,50 +66,93 @@ P3D_HD void jacobi_rot(double app, double aqq, double apq, double& c, double& s)
   c = 1.0 / sqrt(t * t + 1.0);
   s = t * c;
 }
+P3D_HD void jacobi_rot_f(float app, float aqq, float apq, float& c, float& s) {
+  if (apq == 0.0f) { c = 1.0f; s = 0.0f; return; }
+  const float theta = (aqq - app) / (2.0f * apq);
+  const float t = (theta >= 0.0f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+  c = 1.0f / sqrtf(t * t + 1.0f);
+  s = t * c;
+}
+
+#if defined(__CUDA_ARCH__)
+#define P3D_UNROLL _Pragma("unroll")
+#else
+#define P3D_UNROLL
+#endif
+
+// one cyclic Jacobi sweep (rotations (0,1), (0,2), (1,2)) on symmetric S, accumulating V <- V J
+template <typename T, typename ROT>
+P3D_HD void jacobi_sweep(T S[3][3], T V[3][3], ROT rot) {
+  P3D_UNROLL
+  for (int r = 0; r < 3; ++r) {
+    const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
+    T c, s;
+    rot(S[p][p], S[q][q], S[p][q], c, s);
+    P3D_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      const T skp = S[k][p], skq = S[k][q];
+      S[k][p] = c * skp - s * skq;
+      S[k][q] = s * skp + c * skq;
+    }
+    P3D_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      const T spk = S[p][k], sqk = S[q][k];
+      S[p][k] = c * spk - s * sqk;
+      S[q][k] = s * spk + c * sqk;
+    }
+    P3D_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      const T vkp = V[k][p], vkq = V[k][q];
+      V[k][p] = c * vkp - s * vkq;
+      V[k][q] = s * vkp + c * vkq;
+    }
+  }
+}
 
 P3D_HD void kabsch_rotation(const double A[9], double T[9], double& tr) {
-  // S = A^T A
+  // S = A^T A (symmetric, fp64)
   double S[3][3];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) S[i][j] = A[0 * 3 + i] * A[0 * 3 + j] + A[1 * 3 + i] * A[1 * 3 + j] + A[2 * 3 + i] * A[2 * 3 + j];
-  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int sweep = 0; sweep < 12; ++sweep) {
+  // Stage 1 (cheap): approximate eigenvectors by 5 Jacobi sweeps in fp32 (fp64 sqrt/div are ~30-instruction
+  // software sequences on the GPU; doing all ~18 rotations in fp64 made the evaluation kernel compute bound)
+  float Sf[3][3], Vf[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Sf[i][j] = static_cast<float>(S[i][j]);
+  for (int sweep = 0; sweep < 5; ++sweep) {
+    const float off = fabsf(Sf[0][1]) + fabsf(Sf[0][2]) + fabsf(Sf[1][2]);
+    const float diag = fabsf(Sf[0][0]) + fabsf(Sf[1][1]) + fabsf(Sf[2][2]);
+    if (off <= 1e-9f * diag) break;
+    jacobi_sweep<float>(Sf, Vf, [](float a, float b, float c, float& cc, float& ss) { jacobi_rot_f(a, b, c, cc, ss); });
+  }
+  // Stage 2: re-orthonormalise the fp32 basis in fp64 (Gram-Schmidt), rotate S into it, and polish with
+  // fp64 Jacobi sweeps (quadratic convergence: one sweep takes the ~1e-7 residual below 1e-13)
+  double V[3][3];
+  {
+    double a0[3] = {Vf[0][0], Vf[1][0], Vf[2][0]}, a1[3] = {Vf[0][1], Vf[1][1], Vf[2][1]};
+    const double n0 = 1.0 / sqrt(a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2]);
+    for (int i = 0; i < 3; ++i) a0[i] *= n0;
+    const double d01 = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
+    for (int i = 0; i < 3; ++i) a1[i] -= d01 * a0[i];
+    const double n1 = 1.0 / sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+    for (int i = 0; i < 3; ++i) a1[i] *= n1;
+    const double a2[3] = {a0[1] * a1[2] - a0[2] * a1[1], a0[2] * a1[0] - a0[0] * a1[2], a0[0] * a1[1] - a0[1] * a1[0]};
+    for (int i = 0; i < 3; ++i) { V[i][0] = a0[i]; V[i][1] = a1[i]; V[i][2] = a2[i]; }
+  }
+  {
+    double SV[3][3], S1[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) SV[i][j] = S[i][0] * V[0][j] + S[i][1] * V[1][j] + S[i][2] * V[2][j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) S1[i][j] = V[0][i] * SV[0][j] + V[1][i] * SV[1][j] + V[2][i] * SV[2][j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) S[i][j] = (i <= j) ? S1[i][j] : S1[j][i];   // keep exactly symmetric
+  }
+  for (int sweep = 0; sweep < 6; ++sweep) {
     const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
     const double diag = fabs(S[0][0]) + fabs(S[1][1]) + fabs(S[2][2]);
     if (off <= 1e-17 * diag) break;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int r = 0; r < 3; ++r) {
-      const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;   // (0,1), (0,2), (1,2)
-      double c, s;
-      jacobi_rot(S[p][p], S[q][q], S[p][q], c, s);
-      // S <- J^T S J with J = [[c, s], [-s, c]] on (p,q);  V <- V J
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int k = 0; k < 3; ++k) {
-        const double skp = S[k][p], skq = S[k][q];
-        S[k][p] = c * skp - s * skq;
-        S[k][q] = s * skp + c * skq;
-      }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int k = 0; k < 3; ++k) {
-        const double spk = S[p][k], sqk = S[q][k];
-        S[p][k] = c * spk - s * sqk;
-        S[q][k] = s * spk + c * sqk;
-      }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int k = 0; k < 3; ++k) {
-        const double vkp = V[k][p], vkq = V[k][q];
-        V[k][p] = c * vkp - s * vkq;
-        V[k][q] = s * vkp + c * vkq;
-      }
-    }
+    jacobi_sweep<double>(S, V, [](double a, double b, double c, double& cc, double& ss) { jacobi_rot(a, b, c, cc, ss); });
   }
   // two largest eigenpairs by compare-and-swap of (eigenvalue, column) with constant indices
   double l0 = S[0][0], l1 = S[1][1], l2 = S[2][2];
