@@ -340,9 +340,28 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # The contract is ONE JSON line on stdout: libraries (NCCL's version banner, torchrun notices) also write to
+    # fd 1, so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("{"):
+            _print(*a, file=real_stdout, **k)
+            real_stdout.flush()
+        else:
+            _print(*a, **k)
+    builtins.print = emit
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_ours(args)
+    finally:
+        builtins.print = _print
 
 
 if __name__ == "__main__":

@@ -205,3 +205,17 @@ def test_host_step_pinned_and_pageable_agree():
     del xp
     _lib.check(_lib.lib.p3d_host_free(ptr))
     m.close()
+
+
+def test_width_4096_stress_config():
+    """BASELINE configs[4]: linear_size=4096, num_layers=4 (134.6 M weights = 269 MB bf16 > L2): the same kernel,
+    16 chunks x 64 K-slices per layer, 64 slab barriers."""
+    cfg = M.Config(4096, 4, True, True, True)
+    m, p = make_model(cfg, seed=13, bn="trained", mode="bf16")
+    x, t = synth.mlp_inputs(300, seed=3)
+    _, _, y = m.step(None, x, t, 1.0, isTraining=False)
+    ref = M.forward(p, x.astype(np.float64), cfg, training=False)
+    emu = emulate_bf16_forward(p, x, cfg)
+    assert_matches_emulation(y, emu, np.sqrt(np.mean(ref ** 2)), ref)
+    assert rowwise_rel(y, ref).max() <= 1e-2
+    m.close()
