@@ -23,7 +23,8 @@ namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const flo
 namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t);
                int debug_umma_gemm(const void*, const void*, float*, int, int, cudaStream_t); }
 namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
-                 int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t); }
+                 int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t);
+                 int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t); }
 namespace train { void free_workspace(p3d_model*); }
 
 constexpr int kSmallBatchMax = 16;   // rows served by the latency (GEMV) path
@@ -255,7 +256,7 @@ void p3d_model_destroy(p3d_model* m) {
   train::free_workspace(m);
   cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
   cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
-  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a);
+  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter);
   for (int i = 0; i < 3; ++i) {
     if (m->pipe_streams[i]) cudaStreamDestroy(m->pipe_streams[i]);
     cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
@@ -324,7 +325,7 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
   if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
   if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
   if (B <= kSmallBatchMax || (m->L % 256) != 0) {
-    if (B <= kSmallBatchMax) return simt::forward_small(m, x, y, B, st);
+    if (B <= kSmallBatchMax) return (m->L == 1024) ? simt::forward_latency(m, x, y, B, st) : simt::forward_small(m, x, y, B, st);
     return simt::forward_fp32(m, x, y, B, st);   // widths the tensor-core tiling does not cover
   }
   if (m->xb_cap < B) {

@@ -147,6 +147,8 @@ struct p3d_model {
   int act_grid = 0;
   __nv_bfloat16* xb = nullptr;           // packed input [cap][64]
   int64_t xb_cap = 0;
+  unsigned long long* lat_counter = nullptr;   // grid-barrier counter of the latency kernel (monotonic)
+  unsigned long long lat_base = 0;
   float* f32_a = nullptr;                // fp32-path activations [3][cap][L]
   int64_t f32_cap = 0;
   // host-step pipeline

@@ -198,6 +198,149 @@ __global__ void __launch_bounds__(256) small_batch_layer_kernel(const float* __r
   }
 }
 
+// Latency path, one launch: a cooperative persistent kernel walks all layers; the grid synchronises between
+// layers with a monotonic global counter (no reset needed: the host passes a per-launch epoch).  The bf16
+// weight row of the NEXT layer is prefetched into registers before the barrier, so a layer costs one barrier
+// plus one L2 round trip for the activations.
+struct LatArgs {
+  const float* x; float* y; const __nv_bfloat16* wt; const float* bias; float* hP; float* hQ;
+  unsigned long long* counter; unsigned long long base;   // barrier counter value at kernel entry
+  int rows, L, nlayers, out, kpad, residual;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ull);
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < target) {
+      if (++spins > (1u << 26)) { printf("p3d: grid barrier timeout block=%d\n", (int)blockIdx.x); __trap(); }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int ROWS, int KW>   // KW = uint4 weight words per lane = K / 256
+__global__ void __launch_bounds__(256) latency_forward_kernel(const LatArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int L = a.L;
+  uint4 wreg[KW];
+  // layer 0 weights (K = 32 -> lanes 0..3)
+  {
+    const int n = gw;
+    if (n < L && lane < 4) wreg[0] = __ldg(reinterpret_cast<const uint4*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 8));
+  }
+  unsigned long long target = a.base;
+  int row_off = 0;
+  for (int l = 0; l < a.nlayers; ++l) {
+    const bool first = (l == 0), last = (l == a.nlayers - 1);
+    const int K = first ? kIn : L, N = last ? a.out : L;
+    const float* hin = first ? a.x : ((l & 1) ? a.hP : a.hQ);
+    const int ldin = first ? kIn : L;
+    float* hout = last ? a.y : ((first || !(l & 1)) ? a.hP : a.hQ);
+    const int ldout = last ? a.out : L;
+    const float* res = (!last && a.residual && l >= 2 && !(l & 1)) ? a.hP : nullptr;
+    for (int n = gw; n < N; n += nw) {
+      if (n != gw) {       // rows beyond the prefetched one (only when N > number of warps)
+        const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + n) * a.kpad;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) if (lane * 8 + i * 256 < K) wreg[i] = __ldg(reinterpret_cast<const uint4*>(wrow + lane * 8 + i * 256));
+      }
+      float acc[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < KW; ++i) {
+        const int k = lane * 8 + i * 256;
+        if (k < K) {
+          const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wreg[i]);
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { w[2 * j] = __low2float(w2[j]); w[2 * j + 1] = __high2float(w2[j]); }
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r) {
+            if (r < a.rows) {
+              const float4 u = __ldcg(reinterpret_cast<const float4*>(hin + static_cast<size_t>(r) * ldin + k));
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(hin + static_cast<size_t>(r) * ldin + k + 4));
+              acc[r] = fmaf(u.x, w[0], acc[r]); acc[r] = fmaf(u.y, w[1], acc[r]); acc[r] = fmaf(u.z, w[2], acc[r]); acc[r] = fmaf(u.w, w[3], acc[r]);
+              acc[r] = fmaf(v.x, w[4], acc[r]); acc[r] = fmaf(v.y, w[5], acc[r]); acc[r] = fmaf(v.z, w[6], acc[r]); acc[r] = fmaf(v.w, w[7], acc[r]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        float v = acc[r];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && r < a.rows) {
+          v += __ldg(a.bias + row_off + n);
+          if (!last) v = fmaxf(v, 0.f);
+          if (res) v += __ldcg(res + static_cast<size_t>(r) * ldout + n);
+          __stcg(hout + static_cast<size_t>(r) * ldout + n, v);
+        }
+      }
+    }
+    row_off += N;
+    if (last) break;
+    // prefetch my first weight row of the next layer, then synchronise the grid
+    {
+      const int Nn = (l + 1 == a.nlayers - 1) ? a.out : L;
+      if (gw < Nn) {
+        const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + gw) * a.kpad;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) wreg[i] = __ldg(reinterpret_cast<const uint4*>(wrow + lane * 8 + i * 256));
+      }
+    }
+    target += gridDim.x;
+    grid_barrier(a.counter, target);
+  }
+}
+
+template <int ROWS, int KW>
+static int launch_latency(p3d_model* m, LatArgs& a, cudaStream_t st) {
+  static int grid = 0;
+  if (!grid) {
+    int per_sm = 0;
+    P3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latency_forward_kernel<ROWS, KW>, 256, 0));
+    P3D_REQUIRE(per_sm >= 1, "latency kernel does not fit on an SM");
+    grid = m->num_sms;                      // one block per SM: 8 warps x 148 = 1184 warps >= 1024 outputs
+  }
+  a.base = m->lat_base;
+  m->lat_base += static_cast<unsigned long long>(grid) * (a.nlayers - 1);
+  void* params[] = {&a};
+  P3D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(latency_forward_kernel<ROWS, KW>), dim3(grid), dim3(256), params, 0, st));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
+  const int L = m->L;
+  if (m->f32_cap < SB_ROWS) {
+    if (m->f32_a) cudaFree(m->f32_a);
+    m->f32_a = nullptr; m->f32_cap = 0;
+    P3D_CUDA(cudaMalloc(&m->f32_a, sizeof(float) * 2ull * SB_ROWS * L));
+    m->f32_cap = SB_ROWS;
+  }
+  if (!m->lat_counter) {
+    P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long)));
+    P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long)));
+  }
+  for (int64_t r0 = 0; r0 < B; r0 += SB_ROWS) {
+    LatArgs a;
+    a.rows = static_cast<int>(B - r0 < SB_ROWS ? B - r0 : SB_ROWS);
+    a.x = x + r0 * kIn; a.y = y + r0 * m->out_size; a.wt = m->wt_bf16; a.bias = m->bias_fold;
+    a.hP = m->f32_a; a.hQ = m->f32_a + static_cast<size_t>(m->f32_cap) * L;
+    a.counter = m->lat_counter; a.L = L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size;
+    a.kpad = m->kpad; a.residual = m->cfg.residual;
+    if (a.rows == 1) P3D_TRY((launch_latency<1, 4>(m, a, st)));
+    else P3D_TRY((launch_latency<SB_ROWS, 4>(m, a, st)));
+  }
+  return P3D_OK;
+}
+
 int forward_small(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
   const int L = m->L;
   if (m->f32_cap < SB_ROWS) {
