@@ -1,6 +1,8 @@
 // FP32 (FFMA) kernels: the "fp32 mode" forward (<=1e-4 of the fp64 oracle), the small-batch
 // (latency) forward and the generic SGEMM the training step is built from.
 // Same graph as mlp_tc.cu: src/linear_model.py:102-125,154-201.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace p3d {
@@ -222,8 +224,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
   __syncthreads();
 }
 
-template <int ROWS, int KW>   // KW = uint4 weight words per lane = K / 256
-__global__ void __launch_bounds__(256) latency_forward_kernel(const LatArgs a) {
+template <int ROWS, int KW, int NT>   // KW = uint4 weight words per lane = K / 256, NT = threads per block
+__global__ void __launch_bounds__(NT) latency_forward_kernel(const LatArgs a) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int L = a.L;
@@ -299,19 +301,27 @@ __global__ void __launch_bounds__(256) latency_forward_kernel(const LatArgs a) {
   }
 }
 
-template <int ROWS, int KW>
+template <int ROWS, int KW, int NT>
 static int launch_latency(p3d_model* m, LatArgs& a, cudaStream_t st) {
-  static int grid = 0;
+  static int grid = 0, coop = 1;
   if (!grid) {
     int per_sm = 0;
-    P3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latency_forward_kernel<ROWS, KW>, 256, 0));
+    P3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latency_forward_kernel<ROWS, KW, NT>, NT, 0));
     P3D_REQUIRE(per_sm >= 1, "latency kernel does not fit on an SM");
-    grid = m->num_sms;                      // one block per SM: 8 warps x 148 = 1184 warps >= 1024 outputs
+    // enough warps for one output feature each (L warps), never more blocks than SMs (all must be co-resident)
+    grid = (a.L * 32 + NT - 1) / NT;
+    if (grid > m->num_sms) grid = m->num_sms;
+    if (const char* e = getenv("P3D_LAT_GRID")) { const int g = atoi(e); if (g >= 1 && g <= m->num_sms) grid = g; }
+    if (const char* e = getenv("P3D_LAT_COOP")) coop = atoi(e);
   }
   a.base = m->lat_base;
   m->lat_base += static_cast<unsigned long long>(grid) * (a.nlayers - 1);
-  void* params[] = {&a};
-  P3D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(latency_forward_kernel<ROWS, KW>), dim3(grid), dim3(256), params, 0, st));
+  if (coop) {
+    void* params[] = {&a};
+    P3D_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(latency_forward_kernel<ROWS, KW, NT>), dim3(grid), dim3(NT), params, 0, st));
+  } else {
+    latency_forward_kernel<ROWS, KW, NT><<<grid, NT, 0, st>>>(a);
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -335,8 +345,16 @@ int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStrea
     a.hP = m->f32_a; a.hQ = m->f32_a + static_cast<size_t>(m->f32_cap) * L;
     a.counter = m->lat_counter; a.L = L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size;
     a.kpad = m->kpad; a.residual = m->cfg.residual;
-    if (a.rows == 1) P3D_TRY((launch_latency<1, 4>(m, a, st)));
-    else P3D_TRY((launch_latency<SB_ROWS, 4>(m, a, st)));
+    static int nt = 0;
+    if (!nt) { const char* e = getenv("P3D_LAT_THREADS"); nt = e ? atoi(e) : 1024; }
+    if (a.rows == 1) {
+      if (nt == 256) P3D_TRY((launch_latency<1, 4, 256>(m, a, st)));
+      else if (nt == 512) P3D_TRY((launch_latency<1, 4, 512>(m, a, st)));
+      else P3D_TRY((launch_latency<1, 4, 1024>(m, a, st)));
+    } else {
+      if (nt == 256) P3D_TRY((launch_latency<SB_ROWS, 4, 256>(m, a, st)));
+      else P3D_TRY((launch_latency<SB_ROWS, 4, 512>(m, a, st)));
+    }
   }
   return P3D_OK;
 }
