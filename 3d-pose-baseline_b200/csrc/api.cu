@@ -1,5 +1,6 @@
 // C ABI of libp3d.so (see include/p3d.h): model lifetime, variables by TF name, forward dispatch,
 // the host-buffer evaluation step, misc.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -24,7 +25,8 @@ namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_
                int debug_umma_gemm(const void*, const void*, float*, int, int, cudaStream_t); }
 namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t);
-                 int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t); }
+                 int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t);
+                 int forward_latency_cluster(p3d_model*, const float*, float*, cudaStream_t); }
 namespace train { void free_workspace(p3d_model*); }
 
 constexpr int kSmallBatchMax = 16;   // rows served by the latency (GEMV) path
@@ -325,7 +327,15 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
   if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
   if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
   if (B <= kSmallBatchMax || (m->L % 256) != 0) {
-    if (B <= kSmallBatchMax) return (m->L == 1024) ? simt::forward_latency(m, x, y, B, st) : simt::forward_small(m, x, y, B, st);
+    if (B <= kSmallBatchMax) {
+      if (B == 1 && m->L == 1024) {                     // single pose: 16-CTA cluster kernel, one launch
+        const int rc = simt::forward_latency_cluster(m, x, y, st);
+        if (rc <= 0) return rc;                          // 1 = cluster of 16 not schedulable here -> per-layer kernels
+      }
+      static const bool coop = getenv("P3D_LAT_COOPGRID") != nullptr;   // experimental grid-barrier variant (slower: ~35 us)
+      if (coop && m->L == 1024) return simt::forward_latency(m, x, y, B, st);
+      return simt::forward_small(m, x, y, B, st);
+    }
     return simt::forward_fp32(m, x, y, B, st);   // widths the tensor-core tiling does not cover
   }
   if (m->xb_cap < B) {

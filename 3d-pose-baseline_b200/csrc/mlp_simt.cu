@@ -359,6 +359,145 @@ int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStrea
   return P3D_OK;
 }
 
+// ----------------------------------------------------------------------------- batch-1 cluster kernel
+// One 16-CTA thread-block cluster (non-portable size) serves a single pose: every CTA owns 1/16 of each
+// layer's output features, keeps the FULL activation vector in its own shared memory and pushes its 64 results
+// into all 16 CTAs' shared memory (st.shared::cluster), followed by a hardware cluster barrier (~0.3 us instead
+// of ~3 us of L2 round trips for a grid-wide barrier).  The bf16 weight rows of the NEXT layer are prefetched
+// into registers while the current layer computes, so every weight byte crosses L2->SM once, off the
+// critical path.  L = 1024 only (64 features per CTA, 2 per warp).
+constexpr int LC = 16;            // cluster size
+constexpr int LNT = 1024;         // threads per CTA (32 warps)
+
+__device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(float* local, uint32_t cta, float v) {
+  const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local));
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}"
+               ::"r"(la), "r"(cta), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a) {
+  constexpr int L = 1024, OPW = L / (LC * 32);     // 2 outputs per warp
+  __shared__ __align__(16) float sP[L];
+  __shared__ __align__(16) float sQ[L];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t rank = cl_rank();
+  const int n0 = (static_cast<int>(rank) * 32 + warp) * OPW;     // my first output feature
+  // x -> sQ[0..31] (layer 0 reads "Q"), then the layer loop: even layers Q -> P, odd layers P -> Q
+  if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
+  uint2 wreg[OPW][8];
+  float breg[OPW];
+  // layer 0 weights: K = 32 -> lanes 0..7, one uint2 (4 bf16) each
+#pragma unroll
+  for (int o = 0; o < OPW; ++o) {
+    if (lane < 8) wreg[o][0] = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n0 + o) * a.kpad + lane * 4));
+    breg[o] = __ldg(a.bias + n0 + o);
+  }
+  __syncthreads();
+  int row_off = 0;
+  for (int l = 0; l < a.nlayers; ++l) {
+    const bool first = (l == 0), last = (l == a.nlayers - 1);
+    const int K = first ? kIn : L;
+    const float* src = (l & 1) ? sP : sQ;
+    float* dst = (l & 1) ? sQ : sP;
+    const bool add_res = a.residual && !last && l >= 2 && !(l & 1);
+    // ---- this layer's dot products (weights already in registers)
+    float acc[OPW];
+#pragma unroll
+    for (int o = 0; o < OPW; ++o) acc[o] = 0.f;
+    const int gwarp = static_cast<int>(rank) * 32 + warp;
+    const bool active = last ? (gwarp < a.out) : true;        // output layer: one feature per warp, 48 warps
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = i * 128 + lane * 4;
+        if (k < K) {
+          const float4 h = *reinterpret_cast<const float4*>(src + k);
+#pragma unroll
+          for (int o = 0; o < OPW; ++o) {
+            if (last && o > 0) continue;
+            const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wreg[o][i]);
+            acc[o] = fmaf(h.x, __low2float(w2[0]), acc[o]); acc[o] = fmaf(h.y, __high2float(w2[0]), acc[o]);
+            acc[o] = fmaf(h.z, __low2float(w2[1]), acc[o]); acc[o] = fmaf(h.w, __high2float(w2[1]), acc[o]);
+          }
+        }
+      }
+    }
+    float outv[OPW];
+#pragma unroll
+    for (int o = 0; o < OPW; ++o) {
+      float v = acc[o];
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      v += breg[o];
+      if (!last) v = fmaxf(v, 0.f);
+      if (add_res) v += sP[n0 + o];
+      outv[o] = v;
+    }
+    if (last) {
+      if (active && lane == 0) a.y[gwarp] = outv[0];
+      break;
+    }
+    // ---- prefetch the next layer's weights + bias (independent of the activations being exchanged)
+    row_off += L;
+    {
+      const bool nlast = (l + 1 == a.nlayers - 1);
+      if (!nlast) {
+#pragma unroll
+        for (int o = 0; o < OPW; ++o) {
+          const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + n0 + o) * a.kpad;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wreg[o][i] = __ldg(reinterpret_cast<const uint2*>(wrow + i * 128 + lane * 4));
+          breg[o] = __ldg(a.bias + row_off + n0 + o);
+        }
+      } else if (gwarp < a.out) {
+        const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + gwarp) * a.kpad;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wreg[0][i] = __ldg(reinterpret_cast<const uint2*>(wrow + i * 128 + lane * 4));
+        breg[0] = __ldg(a.bias + row_off + gwarp);
+      }
+    }
+    // ---- push my OPW results into every CTA's copy of the destination vector (lane c -> CTA c)
+    if (lane < LC) {
+#pragma unroll
+      for (int o = 0; o < OPW; ++o) st_cluster_f32(dst + n0 + o, static_cast<uint32_t>(lane), outv[o]);
+    }
+    cl_sync();
+  }
+}
+
+int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) {
+  static int ok = -1;
+  if (ok < 0) {
+    ok = 0;
+    if (cudaFuncSetAttribute(latency_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = LC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, latency_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) ok = 1;
+    }
+    cudaGetLastError();
+    if (const char* e = getenv("P3D_LAT_CLUSTER")) ok = ok && atoi(e);
+  }
+  if (!ok) return 1;       // caller falls back to the per-layer kernels
+  LatArgs a;
+  a.rows = 1; a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.hP = a.hQ = nullptr; a.counter = nullptr; a.base = 0;
+  a.L = m->L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = LC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, latency_cluster_kernel, a));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 int forward_small(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
   const int L = m->L;
   if (m->f32_cap < SB_ROWS) {
