@@ -363,11 +363,16 @@ int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStrea
 // One 16-CTA thread-block cluster (non-portable size) serves a single pose: every CTA owns 1/16 of each
 // layer's output features, keeps the FULL activation vector in its own shared memory and pushes its 64 results
 // into all 16 CTAs' shared memory (st.shared::cluster), followed by a hardware cluster barrier (~0.3 us instead
-// of ~3 us of L2 round trips for a grid-wide barrier).  The bf16 weight rows of the NEXT layer are prefetched
-// into registers while the current layer computes, so every weight byte crosses L2->SM once, off the
-// critical path.  L = 1024 only (64 features per CTA, 2 per warp).
+// of ~3 us of L2 round trips for a grid-wide barrier).
+// Weights: the CTA's slice of a hidden layer is 64 rows x 2 KB = two contiguous 64 KB halves (one output per
+// warp each).  They are streamed by TMA bulk copies (cp.async.bulk) into a 3-slot shared-memory ring that is
+// kept full from the first instruction on, so the 512 KB per CTA cross L2->SM exactly once at the SM's full
+// ingest rate, off the critical path of the layer chain.  L = 1024 only.
 constexpr int LC = 16;            // cluster size
 constexpr int LNT = 1024;         // threads per CTA (32 warps)
+constexpr int LSLOTS = 3;
+constexpr int LHALF_BYTES = 32 * 1024 * 2;     // 32 rows x 1024 bf16
+constexpr int LAT_SMEM = LSLOTS * LHALF_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cl_sync() {
@@ -378,93 +383,137 @@ __device__ __forceinline__ void st_cluster_f32(float* local, uint32_t cta, float
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}"
                ::"r"(la), "r"(cta), "f"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void lat_mbar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_u32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void lat_mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm_u32(b)) : "memory"); }
+__device__ __forceinline__ void lat_mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(sm_u32(b)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) { printf("p3d: latency kernel mbarrier timeout\n"); __trap(); }
+  }
+}
+// 1D bulk copy global -> shared, completion (bytes) signalled on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a) {
-  constexpr int L = 1024, OPW = L / (LC * 32);     // 2 outputs per warp
+  constexpr int L = 1024;
+  extern __shared__ __align__(128) uint8_t lat_smem[];
   __shared__ __align__(16) float sP[L];
   __shared__ __align__(16) float sQ[L];
+  __shared__ uint64_t wfull[LSLOTS], wfree[LSLOTS];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lat_smem) + 127) & ~uintptr_t(127));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t rank = cl_rank();
-  const int n0 = (static_cast<int>(rank) * 32 + warp) * OPW;     // my first output feature
-  // x -> sQ[0..31] (layer 0 reads "Q"), then the layer loop: even layers Q -> P, odd layers P -> Q
-  if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
-  uint2 wreg[OPW][8];
-  float breg[OPW];
-  // layer 0 weights: K = 32 -> lanes 0..7, one uint2 (4 bf16) each
-#pragma unroll
-  for (int o = 0; o < OPW; ++o) {
-    if (lane < 8) wreg[o][0] = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n0 + o) * a.kpad + lane * 4));
-    breg[o] = __ldg(a.bias + n0 + o);
+  const int nhid = a.nlayers - 2;                 // hidden layers with L x L weights (layers 1 .. nlayers-2)
+  const int nhalves = 2 * nhid;                   // half h = (layer 1 + h/2, output o = h%2); rows n = rank*64 + o*32 + warp
+  auto half_src = [&](int h) {
+    const int l = 1 + (h >> 1), o = h & 1;
+    return a.wt + (static_cast<size_t>(l) * L + rank * 64 + o * 32) * a.kpad;
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LSLOTS; ++s) { lat_mbar_init(&wfull[s], 1); lat_mbar_init(&wfree[s], 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int h = 0; h < LSLOTS && h < nhalves; ++h) bulk_load(ring + h * LHALF_BYTES, half_src(h), LHALF_BYTES, &wfull[h]);
   }
+  // x -> sQ[0..31] (layer 0 reads "Q"); layer 0 weights (K = 32: lanes 0..7, 4 bf16 each) straight from L2
+  if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
+  uint2 w0[2]; float b0[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int n = static_cast<int>(rank) * 64 + o * 32 + warp;
+    w0[o] = make_uint2(0, 0);
+    if (lane < 8) w0[o] = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 4));
+    b0[o] = __ldg(a.bias + n);
+  }
+  // bias of the first hidden half is fetched one half ahead
+  float bnext = (nhalves > 0) ? __ldg(a.bias + L + rank * 64 + warp) : 0.f;
   __syncthreads();
-  int row_off = 0;
-  for (int l = 0; l < a.nlayers; ++l) {
-    const bool first = (l == 0), last = (l == a.nlayers - 1);
-    const int K = first ? kIn : L;
-    const float* src = (l & 1) ? sP : sQ;
-    float* dst = (l & 1) ? sQ : sP;
-    const bool add_res = a.residual && !last && l >= 2 && !(l & 1);
-    // ---- this layer's dot products (weights already in registers)
-    float acc[OPW];
+
+  // ---- layer 0 (reads x in sQ, writes sP): both outputs of this warp
+  {
+    float v[2];
 #pragma unroll
-    for (int o = 0; o < OPW; ++o) acc[o] = 0.f;
-    const int gwarp = static_cast<int>(rank) * 32 + warp;
-    const bool active = last ? (gwarp < a.out) : true;        // output layer: one feature per warp, 48 warps
-    if (active) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = i * 128 + lane * 4;
-        if (k < K) {
-          const float4 h = *reinterpret_cast<const float4*>(src + k);
-#pragma unroll
-          for (int o = 0; o < OPW; ++o) {
-            if (last && o > 0) continue;
-            const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wreg[o][i]);
-            acc[o] = fmaf(h.x, __low2float(w2[0]), acc[o]); acc[o] = fmaf(h.y, __high2float(w2[0]), acc[o]);
-            acc[o] = fmaf(h.z, __low2float(w2[1]), acc[o]); acc[o] = fmaf(h.w, __high2float(w2[1]), acc[o]);
-          }
-        }
+    for (int o = 0; o < 2; ++o) {
+      float acc = 0.f;
+      if (lane < 8) {
+        const float4 h = *reinterpret_cast<const float4*>(sQ + lane * 4);
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w0[o]);
+        acc = h.x * __low2float(w2[0]) + h.y * __high2float(w2[0]) + h.z * __low2float(w2[1]) + h.w * __high2float(w2[1]);
       }
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      v[o] = fmaxf(acc + b0[o], 0.f);
     }
-    float outv[OPW];
+    if (nhid > 0) {
+      if (lane < LC) {
 #pragma unroll
-    for (int o = 0; o < OPW; ++o) {
-      float v = acc[o];
-      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-      v += breg[o];
-      if (!last) v = fmaxf(v, 0.f);
-      if (add_res) v += sP[n0 + o];
-      outv[o] = v;
-    }
-    if (last) {
-      if (active && lane == 0) a.y[gwarp] = outv[0];
-      break;
-    }
-    // ---- prefetch the next layer's weights + bias (independent of the activations being exchanged)
-    row_off += L;
-    {
-      const bool nlast = (l + 1 == a.nlayers - 1);
-      if (!nlast) {
-#pragma unroll
-        for (int o = 0; o < OPW; ++o) {
-          const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + n0 + o) * a.kpad;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) wreg[o][i] = __ldg(reinterpret_cast<const uint2*>(wrow + i * 128 + lane * 4));
-          breg[o] = __ldg(a.bias + row_off + n0 + o);
-        }
-      } else if (gwarp < a.out) {
-        const __nv_bfloat16* wrow = a.wt + static_cast<size_t>(row_off + gwarp) * a.kpad;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wreg[0][i] = __ldg(reinterpret_cast<const uint2*>(wrow + i * 128 + lane * 4));
-        breg[0] = __ldg(a.bias + row_off + gwarp);
+        for (int o = 0; o < 2; ++o) st_cluster_f32(sP + rank * 64 + o * 32 + warp, static_cast<uint32_t>(lane), v[o]);
       }
-    }
-    // ---- push my OPW results into every CTA's copy of the destination vector (lane c -> CTA c)
-    if (lane < LC) {
-#pragma unroll
-      for (int o = 0; o < OPW; ++o) st_cluster_f32(dst + n0 + o, static_cast<uint32_t>(lane), outv[o]);
+    } else if (lane == 0) {        // no hidden layers: the output layer reads sP locally... (not a supported config here)
+      sP[rank * 64 + warp] = v[0]; sP[rank * 64 + 32 + warp] = v[1];
     }
     cl_sync();
+  }
+  // ---- hidden layers, one half (one output per warp) at a time from the smem ring
+  for (int h = 0; h < nhalves; ++h) {
+    const int l = 1 + (h >> 1), o = h & 1;
+    const int slot = h % LSLOTS;
+    const float* src = (l & 1) ? sP : sQ;
+    float* dst = (l & 1) ? sQ : sP;
+    const bool add_res = a.residual && l >= 2 && !(l & 1);
+    const int n = static_cast<int>(rank) * 64 + o * 32 + warp;
+    const float bias = bnext;
+    if (h + 1 < nhalves) bnext = __ldg(a.bias + (1 + ((h + 1) >> 1)) * L + rank * 64 + ((h + 1) & 1) * 32 + warp);
+    lat_mbar_wait(&wfull[slot], (h / LSLOTS) & 1);
+    const uint2* wrow = reinterpret_cast<const uint2*>(ring + slot * LHALF_BYTES + warp * 2048);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint2 wv = wrow[i * 32 + lane];                         // k = i*128 + lane*4 .. +3 : conflict-free
+      const float4 hv = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      acc = fmaf(hv.x, __low2float(w2[0]), acc); acc = fmaf(hv.y, __high2float(w2[0]), acc);
+      acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
+    }
+    __syncwarp();
+    if (lane == 0) lat_mbar_arrive(&wfree[slot]);                   // this warp is done with the slot
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    float v = fmaxf(acc + bias, 0.f);
+    if (add_res) v += sP[n];
+    // refill the slot with half h+3 as soon as all 32 warps have released it
+    if (threadIdx.x == 0 && h + LSLOTS < nhalves) {
+      lat_mbar_wait(&wfree[slot], (h / LSLOTS) & 1);
+      bulk_load(ring + slot * LHALF_BYTES, half_src(h + LSLOTS), LHALF_BYTES, &wfull[slot]);
+    }
+    __syncwarp();
+    if (lane < LC) st_cluster_f32(dst + n, static_cast<uint32_t>(lane), v);
+    if (o == 1) cl_sync();                                          // layer complete everywhere
+  }
+  // ---- output layer: feature g = rank*32 + warp < out, weights straight from L2 (3 rows per CTA)
+  {
+    const int l = a.nlayers - 1;
+    const int g = static_cast<int>(rank) * 32 + warp;
+    if (g < a.out) {
+      const float* src = (l & 1) ? sP : sQ;
+      const __nv_bfloat16* wrow = a.wt + (static_cast<size_t>(l) * L + g) * a.kpad;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint2 wv = __ldg(reinterpret_cast<const uint2*>(wrow + i * 128 + lane * 4));
+        const float4 hv = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+        acc = fmaf(hv.x, __low2float(w2[0]), acc); acc = fmaf(hv.y, __high2float(w2[0]), acc);
+        acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
+      }
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) a.y[g] = acc + __ldg(a.bias + l * L + g);
+    }
   }
 }
 
@@ -472,9 +521,10 @@ int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t
   static int ok = -1;
   if (ok < 0) {
     ok = 0;
-    if (cudaFuncSetAttribute(latency_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    if (cudaFuncSetAttribute(latency_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(latency_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM) == cudaSuccess) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT);
+      cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT); cfg.dynamicSmemBytes = LAT_SMEM;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = LC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
@@ -484,12 +534,12 @@ int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t
     cudaGetLastError();
     if (const char* e = getenv("P3D_LAT_CLUSTER")) ok = ok && atoi(e);
   }
-  if (!ok) return 1;       // caller falls back to the per-layer kernels
+  if (!ok || m->layers.size() < 3) return 1;       // caller falls back to the per-layer kernels
   LatArgs a;
   a.rows = 1; a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.hP = a.hQ = nullptr; a.counter = nullptr; a.base = 0;
   a.L = m->L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT); cfg.dynamicSmemBytes = LAT_SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = LC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
