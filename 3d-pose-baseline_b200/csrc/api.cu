@@ -426,6 +426,14 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
   return P3D_OK;
 }
 
+int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n) {
+  P3D_REQUIRE(m && out_host && n >= 1 && n <= 16, "latency_stamps: bad argument");
+  P3D_REQUIRE(m->lat_counter, "latency_stamps: the batch-1 kernel has not run (set P3D_LAT_STAMPS=1)");
+  P3D_CUDA(cudaDeviceSynchronize());
+  P3D_CUDA(cudaMemcpy(out_host, m->lat_counter + 8, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  return P3D_OK;
+}
+
 int p3d_debug_umma_gemm(const void* A, const void* W, float* C, int N, int K, void* stream) {
   P3D_REQUIRE(A && W && C, "debug_umma_gemm: null argument");
   return tc::debug_umma_gemm(A, W, C, N, K, static_cast<cudaStream_t>(stream));

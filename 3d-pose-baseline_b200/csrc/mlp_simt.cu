@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256) small_batch_layer_kernel(const float* __r
 struct LatArgs {
   const float* x; float* y; const __nv_bfloat16* wt; const float* bias; float* hP; float* hQ;
   unsigned long long* counter; unsigned long long base;   // barrier counter value at kernel entry
+  unsigned long long* stamps;                              // optional [16] globaltimer stamps (debug)
   int rows, L, nlayers, out, kpad, residual;
 };
 
@@ -335,15 +336,15 @@ int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStrea
     m->f32_cap = SB_ROWS;
   }
   if (!m->lat_counter) {
-    P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long)));
-    P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long)));
+    P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long) * 32));
+    P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long) * 32));
   }
   for (int64_t r0 = 0; r0 < B; r0 += SB_ROWS) {
     LatArgs a;
     a.rows = static_cast<int>(B - r0 < SB_ROWS ? B - r0 : SB_ROWS);
     a.x = x + r0 * kIn; a.y = y + r0 * m->out_size; a.wt = m->wt_bf16; a.bias = m->bias_fold;
     a.hP = m->f32_a; a.hQ = m->f32_a + static_cast<size_t>(m->f32_cap) * L;
-    a.counter = m->lat_counter; a.L = L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size;
+    a.counter = m->lat_counter; a.stamps = nullptr; a.L = L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size;
     a.kpad = m->kpad; a.residual = m->cfg.residual;
     static int nt = 0;
     if (!nt) { const char* e = getenv("P3D_LAT_THREADS"); nt = e ? atoi(e) : 1024; }
@@ -401,6 +402,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define LAT_STAMP(i) do { if (a.stamps && threadIdx.x == 0 && rank == 0) a.stamps[i] = gtimer(); } while (0)
+
 __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a) {
   constexpr int L = 1024;
   extern __shared__ __align__(128) uint8_t lat_smem[];
@@ -410,6 +414,7 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lat_smem) + 127) & ~uintptr_t(127));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t rank = cl_rank();
+  LAT_STAMP(0);
   const int nhid = a.nlayers - 2;                 // hidden layers with L x L weights (layers 1 .. nlayers-2)
   const int nhalves = 2 * nhid;                   // half h = (layer 1 + h/2, output o = h%2); rows n = rank*64 + o*32 + warp
   auto half_src = [&](int h) {
@@ -460,6 +465,7 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
     }
     cl_sync();
   }
+  LAT_STAMP(1);
   // ---- hidden layers, one half (one output per warp) at a time from the smem ring
   for (int h = 0; h < nhalves; ++h) {
     const int l = 1 + (h >> 1), o = h & 1;
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
     }
     __syncwarp();
     if (lane < LC) st_cluster_f32(dst + n, static_cast<uint32_t>(lane), v);
-    if (o == 1) cl_sync();                                          // layer complete everywhere
+    if (o == 1) { cl_sync(); LAT_STAMP(1 + l); }                   // layer complete everywhere
   }
   // ---- output layer: feature g = rank*32 + warp < out, weights straight from L2 (3 rows per CTA)
   {
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
       if (lane == 0) a.y[g] = acc + __ldg(a.bias + l * L + g);
     }
   }
+  LAT_STAMP(a.nlayers);
 }
 
 int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) {
@@ -536,7 +543,12 @@ int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t
   }
   if (!ok || m->layers.size() < 3) return 1;       // caller falls back to the per-layer kernels
   LatArgs a;
+  if (!m->lat_counter) {
+    P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long) * 32));
+    P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long) * 32));
+  }
   a.rows = 1; a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.hP = a.hQ = nullptr; a.counter = nullptr; a.base = 0;
+  a.stamps = getenv("P3D_LAT_STAMPS") ? m->lat_counter + 8 : nullptr;
   a.L = m->L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(LC); cfg.blockDim = dim3(LNT); cfg.dynamicSmemBytes = LAT_SMEM; cfg.stream = st;

@@ -170,6 +170,9 @@ int p3d_similarity_transform_f64(const double* X, const double* Y, int J, int co
 /* ---------------------------------------------------------------- debug / self-test -----------
  * One-CTA tcgen05 GEMM: C[128,N] = A[128,K] * W[N,K]^T, A/W bf16 row-major (K contiguous),
  * K % 64 == 0, N % 16 == 0, N <= 256.  Exercises TMA + UMMA descriptors + TMEM load in isolation. */
+/* globaltimer stamps (ns) of the batch-1 cluster kernel's last run (P3D_LAT_STAMPS=1): [0] entry, [1] after layer 0,
+ * [1+l] after hidden layer l, [nlayers] exit. */
+int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n);
 int p3d_debug_umma_gemm(const void* A_bf16, const void* W_bf16, float* C, int N, int K, void* stream);
 
 #ifdef __cplusplus

@@ -38,4 +38,10 @@ for B in [int(b) for b in (sys.argv[1:] or ["1", "8", "16"])]:
     torch.cuda.synchronize(); bb = (time.perf_counter() - t0) * 1e3
     print(f"B={B}: p50 device {statistics.median(ev):.1f} us, p50 wall {statistics.median(wall):.1f} us, back-to-back {bb:.1f} us/call "
           f"[grid={os.environ.get('P3D_LAT_GRID','auto')} threads={os.environ.get('P3D_LAT_THREADS','1024')} coop={os.environ.get('P3D_LAT_COOP','1')}]")
+if os.environ.get("P3D_LAT_STAMPS"):
+    import numpy as np
+    st_ = np.zeros(8, np.uint64)
+    _lib.check(lib.p3d_debug_latency_stamps(m._handle, st_.ctypes.data, 7))
+    d = (st_[1:7].astype(np.int64) - st_[0:6].astype(np.int64))
+    print("in-kernel phase times (ns): layer0+setup, hidden1..4, output:", d.tolist(), "total", int(st_[6] - st_[0]))
 m.close()
