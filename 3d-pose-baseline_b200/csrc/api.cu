@@ -427,7 +427,7 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
 }
 
 int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n) {
-  P3D_REQUIRE(m && out_host && n >= 1 && n <= 16, "latency_stamps: bad argument");
+  P3D_REQUIRE(m && out_host && n >= 1 && n <= 24, "latency_stamps: bad argument");
   P3D_REQUIRE(m->lat_counter, "latency_stamps: the batch-1 kernel has not run (set P3D_LAT_STAMPS=1)");
   P3D_CUDA(cudaDeviceSynchronize());
   P3D_CUDA(cudaMemcpy(out_host, m->lat_counter + 8, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));

@@ -370,10 +370,12 @@ int forward_latency(p3d_model* m, const float* x, float* y, int64_t B, cudaStrea
 // kept full from the first instruction on, so the 512 KB per CTA cross L2->SM exactly once at the SM's full
 // ingest rate, off the critical path of the layer chain.  L = 1024 only.
 constexpr int LC = 16;            // cluster size
-constexpr int LNT = 1024;         // threads per CTA (32 warps)
-constexpr int LSLOTS = 3;
-constexpr int LHALF_BYTES = 32 * 1024 * 2;     // 32 rows x 1024 bf16
-constexpr int LAT_SMEM = LSLOTS * LHALF_BYTES + 1024;
+constexpr int LNT = 512;          // threads per CTA (16 warps, 4 output features per warp and layer)
+constexpr int LNW = LNT / 32;
+constexpr int LOPW = 64 / LNW;    // outputs per warp per layer
+constexpr int LSLOTS = 6;
+constexpr int LPART_BYTES = LNW * 1024 * 2;    // one ring slot: LNW rows x 1024 bf16 = 32 KB
+constexpr int LAT_SMEM = LSLOTS * LPART_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cl_sync() {
@@ -395,11 +397,15 @@ __device__ __forceinline__ void lat_mbar_wait(uint64_t* b, uint32_t parity) {
     if (!ok && ++spins > (1u << 26)) { printf("p3d: latency kernel mbarrier timeout\n"); __trap(); }
   }
 }
-// 1D bulk copy global -> shared, completion (bytes) signalled on an mbarrier
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+// 1D bulk copy global -> shared, completion (bytes) signalled on an mbarrier.  The copy is issued as `pieces`
+// independent bulk operations: one operation has a small window of outstanding L2 requests (measured ~30 GB/s
+// per SM for a single 64 KB copy), many in flight reach the SM's ingest rate.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, int pieces = 16) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+  const uint32_t pb = bytes / pieces;
+  for (int i = 0; i < pieces; ++i)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sm_u32(dst) + i * pb), "l"(reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(i) * pb), "r"(pb), "r"(sm_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -416,95 +422,98 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
   const uint32_t rank = cl_rank();
   LAT_STAMP(0);
   const int nhid = a.nlayers - 2;                 // hidden layers with L x L weights (layers 1 .. nlayers-2)
-  const int nhalves = 2 * nhid;                   // half h = (layer 1 + h/2, output o = h%2); rows n = rank*64 + o*32 + warp
-  auto half_src = [&](int h) {
-    const int l = 1 + (h >> 1), o = h & 1;
-    return a.wt + (static_cast<size_t>(l) * L + rank * 64 + o * 32) * a.kpad;
+  const int nparts = LOPW * nhid;                 // part p = (layer 1 + p/LOPW, o = p%LOPW); rows n = rank*64 + o*LNW + warp
+  auto part_src = [&](int p) {
+    const int l = 1 + p / LOPW, o = p % LOPW;
+    return a.wt + (static_cast<size_t>(l) * L + rank * 64 + o * LNW) * a.kpad;
   };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < LSLOTS; ++s) { lat_mbar_init(&wfull[s], 1); lat_mbar_init(&wfree[s], 32); }
+    for (int s = 0; s < LSLOTS; ++s) { lat_mbar_init(&wfull[s], 1); lat_mbar_init(&wfree[s], LNW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int h = 0; h < LSLOTS && h < nhalves; ++h) bulk_load(ring + h * LHALF_BYTES, half_src(h), LHALF_BYTES, &wfull[h]);
+    for (int p = 0; p < LSLOTS && p < nparts; ++p) bulk_load(ring + p * LPART_BYTES, part_src(p), LPART_BYTES, &wfull[p], 4);
   }
   // x -> sQ[0..31] (layer 0 reads "Q"); layer 0 weights (K = 32: lanes 0..7, 4 bf16 each) straight from L2
   if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
-  uint2 w0[2]; float b0[2];
+  uint2 w0[LOPW]; float b0[LOPW];
 #pragma unroll
-  for (int o = 0; o < 2; ++o) {
-    const int n = static_cast<int>(rank) * 64 + o * 32 + warp;
+  for (int o = 0; o < LOPW; ++o) {
+    const int n = static_cast<int>(rank) * 64 + o * LNW + warp;
     w0[o] = make_uint2(0, 0);
     if (lane < 8) w0[o] = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 4));
     b0[o] = __ldg(a.bias + n);
   }
-  // bias of the first hidden half is fetched one half ahead
-  float bnext = (nhalves > 0) ? __ldg(a.bias + L + rank * 64 + warp) : 0.f;
+  float bias_next[LOPW];       // biases of the next hidden layer, fetched a layer ahead
+#pragma unroll
+  for (int o = 0; o < LOPW; ++o) bias_next[o] = (nhid > 0) ? __ldg(a.bias + L + rank * 64 + o * LNW + warp) : 0.f;
   __syncthreads();
 
-  // ---- layer 0 (reads x in sQ, writes sP): both outputs of this warp
+  // ---- layer 0 (reads x in sQ, writes sP)
   {
-    float v[2];
+    float hv4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < 8) { const float4 h = *reinterpret_cast<const float4*>(sQ + lane * 4); hv4[0] = h.x; hv4[1] = h.y; hv4[2] = h.z; hv4[3] = h.w; }
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      float acc = 0.f;
-      if (lane < 8) {
-        const float4 h = *reinterpret_cast<const float4*>(sQ + lane * 4);
-        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w0[o]);
-        acc = h.x * __low2float(w2[0]) + h.y * __high2float(w2[0]) + h.z * __low2float(w2[1]) + h.w * __high2float(w2[1]);
-      }
+    for (int o = 0; o < LOPW; ++o) {
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w0[o]);
+      float acc = hv4[0] * __low2float(w2[0]) + hv4[1] * __high2float(w2[0]) + hv4[2] * __low2float(w2[1]) + hv4[3] * __high2float(w2[1]);
       for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-      v[o] = fmaxf(acc + b0[o], 0.f);
-    }
-    if (nhid > 0) {
-      if (lane < LC) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o) st_cluster_f32(sP + rank * 64 + o * 32 + warp, static_cast<uint32_t>(lane), v[o]);
-      }
-    } else if (lane == 0) {        // no hidden layers: the output layer reads sP locally... (not a supported config here)
-      sP[rank * 64 + warp] = v[0]; sP[rank * 64 + 32 + warp] = v[1];
+      const float v = fmaxf(acc + b0[o], 0.f);
+      if (lane < LC) st_cluster_f32(sP + rank * 64 + o * LNW + warp, static_cast<uint32_t>(lane), v);
     }
     cl_sync();
   }
   LAT_STAMP(1);
-  // ---- hidden layers, one half (one output per warp) at a time from the smem ring
-  for (int h = 0; h < nhalves; ++h) {
-    const int l = 1 + (h >> 1), o = h & 1;
-    const int slot = h % LSLOTS;
+  // ---- hidden layers: activations in registers for the whole layer, weights from the smem ring
+  int p = 0;
+  for (int l = 1; l <= nhid; ++l) {
     const float* src = (l & 1) ? sP : sQ;
     float* dst = (l & 1) ? sQ : sP;
     const bool add_res = a.residual && l >= 2 && !(l & 1);
-    const int n = static_cast<int>(rank) * 64 + o * 32 + warp;
-    const float bias = bnext;
-    if (h + 1 < nhalves) bnext = __ldg(a.bias + (1 + ((h + 1) >> 1)) * L + rank * 64 + ((h + 1) & 1) * 32 + warp);
-    lat_mbar_wait(&wfull[slot], (h / LSLOTS) & 1);
-    const uint2* wrow = reinterpret_cast<const uint2*>(ring + slot * LHALF_BYTES + warp * 2048);
-    float acc = 0.f;
+    float4 hreg[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint2 wv = wrow[i * 32 + lane];                         // k = i*128 + lane*4 .. +3 : conflict-free
-      const float4 hv = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
-      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
-      acc = fmaf(hv.x, __low2float(w2[0]), acc); acc = fmaf(hv.y, __high2float(w2[0]), acc);
-      acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
+    for (int i = 0; i < 8; ++i) hreg[i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+    float bias[LOPW];
+#pragma unroll
+    for (int o = 0; o < LOPW; ++o) bias[o] = bias_next[o];
+    if (l < nhid) {
+#pragma unroll
+      for (int o = 0; o < LOPW; ++o) bias_next[o] = __ldg(a.bias + (l + 1) * L + rank * 64 + o * LNW + warp);
     }
-    __syncwarp();
-    if (lane == 0) lat_mbar_arrive(&wfree[slot]);                   // this warp is done with the slot
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    float v = fmaxf(acc + bias, 0.f);
-    if (add_res) v += sP[n];
-    // refill the slot with half h+3 as soon as all 32 warps have released it
-    if (threadIdx.x == 0 && h + LSLOTS < nhalves) {
-      lat_mbar_wait(&wfree[slot], (h / LSLOTS) & 1);
-      bulk_load(ring + slot * LHALF_BYTES, half_src(h + LSLOTS), LHALF_BYTES, &wfull[slot]);
+#pragma unroll 1
+    for (int o = 0; o < LOPW; ++o, ++p) {
+      const int slot = p % LSLOTS;
+      const int n = static_cast<int>(rank) * 64 + o * LNW + warp;
+      lat_mbar_wait(&wfull[slot], (p / LSLOTS) & 1);
+      const uint2* wrow = reinterpret_cast<const uint2*>(ring + slot * LPART_BYTES + warp * 2048);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint2 wv = wrow[i * 32 + lane];                         // k = i*128 + lane*4 .. +3 : conflict-free
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+        acc0 = fmaf(hreg[i].x, __low2float(w2[0]), acc0); acc1 = fmaf(hreg[i].y, __high2float(w2[0]), acc1);
+        acc0 = fmaf(hreg[i].z, __low2float(w2[1]), acc0); acc1 = fmaf(hreg[i].w, __high2float(w2[1]), acc1);
+      }
+      __syncwarp();
+      if (lane == 0) lat_mbar_arrive(&wfree[slot]);                   // this warp is done with the slot
+      float acc = acc0 + acc1;
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      float v = fmaxf(acc + (o == 0 ? bias[0] : o == 1 ? bias[1] : o == 2 ? bias[2] : bias[3]), 0.f);
+      if (add_res) v += sP[n];
+      if (lane < LC) st_cluster_f32(dst + n, static_cast<uint32_t>(lane), v);
+      // refill the slot with part p+LSLOTS as soon as all warps have released it
+      if (threadIdx.x == 0 && p + LSLOTS < nparts) {
+        lat_mbar_wait(&wfree[slot], (p / LSLOTS) & 1);
+        bulk_load(ring + slot * LPART_BYTES, part_src(p + LSLOTS), LPART_BYTES, &wfull[slot], 4);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    if (lane < LC) st_cluster_f32(dst + n, static_cast<uint32_t>(lane), v);
-    if (o == 1) { cl_sync(); LAT_STAMP(1 + l); }                   // layer complete everywhere
+    cl_sync();                                                        // layer complete everywhere
+    LAT_STAMP(1 + l);
   }
-  // ---- output layer: feature g = rank*32 + warp < out, weights straight from L2 (3 rows per CTA)
+  // ---- output layer: feature g = rank*LNW + warp < out, weights straight from L2
   {
     const int l = a.nlayers - 1;
-    const int g = static_cast<int>(rank) * 32 + warp;
+    const int g = static_cast<int>(rank) * LNW + warp;
     if (g < a.out) {
       const float* src = (l & 1) ? sP : sQ;
       const __nv_bfloat16* wrow = a.wt + (static_cast<size_t>(l) * L + g) * a.kpad;

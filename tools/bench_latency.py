@@ -40,7 +40,7 @@ for B in [int(b) for b in (sys.argv[1:] or ["1", "8", "16"])]:
           f"[grid={os.environ.get('P3D_LAT_GRID','auto')} threads={os.environ.get('P3D_LAT_THREADS','1024')} coop={os.environ.get('P3D_LAT_COOP','1')}]")
 if os.environ.get("P3D_LAT_STAMPS"):
     import numpy as np
-    st_ = np.zeros(8, np.uint64)
+    st_ = np.zeros(16, np.uint64)
     _lib.check(lib.p3d_debug_latency_stamps(m._handle, st_.ctypes.data, 7))
     d = (st_[1:7].astype(np.int64) - st_[0:6].astype(np.int64))
     print("in-kernel phase times (ns): layer0+setup, hidden1..4, output:", d.tolist(), "total", int(st_[6] - st_[0]))
