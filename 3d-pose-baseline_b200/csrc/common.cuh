@@ -115,6 +115,23 @@ struct Epilogue {
 int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
           int ldc, const Epilogue& e, cudaStream_t st);
 }  // namespace simt
+namespace tcg {
+// tcgen05 GEMM (tc_gemm.cu): C[M,N] (+)= alpha * A B^T-form product of bf16 operands, fp32 result.
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr; int lda = 0; int a_mn = 0;   // a_mn ? [K][M] : [M][K]  (bf16)
+  const void* B = nullptr; int ldb = 0; int b_mn = 0;   // b_mn ? [K][N] : [N][K]  (bf16)
+  float* C = nullptr; int ldc = 0;
+  const float* bias = nullptr;        // [N]
+  const float* res = nullptr; int ldres = 0;
+  const float* alpha_dev = nullptr;   // optional device scalar multiplied into alpha
+  float alpha = 1.f;
+  int split_k = 0;                    // split K over gridDim.z, fp32 atomics into C (C must hold the addend, e.g. zeros)
+  int accumulate = 0;                 // C += (atomics) even when unsplit
+  double* colsum = nullptr;           // optional [2][N] (+=): column sums of the result and of its square
+};
+int gemm(const GemmArgs& g, cudaStream_t st);
+}  // namespace tcg
 int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st);
 
 }  // namespace p3d

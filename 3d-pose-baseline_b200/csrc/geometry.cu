@@ -63,8 +63,6 @@ static inline int grid_for(long long n, int block = 256) {
 
 // ------------------------------------------------------------------ fused project + normalise
 constexpr int MAXCAMS = 8;
-constexpr int PPB = 16;   // poses per block (16 poses x 16 joints = 256 threads)
-
 struct FusedArgs {
   CamT<float> cam[MAXCAMS];
   float mean2[32], istd2[32];   // gathered to the used dims
@@ -75,14 +73,22 @@ struct FusedArgs {
   int predict_14;
 };
 
-__global__ void __launch_bounds__(256) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
-                                                               float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
-  __shared__ __align__(16) float sw[PPB * 96];
-  __shared__ __align__(16) float s3[MAXCAMS * PPB * 48];
-  const int tid = threadIdx.x;
-  const int lp = tid >> 4, j = tid & 15;   // local pose, joint slot
-  // per-thread constants (indexing the tables with a per-lane index inside the loop would serialise
-  // the constant cache 16 ways)
+// One WARP owns a pair of poses (lane = local pose * 16 + joint slot) and never meets a block barrier:
+//   world rows (2 x 384 B) : two coalesced float4 loads per lane, prefetched one pair ahead in registers,
+//                            staged in a 768 B per-warp smem slab for the 12-byte joint gathers
+//   2D output              : one float2 per lane per camera = 256 contiguous bytes per warp
+//   3D output              : 12-byte joint rows repacked through a double-buffered 384 B smem slab into
+//                            float4 stores (384 contiguous bytes per warp per camera)
+// The camera-frame root-centred joint is R(q - hip): T cancels, so the hip is subtracted once in world space.
+constexpr int PN_WARPS = 8;
+__global__ void __launch_bounds__(PN_WARPS * 32, 4) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
+                                                                            float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
+  __shared__ __align__(16) float s_in[PN_WARPS][2 * 96];
+  __shared__ __align__(16) float s_out[PN_WARPS][2][2 * 48];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lp = lane >> 4, j = lane & 15;
+  float* sw = s_in[wib];
+  // per-lane constants (indexing the tables with a per-lane index inside the loop would serialise the constant cache)
   const int j2 = kJoints2D[j];
   const bool has3 = j < a.nj3;
   const int j3 = has3 ? (a.predict_14 ? kJoints3D14[j] : kJoints3D16[j]) : 0;
@@ -91,52 +97,78 @@ __global__ void __launch_bounds__(256) project_normalize_kernel(const float* __r
 #pragma unroll
   for (int d = 0; d < 3; ++d) { m3[d] = has3 ? a.mean3[3 * j + d] : 0.f; i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; }
   const int out3 = a.out3;
-  const long long ntiles = (N + PPB - 1) / PPB;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long p0 = tile * PPB;
-    const int np = static_cast<int>((N - p0 < PPB) ? (N - p0) : PPB);
-    // coalesced stage-in of np*96 floats (rows are 384 B => float4 aligned)
-    const float4* src = reinterpret_cast<const float4*>(world + p0 * 96);
-    for (int i = tid; i < np * 24; i += 256) reinterpret_cast<float4*>(sw)[i] = __ldg(src + i);
-    __syncthreads();                       // also orders the previous tile's reads of s3 before this tile's writes
-    const bool live = lp < np;
-    if (live) {
-      const float* w = sw + lp * 96;
-      const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
-      const float qx = w[j3 * 3], qy = w[j3 * 3 + 1], qz = w[j3 * 3 + 2];
-      const float hx = w[0], hy = w[1], hz = w[2];
-      for (int c = 0; c < a.ncams; ++c) {
-        if (x2d) {
-          float u, v, d, ra, ta, r2;
-          project_point(a.cam[c], px, py, pz, u, v, d, ra, ta, r2);
-          // a warp = 2 poses x 16 joints writes 256 contiguous bytes
-          __stcs(reinterpret_cast<float2*>(x2d + (static_cast<long long>(c) * N + p0 + lp) * 32) + j,
+  const int pair_f4 = 2 * out3 / 4;                       // float4s per camera per pose pair (24 or 21)
+  const bool y_vec = y3d && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0);
+  const long long npairs = (N + 1) / 2;
+  const long long nwarps = static_cast<long long>(gridDim.x) * PN_WARPS;
+  const long long tot_f4 = N * 24;
+  const float4* src = reinterpret_cast<const float4*>(world);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long pair = static_cast<long long>(blockIdx.x) * PN_WARPS + wib;
+  float4 c0 = zero4, c1 = zero4;
+  if (pair < npairs) {
+    const long long b = pair * 48;
+    if (b + lane < tot_f4) c0 = __ldcs(src + b + lane);
+    if (lane < 16 && b + 32 + lane < tot_f4) c1 = __ldcs(src + b + 32 + lane);
+  }
+  int buf = 0;
+  for (; pair < npairs; pair += nwarps) {
+    // prefetch the next pair of this warp
+    float4 n0 = zero4, n1 = zero4;
+    {
+      const long long b = (pair + nwarps) * 48;
+      if (b + lane < tot_f4) n0 = __ldcs(src + b + lane);
+      if (lane < 16 && b + 32 + lane < tot_f4) n1 = __ldcs(src + b + 32 + lane);
+    }
+    reinterpret_cast<float4*>(sw)[lane] = c0;
+    if (lane < 16) reinterpret_cast<float4*>(sw)[32 + lane] = c1;
+    __syncwarp();
+    const long long p = pair * 2 + lp;
+    const bool live = p < N;
+    const float* w = sw + lp * 96;
+    const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
+    const float qx = w[j3 * 3] - w[0], qy = w[j3 * 3 + 1] - w[1], qz = w[j3 * 3 + 2] - w[2];
+    __syncwarp();                                    // slab consumed: the next iteration may overwrite it
+    for (int c = 0; c < a.ncams; ++c) {
+      const CamT<float>& cam = a.cam[c];
+      if (x2d) {
+        // cameras.project_point_radial (src/cameras.py:39-51) in fp32
+        const float dx = px - cam.Tr[0], dy = py - cam.Tr[1], dz = pz - cam.Tr[2];
+        const float X0 = cam.R[0] * dx + cam.R[1] * dy + cam.R[2] * dz;
+        const float X1 = cam.R[3] * dx + cam.R[4] * dy + cam.R[5] * dz;
+        const float X2 = cam.R[6] * dx + cam.R[7] * dy + cam.R[8] * dz;
+        const float rz = __frcp_rn(X2);
+        const float x = X0 * rz, y = X1 * rz;
+        const float r2 = x * x + y * y;
+        const float radial = 1.f + r2 * (cam.k[0] + r2 * (cam.k[1] + r2 * cam.k[2]));
+        const float s = radial + (cam.p[0] * y + cam.p[1] * x);
+        const float u = cam.f[0] * (x * s + cam.p[1] * r2) + cam.c[0];
+        const float v = cam.f[1] * (y * s + cam.p[0] * r2) + cam.c[1];
+        if (live)
+          __stcs(reinterpret_cast<float2*>(x2d + (static_cast<long long>(c) * N + p) * 32) + j,
                  make_float2((u - m2x) * i2x, (v - m2y) * i2y));
-        }
-        if (y3d && has3) {
-          float X0, X1, X2, H0, H1, H2;
-          world_to_cam(a.cam[c], qx, qy, qz, X0, X1, X2);
-          world_to_cam(a.cam[c], hx, hy, hz, H0, H1, H2);     // root (hip) for postprocess_3d
-          float* o = s3 + (c * PPB + lp) * out3 + 3 * j;
-          o[0] = ((X0 - H0) - m3[0]) * i3[0];
-          o[1] = ((X1 - H1) - m3[1]) * i3[1];
-          o[2] = ((X2 - H2) - m3[2]) * i3[2];
-        }
       }
-    }
-    __syncthreads();                       // sw fully consumed; s3 complete
-    if (y3d) {
-      const int tot = np * out3;
-      for (int c = 0; c < a.ncams; ++c) {
-        float* dst = y3d + (static_cast<long long>(c) * N + p0) * out3;
-        const float* srcs = s3 + c * PPB * out3;
-        if (((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (tot % 4 == 0)) {
-          for (int i = tid; i < tot / 4; i += 256) __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(srcs)[i]);
+      if (y3d) {
+        float* so = s_out[wib][buf];
+        if (has3) {
+          float* o = so + lp * out3 + 3 * j;
+          o[0] = ((cam.R[0] * qx + cam.R[1] * qy + cam.R[2] * qz) - m3[0]) * i3[0];
+          o[1] = ((cam.R[3] * qx + cam.R[4] * qy + cam.R[5] * qz) - m3[1]) * i3[1];
+          o[2] = ((cam.R[6] * qx + cam.R[7] * qy + cam.R[8] * qz) - m3[2]) * i3[2];
+        }
+        __syncwarp();
+        float* dst = y3d + (static_cast<long long>(c) * N + pair * 2) * out3;
+        const bool full = pair * 2 + 1 < N;
+        if (y_vec && full && ((pair * 2 * out3) & 3) == 0) {
+          if (lane < pair_f4) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(so)[lane]);
         } else {
-          for (int i = tid; i < tot; i += 256) __stcs(dst + i, srcs[i]);
+          const int tot = (full ? 2 : 1) * out3;
+          for (int i = lane; i < tot; i += 32) __stcs(dst + i, so[i]);
         }
+        buf ^= 1;                                    // the other slab is free: its readers passed the __syncwarp above
       }
     }
+    c0 = n0; c1 = n1;
   }
 }
 
@@ -292,9 +324,9 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
     P3D_TRY(use_table(3, predict_14, use, &n));
     for (int d = 0; d < n; ++d) { a.mean3[d] = (float)mean3d[use[d]]; a.istd3[d] = (float)(1.0 / std3d[use[d]]); }
   }
-  long long ntiles = (N + PPB - 1) / PPB;
-  int grid = ntiles < 148 * 16 ? (int)ntiles : 148 * 16;
-  project_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(world, a, x2d, y3d, N);
+  const long long nblocks = ((N + 1) / 2 + PN_WARPS - 1) / PN_WARPS;
+  const int grid = nblocks < 148 * 4 ? (int)nblocks : 148 * 4;
+  project_normalize_kernel<<<grid, PN_WARPS * 32, 0, (cudaStream_t)stream>>>(world, a, x2d, y3d, N);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -1,0 +1,286 @@
+// Generic tcgen05 GEMM for the training step (src/linear_model.py:129-145: the MatMuls of the forward
+// graph, of tf.gradients and of the weight gradients), bf16 operands, fp32 accumulation in TMEM.
+//
+//   C[M,N] (+)= alpha * sum_k A(m,k) B(n,k)  (+ bias[n]) (+ res[m,n])
+//
+// Each operand is described by how it lies in memory:
+//   K-major  : [rows = M or N][K contiguous]   (activations for Z = H W;  dZ and W for dH = dZ W^T)
+//   MN-major : [K rows][M or N contiguous]     (W for Z = H W;  H and dZ for dW = H^T dZ)
+// so the three GEMMs of a layer read H, dZ and W in their NATURAL row-major layouts - no transposed
+// copies exist anywhere.  MN-major tiles are fetched as 64-column TMA boxes (128B swizzle) and consumed
+// through the MN-major canonical UMMA layout ((8,n),(8,k)):((1,LBO),(8,SBO)) [16-byte units].
+//
+// One CTA per 128 x BN output tile (BN = 64/128/256 chosen per problem so the grid covers the SMs),
+// optional split-K over gridDim.z (fp32 atomics into a zeroed C - the weight-gradient GEMMs have only
+// (L/128)*(L/BN) tiles but K = batch).  Warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> alpha/bias/residual -> global).  Out-of-range rows/cols
+// and the K tail are zero-filled by TMA, so M, N, K need no padding (K=32 input layer, N=48 output).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace p3d {
+namespace tcg {
+
+using namespace ptx;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
+constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box = 8 KB
+constexpr int NTHREADS = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + 256;
+
+struct Params {
+  int M, N, K;
+  int bn;            // 64 / 128 / 256
+  int k_per_split;   // multiple of BK
+  int a_mn, b_mn;
+  float* C; int ldc;
+  const float* bias;        // [N] or null (added by split 0 only)
+  const float* res; int ldres;   // [M,N] or null (added by split 0 only)
+  const float* alpha_dev;   // optional device scalar
+  float alpha;
+  int atomic;               // accumulate into C with fp32 atomics (split-K)
+  double* colsum;           // optional [2][N]: column sums of the stored values and of their squares
+};
+
+// K-major operand, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_k(uint32_t smem_addr) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// MN-major operand, 128B swizzle: 64 MN-elements (128 B) contiguous, k rows 128 B apart, 8-k groups SBO = 1024 B
+// apart, the next 64 MN-elements LBO = one box (8 KB) further
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint32_t>(BOX_BYTES >> 4) << 16);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES_MAX);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accf = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    const uint32_t bytes = A_BYTES + p.bn * BK * 2;
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int k0 = kbeg + kb * BK;
+      mbar_wait(&empty[stage], phase ^ 1, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        uint8_t* a = sA + stage * A_BYTES;
+        uint8_t* b = sB + stage * B_BYTES_MAX;
+        if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
+        else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
+        if (!p.b_mn) tma_load_2d(b, &tm_b, &full[stage], k0, n0);
+        else for (int i = 0; i < p.bn / 64; ++i) tma_load_2d(b + i * BOX_BYTES, &tm_b, &full[stage], n0 + 64 * i, k0);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K=16 slice
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < nk; ++kb) {
+      mbar_wait(&full[stage], phase, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aa = a_base + stage * A_BYTES, bb = b_base + stage * B_BYTES_MAX;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
+          const uint64_t bd = p.b_mn ? desc_mn(bb + k * b_step) : desc_k(bb + k * b_step);
+          umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (kb == nk - 1) umma_commit(accf);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: warp w reads TMEM lanes 32*(w%4)..+31
+    const int ew = warp & 3;
+    const int m = m0 + ew * 32 + lane;
+    const bool first_split = (blockIdx.z == 0);
+    const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
+    mbar_wait(accf, 0, 3);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && !p.atomic &&
+                        (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      if (n0 + c0 >= p.N) break;     // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + c0, v);
+      tmem_ld_wait();
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        float val = alpha * __uint_as_float(v[j]);
+        if (first_split && p.bias && n < p.N) val += __ldg(p.bias + n);
+        o[j] = val;
+      }
+      if (p.colsum) {
+        // column sums over this warp's 32 rows (rows >= M count as zero) by a transposing butterfly: 31 shuffles
+        // leave lane l with the sum of column c0 + l; then one fp64 atomic per column per warp
+        float a1[32], a2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a1[j] = (m < p.M) ? o[j] : 0.f; a2[j] = a1[j] * a1[j]; }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < off; ++j) {
+            const float s1 = upper ? a1[j] : a1[j + off], k1 = upper ? a1[j + off] : a1[j];
+            const float s2 = upper ? a2[j] : a2[j + off], k2 = upper ? a2[j + off] : a2[j];
+            a1[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
+            a2[j] = k2 + __shfl_xor_sync(0xffffffffu, s2, off);
+          }
+        }
+        if (n0 + c0 + lane < p.N) {
+          atomicAdd(p.colsum + n0 + c0 + lane, static_cast<double>(a1[0]));
+          atomicAdd(p.colsum + p.N + n0 + c0 + lane, static_cast<double>(a2[0]));
+        }
+      }
+      if (m < p.M) {
+        float* crow = p.C + static_cast<size_t>(m) * p.ldc + n0 + c0;
+        const float* rrow = (p.res && first_split) ? p.res + static_cast<size_t>(m) * p.ldres + n0 + c0 : nullptr;
+        if (vec_ok && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            if (rrow) { const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j)); q.x += r.x; q.y += r.y; q.z += r.z; q.w += r.w; }
+            *reinterpret_cast<float4*>(crow + j) = q;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + c0 + j < p.N) {
+              float val = o[j];
+              if (rrow) val += __ldg(rrow + j);
+              if (p.atomic) atomicAdd(crow + j, val); else crow[j] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// bf16 row-major [outer][inner] (pitch in elements), box [box_outer][64], 128B swizzle, zero fill out of range
+static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return P3D_ERR_CUDA; }
+  if ((pitch * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tc_gemm: operand pitch/base must be 16-byte aligned (pitch %llu elements)", (unsigned long long)pitch);
+    return P3D_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {pitch * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return P3D_ERR_CUDA; }
+  return P3D_OK;
+}
+
+// A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
+int gemm(const GemmArgs& g, cudaStream_t st) {
+  P3D_REQUIRE(g.M >= 1 && g.N >= 1 && g.K >= 1 && g.A && g.B && g.C, "tc_gemm: bad argument");
+  const int num_sms = 148;
+  const int mt = (g.M + BM - 1) / BM;
+  const int n64 = (g.N + 63) / 64 * 64;
+  const int kblocks = (g.K + BK - 1) / BK;
+  // tile width: the widest BN that still gives the grid about one CTA per SM; a split-K problem keeps the
+  // wide tile (better MMA efficiency) and fills the machine through gridDim.z instead
+  int bn = 256;
+  while (bn > 64 && (bn > n64 || (!g.split_k && mt * ((g.N + bn - 1) / bn) < 100))) bn >>= 1;
+  const int nt = (g.N + bn - 1) / bn;
+  int splits = 1;
+  if (g.split_k) {
+    splits = num_sms / (mt * nt);
+    if (splits < 1) splits = 1;
+    if (splits > kblocks) splits = kblocks;
+    if (splits > 32) splits = 32;
+  }
+  const int kps = ((kblocks + splits - 1) / splits) * BK;
+  splits = (g.K + kps - 1) / kps;
+  CUtensorMap ta, tb;
+  if (!g.a_mn) P3D_TRY(make_map(&ta, g.A, g.K, g.M, g.lda, BM));
+  else P3D_TRY(make_map(&ta, g.A, g.M, g.K, g.lda, BK));
+  if (!g.b_mn) P3D_TRY(make_map(&tb, g.B, g.K, g.N, g.ldb, bn));
+  else P3D_TRY(make_map(&tb, g.B, g.N, g.K, g.ldb, BK));
+  Params p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.bn = bn; p.k_per_split = kps; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
+  p.C = g.C; p.ldc = g.ldc; p.bias = g.bias; p.res = g.res; p.ldres = g.ldres; p.alpha_dev = g.alpha_dev; p.alpha = g.alpha;
+  p.atomic = (splits > 1 || g.accumulate) ? 1 : 0;
+  p.colsum = g.colsum;
+  P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
+  static bool attr = false;
+  if (!attr) {
+    P3D_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  tc_gemm_kernel<<<dim3(nt, mt, splits), NTHREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+}  // namespace tcg
+}  // namespace p3d

@@ -173,6 +173,12 @@ int p3d_similarity_transform_f64(const double* X, const double* Y, int J, int co
 /* globaltimer stamps (ns) of the batch-1 cluster kernel's last run (P3D_LAT_STAMPS=1): [0] entry, [1] after layer 0,
  * [1+l] after hidden layer l, [nlayers] exit. */
 int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n);
+/* Diagnostics: the generic tcgen05 GEMM of the training step (csrc/tc_gemm.cu).  A: a_mn ? [K][M] : [M][K],
+ * B: b_mn ? [K][N] : [N][K], both bf16 with pitches lda/ldb (elements); C fp32 [M][ldc].
+ * C = alpha * A.B (+bias[n]) (+res[m][n]); split_k != 0 splits K over the grid with fp32 atomics (C must be
+ * zeroed); colsum (optional, [2][N] doubles, +=) receives the column sums of C and C^2. */
+int p3d_debug_tc_gemm(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
+                      const float* bias, const float* res, float alpha, int split_k, double* colsum, void* stream);
 int p3d_debug_umma_gemm(const void* A_bf16, const void* W_bf16, float* C, int N, int K, void* stream);
 
 #ifdef __cplusplus
