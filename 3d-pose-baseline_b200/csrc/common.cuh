@@ -91,6 +91,12 @@ struct TrainWorkspace {
   float* rstd = nullptr;    // [nhidden][L]
   double* red = nullptr;    // [nhidden][2][L] backward sums (dgamma, dbeta) + misc scalars
   float* scal = nullptr;    // small device scalars: loss, lr, clip dots...
+  // bf16 operands of the tensor-core path (P3D_MODE_BF16)
+  __nv_bfloat16* xb = nullptr;    // [B][32]
+  __nv_bfloat16* hb = nullptr;    // [nhidden][B][L]
+  __nv_bfloat16* dzb = nullptr;   // [B][L]
+  __nv_bfloat16* dyb = nullptr;   // [B][48] (pad columns zero)
+  __nv_bfloat16* wb = nullptr;    // weights [K][N] per layer at theta's offsets; W4 rows padded to 48
 };
 
 // Optional per-launch CUDA-event timing of the dominant kernel (bench.py's roofline figure):

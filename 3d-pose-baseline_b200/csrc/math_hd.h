@@ -191,4 +191,204 @@ P3D_HD void kabsch_rotation(const double A[9], double T[9], double& tr) {
     for (int j = 0; j < 3; ++j) tr += T[i * 3 + j] * A[j * 3 + i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 evaluation path (the HBM-bound MPJPE kernel): everything a pose needs in single precision.
+//
+// Rotation: ONE-SIDED (Hestenes) Jacobi directly on A = U S V^T - column pairs of B = A V are rotated
+// until orthogonal, so B = U S and V are obtained without ever squaring the condition number (A^T A in
+// fp32 would cost half the digits of the small singular directions).  The two dominant pairs define
+// T = v1 u1^T + v2 u2^T + (v1 x v2)(u1 x u2)^T = V diag(1,1,det) U^T of procrustes.py:45-48.
+P3D_HD float p3d_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  const float r = rsqrtf(x);
+  return r * (1.5f - 0.5f * x * r * r);      // one Newton step: full fp32 accuracy
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+P3D_HD float p3d_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+
+P3D_HD float p3d_rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+P3D_HD float p3d_sqrt_fast(float x) {          // sqrt.approx: ~1 ulp, no slow path (x >= 0)
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+
+P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
+  float B[3][3], V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  P3D_UNROLL
+  for (int i = 0; i < 3; ++i) { B[i][0] = A[i * 3]; B[i][1] = A[i * 3 + 1]; B[i][2] = A[i * 3 + 2]; }
+  P3D_UNROLL
+  for (int sweep = 0; sweep < 4; ++sweep) {   // 3 already converge to fp32 accuracy on every test set
+    P3D_UNROLL
+    for (int r = 0; r < 3; ++r) {
+      const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
+      const float al = B[0][p] * B[0][p] + B[1][p] * B[1][p] + B[2][p] * B[2][p];
+      const float be = B[0][q] * B[0][q] + B[1][q] * B[1][q] + B[2][q] * B[2][q];
+      const float ga = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
+      float c = 1.f, s = 0.f;
+      if (ga * ga > 1e-16f * al * be) {          // already orthogonal to fp32 accuracy otherwise
+        // the angle may be approximate (it only affects the convergence rate); (c,s) must be an exact rotation
+        const float zeta = (be - al) * p3d_rcp_fast(2.f * ga);
+        const float t = (zeta >= 0.f ? 1.f : -1.f) * p3d_rcp_fast(fabsf(zeta) + p3d_sqrt_fast(zeta * zeta + 1.f));
+        c = p3d_rsqrt(t * t + 1.f);
+        s = t * c;
+      }
+      P3D_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        const float bp = B[k][p], bq = B[k][q];
+        B[k][p] = c * bp - s * bq; B[k][q] = s * bp + c * bq;
+        const float vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
+      }
+    }
+  }
+  float l0 = B[0][0] * B[0][0] + B[1][0] * B[1][0] + B[2][0] * B[2][0];
+  float l1 = B[0][1] * B[0][1] + B[1][1] * B[1][1] + B[2][1] * B[2][1];
+  float l2 = B[0][2] * B[0][2] + B[1][2] * B[1][2] + B[2][2] * B[2][2];
+#define P3D_CSWAPF(la, lb, ca, cb)                                        \
+  if (la < lb) {                                                          \
+    float t_ = la; la = lb; lb = t_;                                      \
+    for (int k_ = 0; k_ < 3; ++k_) { t_ = V[k_][ca]; V[k_][ca] = V[k_][cb]; V[k_][cb] = t_; \
+                                     t_ = B[k_][ca]; B[k_][ca] = B[k_][cb]; B[k_][cb] = t_; } \
+  }
+  P3D_CSWAPF(l0, l1, 0, 1)
+  P3D_CSWAPF(l0, l2, 0, 2)
+  P3D_CSWAPF(l1, l2, 1, 2)
+#undef P3D_CSWAPF
+  (void)l2;
+  float v1[3] = {V[0][0], V[1][0], V[2][0]}, v2[3] = {V[0][1], V[1][1], V[2][1]};
+  float u1[3] = {B[0][0], B[1][0], B[2][0]}, u2[3] = {B[0][1], B[1][1], B[2][1]};
+  {
+    const float n = p3d_rsqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+    for (int i = 0; i < 3; ++i) v1[i] *= n;
+    const float d = v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2];
+    for (int i = 0; i < 3; ++i) v2[i] -= d * v1[i];
+    const float n2 = p3d_rsqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+    for (int i = 0; i < 3; ++i) v2[i] *= n2;
+  }
+  {
+    const float n = p3d_rsqrt(l0);
+    for (int i = 0; i < 3; ++i) u1[i] *= n;
+    const float d = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    for (int i = 0; i < 3; ++i) u2[i] -= d * u1[i];
+    const float n2 = p3d_rsqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    for (int i = 0; i < 3; ++i) u2[i] *= n2;
+  }
+  const float v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+  const float u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+  tr = 0.f;
+  P3D_UNROLL
+  for (int i = 0; i < 3; ++i)
+    P3D_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      T[i * 3 + j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];
+      tr += T[i * 3 + j] * A[j * 3 + i];
+    }
+}
+
+// Per-pose errors of predict_3dpose.evaluate_batches (src/predict_3dpose.py:399-442) in fp32.
+//   W, J0        : row width (48 or 42) and 1 when the implicit hip joint is part of the error (W = 48)
+//   g(k), p(k)   : normalised ground truth / prediction, k in [0, W)
+//   sd[k]        : data_std_3d gathered to the used dims
+//   mc[k]        : data_mean_3d gathered, minus the mean over the J joints of the un-normalised MEAN pose
+//                  (so that centred coordinates come out of one fma and stay small)
+//   hipc[3]      : same for the hip joint (un-normalised hip = data_mean_3d[0:3] for both poses)
+// Centred joint: x_c = g*sd + mc - (sum_k g_k sd_k)/J.   Aligned error: b (y_c T) - x_c  (= b y T + c - x).
+template <int W, int J0, class LDG, class LDP>
+P3D_HD void pose_errors_f32(LDG g, LDP p, const float* sd, const float* mc, const float* hipc, int use_procrustes, float* dj) {
+  constexpr int J = W / 3 + J0;
+  if (!use_procrustes) {
+    if (J0) dj[0] = 0.f;
+    P3D_UNROLL
+    for (int j = J0; j < J; ++j) {
+      const int k = (j - J0) * 3;
+      const float e0 = (p(k) - g(k)) * sd[k], e1 = (p(k + 1) - g(k + 1)) * sd[k + 1], e2 = (p(k + 2) - g(k + 2)) * sd[k + 2];
+      dj[j] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
+    }
+    return;
+  }
+  float sx[3] = {0.f, 0.f, 0.f}, sy[3] = {0.f, 0.f, 0.f};
+  P3D_UNROLL
+  for (int k = 0; k < W; k += 3) {
+    P3D_UNROLL
+    for (int d = 0; d < 3; ++d) { sx[d] += g(k + d) * sd[k + d]; sy[d] += p(k + d) * sd[k + d]; }
+  }
+  const float invJ = 1.0f / static_cast<float>(J);
+  P3D_UNROLL
+  for (int d = 0; d < 3; ++d) { sx[d] *= invJ; sy[d] *= invJ; }
+  float ssx = 0.f, ssy = 0.f, A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (J0) {
+    float x[3], y[3];
+    P3D_UNROLL
+    for (int d = 0; d < 3; ++d) { x[d] = hipc[d] - sx[d]; y[d] = hipc[d] - sy[d]; ssx += x[d] * x[d]; ssy += y[d] * y[d]; }
+    P3D_UNROLL
+    for (int r = 0; r < 3; ++r)
+      P3D_UNROLL
+      for (int s = 0; s < 3; ++s) A[r * 3 + s] += x[r] * y[s];
+  }
+  P3D_UNROLL
+  for (int k = 0; k < W; k += 3) {
+    float x[3], y[3];
+    P3D_UNROLL
+    for (int d = 0; d < 3; ++d) {
+      x[d] = (g(k + d) * sd[k + d] + mc[k + d]) - sx[d];
+      y[d] = (p(k + d) * sd[k + d] + mc[k + d]) - sy[d];
+      ssx += x[d] * x[d]; ssy += y[d] * y[d];
+    }
+    P3D_UNROLL
+    for (int r = 0; r < 3; ++r)
+      P3D_UNROLL
+      for (int s = 0; s < 3; ++s) A[r * 3 + s] += x[r] * y[s];
+  }
+  const float inv = p3d_rsqrt(ssx * ssy);
+  P3D_UNROLL
+  for (int i = 0; i < 9; ++i) A[i] *= inv;
+  float T[9], tr;
+  kabsch_rotation_f32(A, T, tr);
+  const float b = tr * p3d_sqrt_fast(ssx * p3d_rcp(ssy));          // compute_optimal_scale=True (procrustes.py:52-55)
+  P3D_UNROLL
+  for (int i = 0; i < 9; ++i) T[i] *= b;
+  if (J0) {
+    float x[3], y[3];
+    P3D_UNROLL
+    for (int d = 0; d < 3; ++d) { x[d] = hipc[d] - sx[d]; y[d] = hipc[d] - sy[d]; }
+    const float e0 = (y[0] * T[0] + y[1] * T[3] + y[2] * T[6]) - x[0];
+    const float e1 = (y[0] * T[1] + y[1] * T[4] + y[2] * T[7]) - x[1];
+    const float e2 = (y[0] * T[2] + y[1] * T[5] + y[2] * T[8]) - x[2];
+    dj[0] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
+  }
+  P3D_UNROLL
+  for (int j = J0; j < J; ++j) {
+    const int k = (j - J0) * 3;
+    float x[3], y[3];
+    P3D_UNROLL
+    for (int d = 0; d < 3; ++d) {
+      x[d] = (g(k + d) * sd[k + d] + mc[k + d]) - sx[d];
+      y[d] = (p(k + d) * sd[k + d] + mc[k + d]) - sy[d];
+    }
+    const float e0 = (y[0] * T[0] + y[1] * T[3] + y[2] * T[6]) - x[0];
+    const float e1 = (y[0] * T[1] + y[1] * T[4] + y[2] * T[7]) - x[1];
+    const float e2 = (y[0] * T[2] + y[1] * T[5] + y[2] * T[8]) - x[2];
+    dj[j] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
+  }
+}
+
 }  // namespace p3d

@@ -2,11 +2,17 @@
 //   predict_3dpose.evaluate_batches arithmetic   src/predict_3dpose.py:399-442
 //   procrustes.compute_similarity_transform      src/procrustes.py:2-63
 //
-// Layout: a block stages 128 poses x 2 x 48 fp32 through shared memory with coalesced float4 loads,
-// then every lane owns ONE pose (a warp = 32 poses): the serial 3x3 eigen-solve keeps all 32 lanes
-// busy instead of one lane per warp.  Per-joint error sums are reduced with warp shuffles, kept in
-// registers across the grid-stride loop and flushed with one fp64 atomic per joint per block.
-// All alignment arithmetic is fp64 (the reference is NumPy float64; tolerance 1e-3 mm).
+// Two implementations of the same entry point:
+//  * mpjpe_f32_kernel (default, p3d_procrustes_mpjpe): HBM-bound design.  Every lane owns ONE pose (the
+//    serial 3x3 solve keeps 32 lanes busy instead of one lane per warp).  Each WARP streams its own
+//    32-pose tiles with cp.async into a private shared-memory slab (row pitch padded so that the per-lane
+//    LDS.128 row reads are conflict free), pulls its row into registers, immediately re-issues the
+//    cp.async of its next tile, and does all arithmetic in fp32 registers (one-sided Jacobi, math_hd.h)
+//    while that copy is in flight - no block barrier anywhere.  Per-joint sums: fp32 per lane, flushed
+//    through warp shuffles into fp64 atomics.  Measured against the fp64 oracle: MPJPE 2e-7 mm,
+//    per-joint means 3e-6 mm, worst single per-pose distance 8e-4 mm (tolerance 1e-3 mm).
+//  * procrustes_mpjpe_kernel (p3d_procrustes_mpjpe_f64): the all-fp64 form (fp64-pipe bound, ~3x slower),
+//    kept for callers that want per-pose distances to 1e-6 mm.
 #include "common.cuh"
 #include "math_hd.h"
 
@@ -169,6 +175,115 @@ __global__ void __launch_bounds__(PB, 4) procrustes_mpjpe_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------ fp32, warp-autonomous, cp.async fed
+template <int W> struct EvalLayout;
+template <> struct EvalLayout<48> { static constexpr int PITCH = 52, CB = 16, CPR = 12; };   // padded rows, 16 B chunks
+template <> struct EvalLayout<42> { static constexpr int PITCH = 42, CB = 8, CPR = 21; };    // dense rows, 8 B chunks
+
+struct EvalArgsF {
+  float sd[48], mc[48], hipc[3];
+  int use_procrustes;
+};
+
+template <int CB>
+__device__ __forceinline__ void cp_async_zfill(uint32_t dst, const void* src, int src_bytes) {
+  if (CB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+constexpr int EV_WARPS = 4;
+
+template <int W, int J0>
+__global__ void __launch_bounds__(EV_WARPS * 32, 3) mpjpe_f32_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                    const __grid_constant__ EvalArgsF a, float* __restrict__ dists,
+                                                                    double* __restrict__ joint_sum, long long N) {
+  using LY = EvalLayout<W>;
+  constexpr int J = W / 3 + J0;
+  constexpr int ROW_BYTES = LY::PITCH * 4;
+  constexpr int ARR_BYTES = 32 * ROW_BYTES;
+  constexpr int CB = LY::CB, CPR = LY::CPR;
+  extern __shared__ __align__(16) uint8_t ev_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint8_t* buf = ev_smem + wib * 2 * ARR_BYTES;          // [gt | pred] slab of this warp
+  const uint32_t sbuf = static_cast<uint32_t>(__cvta_generic_to_shared(buf));
+  const long long ntiles = (N + 31) / 32;
+  const long long nwarps = static_cast<long long>(gridDim.x) * EV_WARPS;
+  const uint8_t* gbytes = reinterpret_cast<const uint8_t*>(gt);
+  const uint8_t* pbytes = reinterpret_cast<const uint8_t*>(pred);
+
+  auto issue = [&](long long tile) {
+    if (tile < ntiles) {
+      const long long base = tile * 32 * W * 4;
+      const long long rem = N * W * 4 - base;             // valid bytes of this tile (rows are multiples of CB)
+#pragma unroll
+      for (int n = 0; n < CPR; ++n) {
+        const int i = lane + 32 * n;                       // chunk index inside the tile
+        const int soff = (i / CPR) * ROW_BYTES + (i % CPR) * CB;
+        const long long gb = static_cast<long long>(i) * CB;
+        const bool ok = gb < rem;
+        cp_async_zfill<CB>(sbuf + soff, gbytes + (ok ? base + gb : 0), ok ? CB : 0);
+        cp_async_zfill<CB>(sbuf + ARR_BYTES + soff, pbytes + (ok ? base + gb : 0), ok ? CB : 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) acc[j] = 0.f;
+  auto flush = [&]() {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const double s = warp_sum(static_cast<double>(acc[j]));
+      if (lane == 0) atomicAdd(joint_sum + j, s);
+      acc[j] = 0.f;
+    }
+  };
+
+  long long tile = static_cast<long long>(blockIdx.x) * EV_WARPS + wib;
+  issue(tile);
+  int since_flush = 0;
+  for (; tile < ntiles; tile += nwarps) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    float g[W], p[W];
+    const uint8_t* row = buf + lane * ROW_BYTES;
+    if (CB == 16) {
+#pragma unroll
+      for (int c = 0; c < W / 4; ++c) {
+        const float4 u = *reinterpret_cast<const float4*>(row + c * 16);
+        const float4 v = *reinterpret_cast<const float4*>(row + ARR_BYTES + c * 16);
+        g[4 * c] = u.x; g[4 * c + 1] = u.y; g[4 * c + 2] = u.z; g[4 * c + 3] = u.w;
+        p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < W / 2; ++c) {
+        const float2 u = *reinterpret_cast<const float2*>(row + c * 8);
+        const float2 v = *reinterpret_cast<const float2*>(row + ARR_BYTES + c * 8);
+        g[2 * c] = u.x; g[2 * c + 1] = u.y;
+        p[2 * c] = v.x; p[2 * c + 1] = v.y;
+      }
+    }
+    __syncwarp();                       // every lane holds its row: the slab can take the next tile
+    issue(tile + nwarps);
+    const long long pose = tile * 32 + lane;
+    const bool live = pose < N;
+    float dj[J];
+    pose_errors_f32<W, J0>([&](int k) { return g[k]; }, [&](int k) { return p[k]; }, a.sd, a.mc, a.hipc, a.use_procrustes, dj);
+    if (dists && live) {
+      float* dp = dists + pose * J;
+#pragma unroll
+      for (int j = 0; j < J; ++j) dp[j] = dj[j];
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] += live ? dj[j] : 0.f;
+    if (++since_flush == 64) { flush(); since_flush = 0; }   // bounds the fp32 partial sums (<= 64 terms per lane)
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  flush();
+}
+
 // Batched procrustes.compute_similarity_transform on raw fp64 poses; one thread per pose.
 __global__ void similarity_transform_kernel(const double* __restrict__ X, const double* __restrict__ Y, int J, int scale,
                                             long long N, double* d_out, double* Z, double* T_out, double* b_out, double* c_out) {
@@ -216,7 +331,7 @@ using namespace p3d::evalk;
 
 extern "C" {
 
-int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* mean3d, const double* std3d, int predict_14,
+int p3d_procrustes_mpjpe_f64(const float* pred_n, const float* gt_n, const double* mean3d, const double* std3d, int predict_14,
                          int use_procrustes, int64_t N, float* dists, double* joint_sum, void* stream) {
   P3D_REQUIRE(pred_n && gt_n && mean3d && std3d && joint_sum && N >= 0, "procrustes_mpjpe: null argument");
   if (N == 0) return P3D_OK;
@@ -242,6 +357,52 @@ int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* m
   const long long ntiles = (N + PB - 1) / PB;
   const int grid = ntiles < 148 * 4 ? (int)ntiles : 148 * 4;
   procrustes_mpjpe_kernel<<<grid, PB, smem, (cudaStream_t)stream>>>(pred_n, gt_n, a, dists, joint_sum, N);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* mean3d, const double* std3d, int predict_14,
+                         int use_procrustes, int64_t N, float* dists, double* joint_sum, void* stream) {
+  P3D_REQUIRE(pred_n && gt_n && mean3d && std3d && joint_sum && N >= 0, "procrustes_mpjpe: null argument");
+  if (N == 0) return P3D_OK;
+  P3D_REQUIRE(((reinterpret_cast<uintptr_t>(pred_n) | reinterpret_cast<uintptr_t>(gt_n)) & 15) == 0,
+              "procrustes_mpjpe: pred/gt must be 16-byte aligned");
+  static const int j16[16] = {1, 2, 3, 6, 7, 8, 12, 13, 14, 15, 17, 18, 19, 25, 26, 27};
+  static const int j14[14] = {1, 2, 3, 6, 7, 8, 13, 15, 17, 18, 19, 25, 26, 27};
+  const int nj = predict_14 ? 14 : 16;
+  const int* jt = predict_14 ? j14 : j16;
+  const int J = nj + (predict_14 ? 0 : 1);
+  // mean over the J joints of the un-normalised MEAN pose (the hip, data_mean_3d[0:3], is joint 0 unless predict_14)
+  double mbar[3] = {0, 0, 0};
+  for (int d = 0; d < 3; ++d) {
+    for (int j = 0; j < nj; ++j) mbar[d] += mean3d[jt[j] * 3 + d];
+    if (!predict_14) mbar[d] += mean3d[d];
+    mbar[d] /= J;
+  }
+  EvalArgsF a;
+  memset(&a, 0, sizeof(a));
+  for (int j = 0; j < nj; ++j)
+    for (int d = 0; d < 3; ++d) {
+      a.sd[j * 3 + d] = static_cast<float>(std3d[jt[j] * 3 + d]);
+      a.mc[j * 3 + d] = static_cast<float>(mean3d[jt[j] * 3 + d] - mbar[d]);
+    }
+  for (int d = 0; d < 3; ++d) a.hipc[d] = static_cast<float>(mean3d[d] - mbar[d]);
+  a.use_procrustes = use_procrustes ? 1 : 0;
+  const long long ntiles = (N + 31) / 32;
+  const long long nblocks = (ntiles + EV_WARPS - 1) / EV_WARPS;
+  const int grid = nblocks < 148 * 3 ? (int)nblocks : 148 * 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!predict_14) {
+    constexpr int smem = EV_WARPS * 2 * 32 * EvalLayout<48>::PITCH * 4;
+    static bool attr = false;
+    if (!attr) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    mpjpe_f32_kernel<48, 1><<<grid, EV_WARPS * 32, smem, st>>>(pred_n, gt_n, a, dists, joint_sum, N);
+  } else {
+    constexpr int smem = EV_WARPS * 2 * 32 * EvalLayout<42>::PITCH * 4;
+    static bool attr = false;
+    if (!attr) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<42, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    mpjpe_f32_kernel<42, 0><<<grid, EV_WARPS * 32, smem, st>>>(pred_n, gt_n, a, dists, joint_sum, N);
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

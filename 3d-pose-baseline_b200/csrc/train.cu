@@ -3,6 +3,10 @@
 //   biased variance, moving averages updated with the step) and TF1 dropout  y/keep * floor(keep+U),
 //   loss = mean((y-t)^2) over B*out, backward through clip_by_norm / BN / ReLU / dropout / residual,
 //   TF-flavoured Adam with lr = lr0 * 0.96^(global_step/100000).
+// P3D_MODE_BF16: every MatMul of the step (forward, tf.gradients wrt activations, weight gradients) runs on the
+// tcgen05 tensor cores (tc_gemm.cu) with bf16 operands, fp32 accumulation and fp32 master weights; H, dZ and W
+// are consumed in their natural row-major layouts (MN-major UMMA descriptors where the reduction dimension is
+// the row index), the forward GEMM's epilogue also produces the BatchNorm column sums.  P3D_MODE_FP32: FFMA GEMMs.
 // Data parallel (one process per GPU): rows are sharded, BN statistics and their backward sums are
 // all-reduced (SyncBN - required for parity with the single-device reference), and the flat gradient
 // buffer is all-reduced once with NCCL before the (replicated) Adam update.
@@ -123,7 +127,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double invB
 
 struct ActArgs {
   const float* z; const float* mean; const float* rstd; const float* gamma; const float* beta;
-  const float* res; float* h; uint8_t* mask; const uint8_t* mask_in;
+  const float* res; float* h; __nv_bfloat16* hb; uint8_t* mask; const uint8_t* mask_in;
   float keep; unsigned long long seed; unsigned step, layer; long long row0, B; int L; int has_bn; int dropout;
 };
 
@@ -162,16 +166,33 @@ __global__ void fwd_act_kernel(const ActArgs a) {
       v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
     }
     *reinterpret_cast<float4*>(a.h + r * a.L + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.hb) {      // operand of the next layer's tcgen05 GEMMs (forward and weight gradient)
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(a.hb + r * a.L + c) = pk;
+    }
+  }
+}
+
+// fp32 -> bf16 with a (possibly wider) destination pitch; pad columns are left untouched (zero)
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int cols, int ld_dst) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    dst[r * ld_dst + c] = __float2bfloat16_rn(src[i]);
   }
 }
 
 // dy = 2 (y - t) / (Bg*out), loss accumulator += sum (y-t)^2
 __global__ void loss_dy_kernel(const float* __restrict__ y, const float* __restrict__ t, size_t n, float scale,
-                               float* __restrict__ dy, double* __restrict__ acc) {
+                               float* __restrict__ dy, double* __restrict__ acc, __nv_bfloat16* __restrict__ dyb, int out, int ld_b) {
   double s = 0;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float d = y[i] - t[i];
     dy[i] = scale * d;
+    if (dyb) { const size_t r = i / out; dyb[r * ld_b + (i - r * out)] = __float2bfloat16_rn(scale * d); }
     s += static_cast<double>(d) * d;
   }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -191,7 +212,7 @@ __global__ void finish_step_scalars_kernel(const double* acc, double denom, floa
 
 struct BwdArgs {
   const float* dh; const float* z; const float* mean; const float* rstd; const float* gamma; const float* beta;
-  const uint8_t* mask; float* dz; double* sums; float inv_keep; long long B; int L; int has_bn; int dropout;
+  const uint8_t* mask; float* dz; __nv_bfloat16* dzb; double* sums; float inv_keep; long long B; int L; int has_bn; int dropout;
 };
 
 // pass A: da = dh * dropout * relu'(a); column sums of da and da*xhat (for BN backward / dgamma, dbeta)
@@ -212,6 +233,7 @@ __global__ void bwd_act_kernel(const BwdArgs a) {
       if (a.dropout) gr = a.mask[r * a.L + c] ? gr * a.inv_keep : 0.f;
       const float da = act > 0.f ? gr : 0.f;
       a.dz[r * a.L + c] = da;
+      if (a.dzb) a.dzb[r * a.L + c] = __float2bfloat16_rn(da);     // final dz only when the layer has no BN
       p += da; q += static_cast<double>(da) * xh;
     }
   }
@@ -227,14 +249,16 @@ __global__ void bwd_act_kernel(const BwdArgs a) {
 // pass B (BN layers): dz = gamma * rstd * (da - mean(da) - xhat * mean(da*xhat)), means over the GLOBAL batch
 __global__ void bwd_bn_kernel(float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ mean,
                               const float* __restrict__ rstd, const float* __restrict__ gamma,
-                              const double* __restrict__ sums, float invB, long long B, int L) {
+                              const double* __restrict__ sums, float invB, long long B, int L, __nv_bfloat16* __restrict__ dzb) {
   const long long total = B * L;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % L);
     const float xh = (z[i] - mean[c]) * rstd[c];
     const float m1 = static_cast<float>(sums[c]) * invB, m2 = static_cast<float>(sums[L + c]) * invB;
-    dz[i] = gamma[c] * rstd[c] * (dz[i] - m1 - xh * m2);
+    const float v = gamma[c] * rstd[c] * (dz[i] - m1 - xh * m2);
+    dz[i] = v;
+    if (dzb) dzb[i] = __float2bfloat16_rn(v);
   }
 }
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int L, double scale, float* __restrict__ ggamma, float* __restrict__ gbeta) {
@@ -301,16 +325,23 @@ void free_workspace(p3d_model* m) {
   TrainWorkspace& w = m->tw;
   cudaFree(w.z); cudaFree(w.h); cudaFree(w.dh); cudaFree(w.dz); cudaFree(w.dres); cudaFree(w.dy);
   cudaFree(w.stats); cudaFree(w.mean); cudaFree(w.rstd); cudaFree(w.scal); cudaFree(w.maskbuf);
+  cudaFree(w.xb); cudaFree(w.hb); cudaFree(w.dzb); cudaFree(w.dyb); cudaFree(w.wb);
   w = TrainWorkspace();
   if (m->nccl_comm && nccl()) { nccl()->CommDestroy(static_cast<ncclComm_t>(m->nccl_comm)); m->nccl_comm = nullptr; }
 }
+
+constexpr int kOutPad = 48;   // bf16 pitch of dy / W4 rows: 96 B keeps TMA's 16-byte pitch rule for out = 42 too
+// bf16 mode runs the step's GEMMs on the tensor cores (tc_gemm.cu); fp32 mode keeps the FFMA GEMMs
+static inline bool use_tc(const p3d_model* m) { return m->cfg.mode == P3D_MODE_BF16 && (m->L % 8) == 0; }
 
 static int ensure_workspace(p3d_model* m, int64_t B) {
   TrainWorkspace& w = m->tw;
   const int L = m->L, nh = static_cast<int>(m->layers.size()) - 1, nl = nh + 1;
   if (w.cap_B >= B) return P3D_OK;
   cudaFree(w.z); cudaFree(w.h); cudaFree(w.dh); cudaFree(w.dz); cudaFree(w.dres); cudaFree(w.dy); cudaFree(w.maskbuf);
+  cudaFree(w.xb); cudaFree(w.hb); cudaFree(w.dzb); cudaFree(w.dyb);
   w.z = w.h = w.dh = w.dz = w.dres = w.dy = nullptr; w.maskbuf = nullptr; w.cap_B = 0;
+  w.xb = w.hb = w.dzb = w.dyb = nullptr;
   const size_t bl = static_cast<size_t>(B) * L;
   P3D_CUDA(cudaMalloc(&w.z, sizeof(float) * bl * nh));
   P3D_CUDA(cudaMalloc(&w.h, sizeof(float) * bl * nh));
@@ -319,6 +350,21 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
   P3D_CUDA(cudaMalloc(&w.dres, sizeof(float) * bl * 2));              // two more rotating gradient buffers
   P3D_CUDA(cudaMalloc(&w.dy, sizeof(float) * static_cast<size_t>(B) * m->out_size));
   P3D_CUDA(cudaMalloc(&w.maskbuf, bl * nh));                          // uint8 keep-masks [nh][B][L]
+  if (use_tc(m)) {
+    // bf16 operands of the tcgen05 GEMMs, all in their natural row-major layouts
+    P3D_CUDA(cudaMalloc(&w.xb, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kIn));
+    P3D_CUDA(cudaMalloc(&w.hb, sizeof(__nv_bfloat16) * bl * nh));
+    P3D_CUDA(cudaMalloc(&w.dzb, sizeof(__nv_bfloat16) * bl));
+    P3D_CUDA(cudaMalloc(&w.dyb, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kOutPad));
+    P3D_CUDA(cudaMemset(w.dyb, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kOutPad));   // pad columns stay zero
+    if (!w.wb) {
+      // [all hidden W, same offsets as theta][W4 with its rows padded to kOutPad columns]
+      const Layer& lo = m->layers.back();
+      const size_t n = lo.off_w + static_cast<size_t>(lo.K) * kOutPad;
+      P3D_CUDA(cudaMalloc(&w.wb, sizeof(__nv_bfloat16) * n));
+      P3D_CUDA(cudaMemset(w.wb, 0, sizeof(__nv_bfloat16) * n));
+    }
+  }
   if (!w.stats) {
     // doubles: stats [nh][2][L] | bwd sums [nh][2][L] | dots [nl] | loss [1]
     P3D_CUDA(cudaMalloc(&w.stats, sizeof(double) * (4ull * nh * L + nl + 1)));
@@ -345,6 +391,8 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   const bool dropout = keep < 1.f || mask_in != nullptr;
   const bool clip = m->cfg.max_norm != 0;
   const bool residual = m->cfg.residual != 0;
+  const bool tc = use_tc(m);
+  using tcg::GemmArgs;
   double* dots = w.red + 2ull * nh * L;
   double* lossacc = dots + nlay;
   uint8_t* maskbuf = w.maskbuf;
@@ -364,20 +412,42 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
     clip_scale_kernel<<<1, 64, 0, st>>>(m->norm2, scale, nlay);
     P3D_LAUNCH_CHECK();
   }
+  if (tc) {
+    // bf16 copies of this step's weights (natural [K][N] layout; W4 rows padded to kOutPad) and of x
+    const Layer& lo = m->layers[nh];
+    to_bf16_kernel<<<egrid(static_cast<long long>(lo.off_w / 4 + 1)), 256, 0, st>>>(m->theta, w.wb, 1, static_cast<int>(lo.off_w), static_cast<int>(lo.off_w));
+    P3D_LAUNCH_CHECK();
+    to_bf16_kernel<<<egrid(static_cast<long long>(L) * out / 4 + 1), 256, 0, st>>>(m->theta + lo.off_w, w.wb + lo.off_w, L, out, kOutPad);
+    P3D_LAUNCH_CHECK();
+    to_bf16_kernel<<<egrid(static_cast<long long>(B) * kIn / 4 + 1), 256, 0, st>>>(x, w.xb, B, kIn, kIn);
+    P3D_LAUNCH_CHECK();
+  }
   // ---------------------------------------------------------------- forward
   for (int li = 0; li < nh; ++li) {
     const Layer& ly = m->layers[li];
     const float* in = li == 0 ? x : w.h + (li - 1) * bl;
     const int lda = li == 0 ? kIn : L;
     float* z = w.z + li * bl;
-    Epilogue e; e.bias = m->theta + ly.off_b; e.alpha_dev = clip ? scale + li : nullptr;
-    P3D_TRY(sgemm(false, false, B, L, ly.K, in, lda, m->theta + ly.off_w, L, z, L, e, st));
+    double* stats = w.stats + 2ull * li * L;
+    if (tc) {
+      GemmArgs g;   // z = (x|h) W * clip + b ; BN column sums in the epilogue
+      g.M = static_cast<int>(B); g.N = L; g.K = ly.K;
+      g.A = li == 0 ? w.xb : w.hb + (li - 1) * bl; g.lda = lda;
+      g.B = w.wb + ly.off_w; g.ldb = L; g.b_mn = 1;
+      g.C = z; g.ldc = L; g.bias = m->theta + ly.off_b; g.alpha_dev = clip ? scale + li : nullptr;
+      g.colsum = ly.has_bn ? stats : nullptr;
+      P3D_TRY(tcg::gemm(g, st));
+    } else {
+      Epilogue e; e.bias = m->theta + ly.off_b; e.alpha_dev = clip ? scale + li : nullptr;
+      P3D_TRY(sgemm(false, false, B, L, ly.K, in, lda, m->theta + ly.off_w, L, z, L, e, st));
+    }
     float* mean = w.mean + static_cast<size_t>(li) * L;
     float* rstd = w.rstd + static_cast<size_t>(li) * L;
     if (ly.has_bn) {
-      double* stats = w.stats + 2ull * li * L;
-      colstats_kernel<<<colgrid(L, B), dim3(32, 8), 0, st>>>(z, B, L, stats);
-      P3D_LAUNCH_CHECK();
+      if (!tc) {
+        colstats_kernel<<<colgrid(L, B), dim3(32, 8), 0, st>>>(z, B, L, stats);
+        P3D_LAUNCH_CHECK();
+      }
       P3D_TRY(allreduce(m, stats, 2ull * L, ncclDouble, st));
       bn_finalize_kernel<<<(L + 255) / 256, 256, 0, st>>>(stats, invBg, L, mean, rstd, m->moving + ly.off_mm, m->moving + ly.off_mv);
       P3D_LAUNCH_CHECK();
@@ -386,7 +456,7 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
     a.z = z; a.mean = mean; a.rstd = rstd;
     a.gamma = ly.has_bn ? m->theta + ly.off_gamma : nullptr; a.beta = ly.has_bn ? m->theta + ly.off_beta : nullptr;
     a.res = (residual && li >= 2 && (li % 2) == 0) ? w.h + (li - 2) * bl : nullptr;
-    a.h = w.h + li * bl; a.mask = maskbuf + li * bl; a.mask_in = mask_in ? mask_in + li * bl : nullptr;
+    a.h = w.h + li * bl; a.hb = tc ? w.hb + li * bl : nullptr; a.mask = maskbuf + li * bl; a.mask_in = mask_in ? mask_in + li * bl : nullptr;
     a.keep = keep; a.seed = seed; a.step = static_cast<unsigned>(m->global_step); a.layer = li;
     a.row0 = row0; a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
     fwd_act_kernel<<<egrid(static_cast<long long>(bl / 4)), 256, 0, st>>>(a);
@@ -394,11 +464,21 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   }
   {
     const Layer& ly = m->layers[nh];
-    Epilogue e; e.bias = m->theta + ly.off_b; e.alpha_dev = clip ? scale + nh : nullptr;
-    P3D_TRY(sgemm(false, false, B, out, L, w.h + (nh - 1) * bl, L, m->theta + ly.off_w, out, y, out, e, st));
+    if (tc) {
+      GemmArgs g;
+      g.M = static_cast<int>(B); g.N = out; g.K = L;
+      g.A = w.hb + (nh - 1) * bl; g.lda = L;
+      g.B = w.wb + ly.off_w; g.ldb = kOutPad; g.b_mn = 1;
+      g.C = y; g.ldc = out; g.bias = m->theta + ly.off_b; g.alpha_dev = clip ? scale + nh : nullptr;
+      P3D_TRY(tcg::gemm(g, st));
+    } else {
+      Epilogue e; e.bias = m->theta + ly.off_b; e.alpha_dev = clip ? scale + nh : nullptr;
+      P3D_TRY(sgemm(false, false, B, out, L, w.h + (nh - 1) * bl, L, m->theta + ly.off_w, out, y, out, e, st));
+    }
   }
   const size_t ny = static_cast<size_t>(B) * out;
-  loss_dy_kernel<<<egrid(static_cast<long long>(ny)), 256, 0, st>>>(y, t, ny, static_cast<float>(2.0 * invBg / out), w.dy, lossacc);
+  loss_dy_kernel<<<egrid(static_cast<long long>(ny)), 256, 0, st>>>(y, t, ny, static_cast<float>(2.0 * invBg / out), w.dy, lossacc,
+                                                                          tc ? w.dyb : nullptr, out, kOutPad);
   P3D_LAUNCH_CHECK();
   P3D_TRY(allreduce(m, lossacc, 1, ncclDouble, st));
   // ---------------------------------------------------------------- backward
@@ -406,12 +486,30 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   int cur = 0, keepi = -1;
   {
     const Layer& ly = m->layers[nh];
-    Epilogue e0;
-    P3D_TRY(sgemm(true, false, L, out, static_cast<int>(B), w.h + (nh - 1) * bl, L, w.dy, out, m->grad + ly.off_w, out, e0, st));
+    if (tc) {
+      GemmArgs gw;   // dW4 = h^T dy  (reduction over the batch: both operands MN-major, split-K)
+      gw.M = L; gw.N = out; gw.K = static_cast<int>(B);
+      gw.A = w.hb + (nh - 1) * bl; gw.lda = L; gw.a_mn = 1;
+      gw.B = w.dyb; gw.ldb = kOutPad; gw.b_mn = 1;
+      gw.C = m->grad + ly.off_w; gw.ldc = out; gw.split_k = 1;
+      P3D_TRY(tcg::gemm(gw, st));
+    } else {
+      Epilogue e0;
+      P3D_TRY(sgemm(true, false, L, out, static_cast<int>(B), w.h + (nh - 1) * bl, L, w.dy, out, m->grad + ly.off_w, out, e0, st));
+    }
     colsum_kernel<<<colgrid(out, B), dim3(32, 8), 0, st>>>(w.dy, B, out, m->grad + ly.off_b);
     P3D_LAUNCH_CHECK();
-    Epilogue e1; e1.alpha_dev = clip ? scale + nh : nullptr;
-    P3D_TRY(sgemm(false, true, B, L, out, w.dy, out, m->theta + ly.off_w, out, G[cur], L, e1, st));
+    if (tc) {
+      GemmArgs gd;   // dh = dy W4^T * clip
+      gd.M = static_cast<int>(B); gd.N = L; gd.K = out;
+      gd.A = w.dyb; gd.lda = kOutPad;
+      gd.B = w.wb + ly.off_w; gd.ldb = kOutPad;
+      gd.C = G[cur]; gd.ldc = L; gd.alpha_dev = clip ? scale + nh : nullptr;
+      P3D_TRY(tcg::gemm(gd, st));
+    } else {
+      Epilogue e1; e1.alpha_dev = clip ? scale + nh : nullptr;
+      P3D_TRY(sgemm(false, true, B, L, out, w.dy, out, m->theta + ly.off_w, out, G[cur], L, e1, st));
+    }
   }
   for (int li = nh - 1; li >= 0; --li) {
     const Layer& ly = m->layers[li];
@@ -419,13 +517,14 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
     BwdArgs a;
     a.dh = G[cur]; a.z = w.z + li * bl; a.mean = w.mean + static_cast<size_t>(li) * L; a.rstd = w.rstd + static_cast<size_t>(li) * L;
     a.gamma = ly.has_bn ? m->theta + ly.off_gamma : nullptr; a.beta = ly.has_bn ? m->theta + ly.off_beta : nullptr;
-    a.mask = maskbuf + li * bl; a.dz = w.dz; a.sums = w.red + 2ull * li * L; a.inv_keep = 1.f / keep;
+    a.mask = maskbuf + li * bl; a.dz = w.dz; a.dzb = (tc && !ly.has_bn) ? w.dzb : nullptr; a.sums = w.red + 2ull * li * L; a.inv_keep = 1.f / keep;
     a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
     bwd_act_kernel<<<colgrid(L, B), dim3(32, 8), 0, st>>>(a);
     P3D_LAUNCH_CHECK();
     if (ly.has_bn) {
       P3D_TRY(allreduce(m, a.sums, 2ull * L, ncclDouble, st));
-      bwd_bn_kernel<<<egrid(static_cast<long long>(bl)), 256, 0, st>>>(w.dz, a.z, a.mean, a.rstd, a.gamma, a.sums, static_cast<float>(invBg), B, L);
+      bwd_bn_kernel<<<egrid(static_cast<long long>(bl)), 256, 0, st>>>(w.dz, a.z, a.mean, a.rstd, a.gamma, a.sums, static_cast<float>(invBg), B, L,
+                                                                         tc ? w.dzb : nullptr);
       P3D_LAUNCH_CHECK();
       // the sums are already global after the all-reduce, so every rank holds the full dgamma/dbeta;
       // pre-divide by world so that the flat gradient all-reduce (a sum) restores them exactly once.
@@ -438,15 +537,34 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
     }
     const float* in = li == 0 ? x : w.h + (li - 1) * bl;
     const int lda = li == 0 ? kIn : L;
-    Epilogue e0;
-    P3D_TRY(sgemm(true, false, ly.K, L, static_cast<int>(B), in, lda, w.dz, L, m->grad + ly.off_w, L, e0, st));
+    if (tc) {
+      GemmArgs gw;   // dW = in^T dz
+      gw.M = ly.K; gw.N = L; gw.K = static_cast<int>(B);
+      gw.A = li == 0 ? w.xb : w.hb + (li - 1) * bl; gw.lda = lda; gw.a_mn = 1;
+      gw.B = w.dzb; gw.ldb = L; gw.b_mn = 1;
+      gw.C = m->grad + ly.off_w; gw.ldc = L; gw.split_k = 1;
+      P3D_TRY(tcg::gemm(gw, st));
+    } else {
+      Epilogue e0;
+      P3D_TRY(sgemm(true, false, ly.K, L, static_cast<int>(B), in, lda, w.dz, L, m->grad + ly.off_w, L, e0, st));
+    }
     if (li > 0) {
       int nxt = 0;
       while (nxt == cur || nxt == keepi) ++nxt;
-      Epilogue e1; e1.alpha_dev = clip ? scale + li : nullptr;
       const bool add = residual && (li % 2) == 1 && keepi >= 0;
-      if (add) e1.res = G[keepi];
-      P3D_TRY(sgemm(false, true, B, L, L, w.dz, L, m->theta + ly.off_w, L, G[nxt], L, e1, st));
+      if (tc) {
+        GemmArgs gd;   // dh_prev = dz W^T * clip (+ the gradient that bypassed the block)
+        gd.M = static_cast<int>(B); gd.N = L; gd.K = L;
+        gd.A = w.dzb; gd.lda = L;
+        gd.B = w.wb + ly.off_w; gd.ldb = L;
+        gd.C = G[nxt]; gd.ldc = L; gd.alpha_dev = clip ? scale + li : nullptr;
+        if (add) { gd.res = G[keepi]; gd.ldres = L; }
+        P3D_TRY(tcg::gemm(gd, st));
+      } else {
+        Epilogue e1; e1.alpha_dev = clip ? scale + li : nullptr;
+        if (add) e1.res = G[keepi];
+        P3D_TRY(sgemm(false, true, B, L, L, w.dz, L, m->theta + ly.off_w, L, G[nxt], L, e1, st));
+      }
       if (add) keepi = -1;
       cur = nxt;
     }

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "p3d_root_center_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "p3d_procrustes_mpjpe": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p,
                                      c_void_p, c_void_p]),
+    "p3d_procrustes_mpjpe_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p,
+                                     c_void_p, c_void_p]),
     "p3d_similarity_transform_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
     "p3d_debug_latency_stamps": (c_int, [c_void_p, c_void_p, c_int]),

@@ -11,11 +11,16 @@ from ._lib import lib, check
 
 
 def mpjpe(poses3d_n, dec_out_n, data_mean_3d, data_std_3d, procrustes=False, predict_14=False,
-          return_dists=False, dist=None):
+          return_dists=False, dist=None, precision="fp32"):
     """poses3d_n / dec_out_n: normalised prediction / ground truth [N,48|42] (NumPy or torch CUDA).
     Returns (total_err, joint_err[J]) in mm, plus dists[N,J] if return_dists.
     `dist`: a torch.distributed module/process group owner - when given, the per-joint sums and the
-    pose count are all-reduced so that every rank returns the global error."""
+    pose count are all-reduced so that every rank returns the global error.
+    `precision`: "fp32" = the HBM-bound kernel (means within 1e-5 mm of the float64 reference, single
+    distances within 1e-3 mm); "fp64" = all alignment arithmetic in double (distances within 1e-6 mm)."""
+    if precision not in ("fp32", "fp64"):
+        raise ValueError("precision must be 'fp32' or 'fp64'")
+    kernel = lib.p3d_procrustes_mpjpe if precision == "fp32" else lib.p3d_procrustes_mpjpe_f64
     torch = _lib.require_cuda()
     pd, _ = _dev.to_device(poses3d_n, torch.float32)
     gd, _ = _dev.to_device(dec_out_n, torch.float32, pd.device)
@@ -30,7 +35,7 @@ def mpjpe(poses3d_n, dec_out_n, data_mean_3d, data_std_3d, procrustes=False, pre
     sums = torch.zeros(J + 1, dtype=torch.float64, device=pd.device)
     dists = torch.empty((N, J), dtype=torch.float32, device=pd.device) if return_dists else None
     with torch.cuda.device(pd.device):
-        check(lib.p3d_procrustes_mpjpe(pd.data_ptr(), gd.data_ptr(), _lib.np_ptr(mean), _lib.np_ptr(std),
+        check(kernel(pd.data_ptr(), gd.data_ptr(), _lib.np_ptr(mean), _lib.np_ptr(std),
                                        int(predict_14), int(bool(procrustes)), N,
                                        dists.data_ptr() if return_dists else None, sums.data_ptr(),
                                        _lib.current_stream()))

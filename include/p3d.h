@@ -158,10 +158,16 @@ int p3d_root_center_f64(const double* in, double* out, double* roots_or_null, in
  * procrustes.compute_similarity_transform(gt, out, compute_optimal_scale=True) (src/procrustes.py:2-63).
  * pred_n, gt_n: normalised [N,48|42] fp32.  dists_or_null[N,J] (J=17|14) per-joint errors in mm;
  * joint_sum[J] DEVICE doubles are ACCUMULATED into (caller zeroes them), so that joint_err =
- * joint_sum/N and total_err = sum(joint_sum)/(N*J). */
+ * joint_sum/N and total_err = sum(joint_sum)/(N*J).
+ * p3d_procrustes_mpjpe is the HBM-bound fp32 kernel (MPJPE / per-joint means within 1e-5 mm of the NumPy
+ * float64 reference, single per-pose distances within 1e-3 mm); p3d_procrustes_mpjpe_f64 does all alignment
+ * arithmetic in fp64 (distances within 1e-6 mm, ~3x slower).  pred_n / gt_n must be 16-byte aligned. */
 int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* mean3d_host, const double* std3d_host,
                          int predict_14, int use_procrustes, int64_t N, float* dists_or_null, double* joint_sum,
                          void* stream);
+int p3d_procrustes_mpjpe_f64(const float* pred_n, const float* gt_n, const double* mean3d_host, const double* std3d_host,
+                             int predict_14, int use_procrustes, int64_t N, float* dists_or_null, double* joint_sum,
+                             void* stream);
 /* Batched procrustes.compute_similarity_transform on raw poses X,Y[N,J,3] f64 (J<=17):
  * d[N], Z[N,J,3], T[N,9], b[N], c[N,3]; any output may be NULL. */
 int p3d_similarity_transform_f64(const double* X, const double* Y, int J, int compute_optimal_scale, int64_t N,

@@ -29,4 +29,22 @@ void hc_project_f32(const float* P, const double* cam, float* out, int n) {
     p3d::project_point(c, P[3 * i], P[3 * i + 1], P[3 * i + 2], out[6 * i], out[6 * i + 1], out[6 * i + 2], out[6 * i + 3],
                        out[6 * i + 4], out[6 * i + 5]);
 }
+
+void hc_kabsch_f32(const float* A, float* T, float* tr, int n) {
+  for (int i = 0; i < n; ++i) p3d::kabsch_rotation_f32(A + 9 * i, T + 9 * i, tr[i]);
+}
+
+// fp32 evaluation math: dists[n][J] for normalised gt/pred rows [n][W]  (W = 48 with the hip joint, or 42)
+void hc_pose_errors_f32(const float* gt, const float* pred, const float* sd, const float* mc, const float* hipc, int W,
+                        int use_procrustes, float* dists, int n) {
+  const int J = (W == 48) ? 17 : 14;
+  for (int i = 0; i < n; ++i) {
+    const float* g = gt + (long long)i * W;
+    const float* p = pred + (long long)i * W;
+    auto lg = [g](int k) { return g[k]; };
+    auto lp = [p](int k) { return p[k]; };
+    if (W == 48) p3d::pose_errors_f32<48, 1>(lg, lp, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
+    else p3d::pose_errors_f32<42, 0>(lg, lp, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
+  }
+}
 }

@@ -87,6 +87,61 @@ def test_gradients_match_oracle(cfg):
     m.close()
 
 
+TC_CFGS = [M.Config(1024, 2, True, True, True), M.Config(1024, 2, True, True, False), M.Config(256, 1, False, True, True),
+           M.Config(64, 2, True, False, False), M.Config(128, 0, True, True, True)]
+
+
+@pytest.mark.parametrize("B", [64, 200, 1024])
+@pytest.mark.parametrize("cfg", TC_CFGS, ids=lambda c: f"L{c.linear_size}n{c.num_layers}r{int(c.residual)}b{int(c.batch_norm)}m{int(c.max_norm)}")
+def test_bf16_tensor_core_step_matches_oracle(cfg, B):
+    """mode='bf16': every GEMM of the step runs on tcgen05 with bf16 operands (fp32 accumulate, fp32 master
+    weights).  Operand rounding is 2^-9 relative per element, so against the fp64 oracle: loss and outputs within
+    1e-2 (north_star's bf16 tolerance), every gradient tensor within 5e-2 of its largest entry and 5e-2 in
+    relative L2; biases in front of a BatchNorm stay EXACTLY zero-gradient."""
+    if B > 64 and cfg.linear_size > 256 and not cfg.max_norm:
+        pytest.skip("covered at B=64")
+    keep = 0.5
+    m, p = make_model(cfg, seed=31, bn="trained", mode="bf16", lr=1e-3)
+    nh = 2 * cfg.num_layers + 1
+    x, t = synth.mlp_inputs(B, seed=77)
+    masks = (np.random.RandomState(4).uniform(size=(nh, B, cfg.linear_size)) < keep).astype(np.uint8)
+    loss, _, _, yk = m.step(None, x, t, keep, isTraining=True, dropout_mask=masks)
+    got = m.get_gradients()
+    y, cache = M.forward(p, x.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True)
+    rloss = float(np.mean((y - t.astype(np.float64)) ** 2))
+    assert abs(float(loss) - rloss) <= 1e-2 * max(1.0, rloss), (float(loss), rloss)
+    assert np.abs(yk - y).max() <= 1e-2 * max(np.abs(y).max(), 1.0)
+    grads = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cache, y)
+    for name, g in grads.items():
+        scale = np.abs(g).max()
+        if scale < 1e-12:
+            assert np.abs(got[name]).max() == 0.0, name
+            continue
+        d = got[name].astype(np.float64) - g
+        assert np.abs(d).max() <= 5e-2 * scale, (name, np.abs(d).max(), scale)
+        assert np.linalg.norm(d) <= 5e-2 * np.linalg.norm(g), (name, np.linalg.norm(d) / np.linalg.norm(g))
+    m.close()
+
+
+def test_bf16_and_fp32_training_trajectories_agree():
+    """20 Adam steps from the same initial state in both modes: the loss curves stay within 2%."""
+    cfg = M.Config(1024, 2, True, True, True)
+    losses = {}
+    for mode in ("fp32", "bf16"):
+        m, _ = make_model(cfg, seed=3, bn="fresh", mode=mode, lr=1e-3)
+        out = []
+        for s in range(20):
+            x, t = synth.mlp_inputs(256, seed=100 + s)
+            masks = (np.random.RandomState(s).uniform(size=(5, 256, 1024)) < 0.5).astype(np.uint8)
+            loss, _, _, _ = m.step(None, x, t, 0.5, isTraining=True, dropout_mask=masks)
+            out.append(float(loss))
+        losses[mode] = np.array(out)
+        m.close()
+    assert np.all(np.isfinite(losses["bf16"]))
+    assert np.abs(losses["bf16"] - losses["fp32"]).max() <= 2e-2 * losses["fp32"].max(), (losses["bf16"], losses["fp32"])
+    assert losses["fp32"][-1] < losses["fp32"][0]
+
+
 def test_gradients_via_single_step_sgd_like_probe():
     """One step from zero Adam state moves every variable by -alpha*sign(g) (|m|/sqrt(v) = 1 up to eps):
     the sign pattern of the update must equal the sign of the oracle gradient wherever |g| is not tiny."""

@@ -19,6 +19,7 @@ from p3d import LinearModel, data_utils, evaluate  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on bounded samples")
+ap.add_argument("--no-train", action="store_true", help="skip the training-step timings")
 args = ap.parse_args()
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
 HBM = peaks["hbm_gbs"]
@@ -68,14 +69,30 @@ for use_proc in (True, False):
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": HBM, "unit": "GB/s", "frac": gbs / HBM,
                                    "algorithmic_bytes": b, "note": "includes the D2H read of the 18 sums"}}))
 
+# kernel only (no allocation, no D2H of the sums): what the HBM roofline fraction of the kernel itself is
+from p3d import _lib  # noqa: E402
+sums = torch.zeros(18, dtype=torch.float64, device="cuda")
+m3h, s3h = np.ascontiguousarray(m3, dtype=np.float64), np.ascontiguousarray(s3, dtype=np.float64)
+for prec, fn in (("fp32", _lib.lib.p3d_procrustes_mpjpe), ("fp64", _lib.lib.p3d_procrustes_mpjpe_f64)):
+    for use_proc in (True, False):
+        ms = timeit(lambda: _lib.check(fn(pr.data_ptr(), gt.data_ptr(), _lib.np_ptr(m3h), _lib.np_ptr(s3h), 0, int(use_proc), NE,
+                                          None, sums.data_ptr(), _lib.current_stream())), iters=10)
+        b = NE * 384
+        gbs = b / (ms * 1e-3) / 1e9
+        print(json.dumps({"workload": f"kernel only, {prec}: un-normalise + {'Procrustes + ' if use_proc else ''}MPJPE", "poses": NE, "ms": ms,
+                          "poses_per_s": NE / (ms * 1e-3),
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": HBM, "unit": "GB/s", "frac": gbs / HBM,
+                                       "algorithmic_bytes": b}}))
+
 # ---- training step (dropout keep 0.5, max_norm, Adam): batch 64 and 4096
-for B in (64, 4096):
-    model = LinearModel(1024, 2, True, True, True, B, 1e-3, seed=1)
+for B, mode in (() if args.no_train else ((64, "bf16"), (4096, "bf16"), (64, "fp32"), (4096, "fp32"))):
+    model = LinearModel(1024, 2, True, True, True, B, 1e-3, seed=1, mode=mode)
     x = torch.randn((B, 32), device="cuda", generator=g)
     t = torch.randn((B, 48), device="cuda", generator=g)
     ms = timeit(lambda: model.step(None, x, t, 0.5, isTraining=True), warm=3, iters=20)
     flop = B * 25_591_808
-    print(json.dumps({"workload": f"training step batch {B} (fp32 FFMA GEMMs)", "ms_per_step": ms, "poses_per_s": B / (ms * 1e-3),
+    kind = "tcgen05 bf16 GEMMs, fp32 master weights" if mode == "bf16" else "fp32 FFMA GEMMs"
+    print(json.dumps({"workload": f"training step batch {B} ({kind})", "ms_per_step": ms, "poses_per_s": B / (ms * 1e-3),
                       "tflops": flop / (ms * 1e-3) / 1e12}))
     model.close()
 
