@@ -82,6 +82,11 @@ struct FusedArgs {
 // The camera-frame root-centred joint is R(q - hip): T cancels, so the hip is subtracted once in world space.
 constexpr int PN_WARPS = 8;
 #define PIN(v) asm volatile("" : "+f"(v))
+// NC = number of cameras, compile time: the camera loop is fully unrolled so that every camera parameter is an
+// immediate constant-bank operand of the FFMA that uses it (with a runtime camera index ptxas emits ~30 LDC per
+// camera and the kernel was issue bound: 706 warp instructions per pose pair, SM 85 % busy at 51 % of the HBM
+// roofline).
+template <int NC>
 __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
                                                                             float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
   __shared__ __align__(16) float s_in[PN_WARPS][2 * 96];
@@ -89,7 +94,6 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int lp = lane >> 4, j = lane & 15;
   float* sw = s_in[wib];
-  // per-lane constants (indexing the tables with a per-lane index inside the loop would serialise the constant cache)
   const int j2 = kJoints2D[j];
   const bool has3 = j < a.nj3;
   const int j3 = has3 ? (a.predict_14 ? kJoints3D14[j] : kJoints3D16[j]) : 0;
@@ -97,17 +101,18 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
   float m3[3], i3[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { m3[d] = has3 ? a.mean3[3 * j + d] : 0.f; i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; }
-  // Pin the per-lane constants in registers: left alone, ptxas rematerialises them INSIDE the camera loop as
-  // lane-indexed constant loads (LDC c[0][R+..]), which serialise 16 ways - measured 2.5x slower.
+  // Pin the per-lane constants in registers: left alone, ptxas rematerialises them inside the loop as lane-indexed
+  // constant loads (LDC c[0][R+..]), which serialise 16 ways - measured 2.5x slower.
   PIN(m2x); PIN(m2y); PIN(i2x); PIN(i2y);
 #pragma unroll
   for (int d = 0; d < 3; ++d) { PIN(m3[d]); PIN(i3[d]); }
   const int out3 = a.out3;
   const int pair_f4 = 2 * out3 / 4;                       // float4s per camera per pose pair (24 or 21)
-  const bool y_vec = y3d && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0);
+  const bool y_vec = y3d && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0) && ((2 * out3) % 4 == 0);
   const long long npairs = (N + 1) / 2;
   const long long nwarps = static_cast<long long>(gridDim.x) * PN_WARPS;
   const long long tot_f4 = N * 24;
+  const long long x_cam_stride = N * 32, y_cam_stride = N * out3;      // floats between camera planes
   const float4* src = reinterpret_cast<const float4*>(world);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   long long pair = static_cast<long long>(blockIdx.x) * PN_WARPS + wib;
@@ -119,8 +124,7 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
   }
   int buf = 0;
   for (; pair < npairs; pair += nwarps) {
-    // prefetch the next pair of this warp
-    float4 n0 = zero4, n1 = zero4;
+    float4 n0 = zero4, n1 = zero4;                          // prefetch the next pair of this warp
     {
       const long long b = (pair + nwarps) * 48;
       if (b + lane < tot_f4) n0 = __ldcs(src + b + lane);
@@ -131,46 +135,47 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
     __syncwarp();
     const long long p = pair * 2 + lp;
     const bool live = p < N;
+    const bool full = pair * 2 + 1 < N;
     const float* w = sw + lp * 96;
     const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
     const float qx = w[j3 * 3] - w[0], qy = w[j3 * 3 + 1] - w[1], qz = w[j3 * 3 + 2] - w[2];
     __syncwarp();                                    // slab consumed: the next iteration may overwrite it
-    for (int c = 0; c < a.ncams; ++c) {
-      const CamT<float>& cam = a.cam[c];
+    float2* xo = reinterpret_cast<float2*>(x2d + p * 32) + j;
+    float* yo = y3d + pair * 2 * out3;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
       if (x2d) {
         // cameras.project_point_radial (src/cameras.py:39-51) in fp32
-        const float dx = px - cam.Tr[0], dy = py - cam.Tr[1], dz = pz - cam.Tr[2];
-        const float X0 = cam.R[0] * dx + cam.R[1] * dy + cam.R[2] * dz;
-        const float X1 = cam.R[3] * dx + cam.R[4] * dy + cam.R[5] * dz;
-        const float X2 = cam.R[6] * dx + cam.R[7] * dy + cam.R[8] * dz;
+        const float dx = px - a.cam[c].Tr[0], dy = py - a.cam[c].Tr[1], dz = pz - a.cam[c].Tr[2];
+        const float X0 = a.cam[c].R[0] * dx + a.cam[c].R[1] * dy + a.cam[c].R[2] * dz;
+        const float X1 = a.cam[c].R[3] * dx + a.cam[c].R[4] * dy + a.cam[c].R[5] * dz;
+        const float X2 = a.cam[c].R[6] * dx + a.cam[c].R[7] * dy + a.cam[c].R[8] * dz;
         const float rz = __frcp_rn(X2);
         const float x = X0 * rz, y = X1 * rz;
         const float r2 = x * x + y * y;
-        const float radial = 1.f + r2 * (cam.k[0] + r2 * (cam.k[1] + r2 * cam.k[2]));
-        const float s = radial + (cam.p[0] * y + cam.p[1] * x);
-        const float u = cam.f[0] * (x * s + cam.p[1] * r2) + cam.c[0];
-        const float v = cam.f[1] * (y * s + cam.p[0] * r2) + cam.c[1];
-        if (live)
-          __stcs(reinterpret_cast<float2*>(x2d + (static_cast<long long>(c) * N + p) * 32) + j,
-                 make_float2((u - m2x) * i2x, (v - m2y) * i2y));
+        const float radial = 1.f + r2 * (a.cam[c].k[0] + r2 * (a.cam[c].k[1] + r2 * a.cam[c].k[2]));
+        const float s = radial + (a.cam[c].p[0] * y + a.cam[c].p[1] * x);
+        const float u = a.cam[c].f[0] * (x * s + a.cam[c].p[1] * r2) + a.cam[c].c[0];
+        const float v = a.cam[c].f[1] * (y * s + a.cam[c].p[0] * r2) + a.cam[c].c[1];
+        if (live) __stcs(xo, make_float2((u - m2x) * i2x, (v - m2y) * i2y));   // 256 contiguous bytes per warp
+        xo += x_cam_stride / 2;
       }
       if (y3d) {
         float* so = s_out[wib][buf];
         if (has3) {
           float* o = so + lp * out3 + 3 * j;
-          o[0] = ((cam.R[0] * qx + cam.R[1] * qy + cam.R[2] * qz) - m3[0]) * i3[0];
-          o[1] = ((cam.R[3] * qx + cam.R[4] * qy + cam.R[5] * qz) - m3[1]) * i3[1];
-          o[2] = ((cam.R[6] * qx + cam.R[7] * qy + cam.R[8] * qz) - m3[2]) * i3[2];
+          o[0] = ((a.cam[c].R[0] * qx + a.cam[c].R[1] * qy + a.cam[c].R[2] * qz) - m3[0]) * i3[0];
+          o[1] = ((a.cam[c].R[3] * qx + a.cam[c].R[4] * qy + a.cam[c].R[5] * qz) - m3[1]) * i3[1];
+          o[2] = ((a.cam[c].R[6] * qx + a.cam[c].R[7] * qy + a.cam[c].R[8] * qz) - m3[2]) * i3[2];
         }
         __syncwarp();
-        float* dst = y3d + (static_cast<long long>(c) * N + pair * 2) * out3;
-        const bool full = pair * 2 + 1 < N;
-        if (y_vec && full && ((pair * 2 * out3) & 3) == 0) {
-          if (lane < pair_f4) __stcs(reinterpret_cast<float4*>(dst) + lane, reinterpret_cast<const float4*>(so)[lane]);
+        if (y_vec && full) {
+          if (lane < pair_f4) __stcs(reinterpret_cast<float4*>(yo) + lane, reinterpret_cast<const float4*>(so)[lane]);
         } else {
           const int tot = (full ? 2 : 1) * out3;
-          for (int i = lane; i < tot; i += 32) __stcs(dst + i, so[i]);
+          for (int i = lane; i < tot; i += 32) __stcs(yo + i, so[i]);
         }
+        yo += y_cam_stride;
         buf ^= 1;                                    // the other slab is free: its readers passed the __syncwarp above
       }
     }
@@ -332,7 +337,12 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
   }
   const long long nblocks = ((N + 1) / 2 + PN_WARPS - 1) / PN_WARPS;
   const int grid = nblocks < 148 * 3 ? (int)nblocks : 148 * 3;
-  project_normalize_kernel<<<grid, PN_WARPS * 32, 0, (cudaStream_t)stream>>>(world, a, x2d, y3d, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ncams) {
+#define P3D_PN_CASE(NC) case NC: project_normalize_kernel<NC><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N); break;
+    P3D_PN_CASE(1) P3D_PN_CASE(2) P3D_PN_CASE(3) P3D_PN_CASE(4) P3D_PN_CASE(5) P3D_PN_CASE(6) P3D_PN_CASE(7) P3D_PN_CASE(8)
+#undef P3D_PN_CASE
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

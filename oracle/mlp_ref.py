@@ -127,8 +127,15 @@ class Config:
     out_size: int = 48
 
 
-def forward(p, x, cfg: Config, training=False, keep_prob=1.0, masks=None, want_cache=False):
+def forward(p, x, cfg: Config, training=False, keep_prob=1.0, masks=None, want_cache=False, quant=None):
     """The graph of linear_model.py:102-125 + two_linear :154-201.
+
+    quant: None for the reference arithmetic.  A rounding function (e.g. bfloat16 round-to-nearest)
+    makes this a statement of the tensor-core training path's rounding points instead: both operands
+    of every MatMul are rounded (activations and the UNCLIPPED weights), the clip scale multiplies the
+    product, everything else stays in high precision.  Used to test that path at tight tolerances:
+    against the exact graph a reduced-precision forward flips the ReLU derivative of the few units
+    whose pre-activation is within rounding of zero, which is a large error in max-norm.
 
     masks: list of 0/1 arrays [B,L] (one per hidden layer, graph order) standing in
     for floor(keep_prob + U[0,1)) of tf.nn.dropout (linear_model.py:114,184,196);
@@ -148,13 +155,19 @@ def forward(p, x, cfg: Config, training=False, keep_prob=1.0, masks=None, want_c
             wc, nrm = clip_by_norm(w)
         else:
             wc = w
-        z = h @ wc + p[bn_]
+        if quant is None:
+            z = h @ wc + p[bn_]
+            h_op, w_op, s_op = h, wc, 1.0
+        else:
+            h_op, w_op = quant(h).astype(dt), quant(w).astype(dt)
+            s_op = (1.0 / max(nrm, 1.0)) if cfg.max_norm else 1.0
+            z = (h_op @ w_op) * dt.type(s_op) + p[bn_]
         if li == n_hidden:             # output layer: no BN / ReLU / dropout (linear_model.py:124)
             if want_cache:
-                cache.append(dict(h_in=h, wc=wc, nrm=nrm))
+                cache.append(dict(h_in=h_op, wc=w_op, nrm=nrm, s=s_op))
             h = z
             break
-        c = dict(h_in=h, wc=wc, nrm=nrm)
+        c = dict(h_in=h_op, wc=w_op, nrm=nrm, s=s_op)
         if cfg.batch_norm:
             g, b = p[bns + "/gamma"], p[bns + "/beta"]
             if training:
@@ -193,9 +206,10 @@ def loss_fn(y, t):
     return float(np.mean(d * d))
 
 
-def backward(p, x, t, cfg: Config, cache, y):
+def backward(p, x, t, cfg: Config, cache, y, quant=None):
     """Gradients of loss wrt every trainable variable (what opt.compute_gradients builds,
-    linear_model.py:143).  Differentiates through clip_by_norm and batch-stat BN."""
+    linear_model.py:143).  Differentiates through clip_by_norm and batch-stat BN.
+    quant: see forward() - the upstream gradient operand of every MatMul is rounded as well."""
     names = layer_names(cfg.num_layers)
     B = x.shape[0]
     grads = {}
@@ -205,7 +219,8 @@ def backward(p, x, t, cfg: Config, cache, y):
     def wgrad(li, dz):
         wn, bn_, _ = names[li]
         c = cache[li]
-        g_wc = c["h_in"].T @ dz
+        dz_op = dz if quant is None else quant(dz).astype(dz.dtype)
+        g_wc = c["h_in"].T @ dz_op
         if cfg.max_norm and c["nrm"] is not None and c["nrm"] > 1.0:
             w = p[wn]
             nrm = c["nrm"]
@@ -215,7 +230,7 @@ def backward(p, x, t, cfg: Config, cache, y):
             g_w = g_wc
         grads[wn] = g_w
         grads[bn_] = dz.sum(axis=0)
-        return dz @ c["wc"].T
+        return (dz_op @ c["wc"].T) * c["s"]
 
     dh = wgrad(n_hidden, dy)
     dres = None  # gradient flowing along the residual stream into the previous block output

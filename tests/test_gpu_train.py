@@ -95,32 +95,48 @@ TC_CFGS = [M.Config(1024, 2, True, True, True), M.Config(1024, 2, True, True, Fa
 @pytest.mark.parametrize("cfg", TC_CFGS, ids=lambda c: f"L{c.linear_size}n{c.num_layers}r{int(c.residual)}b{int(c.batch_norm)}m{int(c.max_norm)}")
 def test_bf16_tensor_core_step_matches_oracle(cfg, B):
     """mode='bf16': every GEMM of the step runs on tcgen05 with bf16 operands (fp32 accumulate, fp32 master
-    weights).  Operand rounding is 2^-9 relative per element, so against the fp64 oracle: loss and outputs within
-    1e-2 (north_star's bf16 tolerance), every gradient tensor within 5e-2 of its largest entry and 5e-2 in
-    relative L2; biases in front of a BatchNorm stay EXACTLY zero-gradient."""
+    weights).
+    (1) Against the oracle restated with the SAME rounding points (oracle forward/backward(quant=bf16)): loss,
+        outputs and every gradient within 2e-3 relative L2 / 1% of the tensor's largest entry - what is left is
+        fp32-vs-fp64 accumulation and the odd ReLU unit whose pre-activation is within 1e-6 of zero.
+    (2) Against the exact fp64 graph: loss and outputs within 1e-2 (north_star's bf16 tolerance).  Gradients are
+        only loosely comparable there: operand rounding moves pre-activations by ~2^-9, which flips the ReLU
+        derivative of ~0.3% of the units, i.e. ~sqrt(0.003) = 5% in relative L2 (measured 3-10%) - so: <= 20%.
+    Biases in front of a BatchNorm stay EXACTLY zero-gradient."""
     if B > 64 and cfg.linear_size > 256 and not cfg.max_norm:
         pytest.skip("covered at B=64")
+    from helpers import bf16_round
     keep = 0.5
     m, p = make_model(cfg, seed=31, bn="trained", mode="bf16", lr=1e-3)
     nh = 2 * cfg.num_layers + 1
     x, t = synth.mlp_inputs(B, seed=77)
+    x64, t64 = x.astype(np.float64), t.astype(np.float64)
     masks = (np.random.RandomState(4).uniform(size=(nh, B, cfg.linear_size)) < keep).astype(np.uint8)
     loss, _, _, yk = m.step(None, x, t, keep, isTraining=True, dropout_mask=masks)
     got = m.get_gradients()
-    y, cache = M.forward(p, x.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True)
-    rloss = float(np.mean((y - t.astype(np.float64)) ** 2))
+    m.close()
+    # (2) exact graph
+    y, cache = M.forward(p, x64, cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True)
+    rloss = M.loss_fn(y, t64)
     assert abs(float(loss) - rloss) <= 1e-2 * max(1.0, rloss), (float(loss), rloss)
     assert np.abs(yk - y).max() <= 1e-2 * max(np.abs(y).max(), 1.0)
-    grads = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cache, y)
+    grads = M.backward(p, x64, t64, cfg, cache, y)
+    # (1) same rounding points
+    q = lambda a: bf16_round(a).astype(np.float64)  # noqa: E731
+    yq, cq = M.forward(p, x64, cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True, quant=q)
+    gq = M.backward(p, x64, t64, cfg, cq, yq, quant=q)
+    assert abs(float(loss) - M.loss_fn(yq, t64)) <= 1e-4 * max(1.0, rloss)
+    assert np.abs(yk - yq).max() <= 1e-4 * max(np.abs(yq).max(), 1.0)
     for name, g in grads.items():
         scale = np.abs(g).max()
         if scale < 1e-12:
             assert np.abs(got[name]).max() == 0.0, name
             continue
-        d = got[name].astype(np.float64) - g
-        assert np.abs(d).max() <= 5e-2 * scale, (name, np.abs(d).max(), scale)
-        assert np.linalg.norm(d) <= 5e-2 * np.linalg.norm(g), (name, np.linalg.norm(d) / np.linalg.norm(g))
-    m.close()
+        k = got[name].astype(np.float64)
+        assert np.linalg.norm(k - g) <= 0.2 * np.linalg.norm(g), (name, "exact graph", np.linalg.norm(k - g) / np.linalg.norm(g))
+        d = k - gq[name]
+        assert np.linalg.norm(d) <= 2e-3 * np.linalg.norm(gq[name]), (name, "same rounding", np.linalg.norm(d) / np.linalg.norm(gq[name]))
+        assert np.abs(d).max() <= 1e-2 * np.abs(gq[name]).max(), (name, "same rounding", np.abs(d).max(), np.abs(gq[name]).max())
 
 
 def test_bf16_and_fp32_training_trajectories_agree():

@@ -149,3 +149,30 @@ def test_philox_known_answer_and_mask_rate():
     m2 = M.dropout_mask_philox(1234, 7, 2, 100, 128, 0.5, row0=100)
     assert np.array_equal(m[100:200], m2)
     assert M.dropout_mask_philox(1, 0, 0, 8, 8, 1.0).all()
+
+
+def test_quant_hook_identity_and_bf16():
+    """forward/backward(quant=...) restate the tensor-core path's rounding points: with an identity rounding
+    they reproduce the exact graph; with bfloat16 rounding the outputs move by ~2^-9 and the gradients stay
+    close in relative L2 (a few ReLU derivatives flip, so the max-norm is NOT a meaningful comparison)."""
+    from helpers import bf16_round
+    cfg = M.Config(128, 1, True, True, True)
+    p = {k: v.astype(np.float64) for k, v in M.init_params(128, 1, seed=3, bn="trained").items()}
+    rng = np.random.RandomState(0)
+    x, t = rng.standard_normal((64, 32)), rng.standard_normal((64, 48))
+    masks = [(rng.uniform(size=(64, 128)) < 0.5).astype(np.uint8) for _ in range(3)]
+    y0, c0 = M.forward(p, x, cfg, training=True, keep_prob=0.5, masks=masks, want_cache=True)
+    g0 = M.backward(p, x, t, cfg, c0, y0)
+    y1, c1 = M.forward(p, x, cfg, training=True, keep_prob=0.5, masks=masks, want_cache=True, quant=lambda a: a)
+    g1 = M.backward(p, x, t, cfg, c1, y1, quant=lambda a: a)
+    assert np.abs(y1 - y0).max() < 1e-12
+    for k in g0:
+        if np.abs(g0[k]).max() > 1e-12:          # biases in front of a BN layer: zero up to rounding
+            assert np.abs(g1[k] - g0[k]).max() <= 1e-10 * np.abs(g0[k]).max(), k
+    q = lambda a: bf16_round(a).astype(np.float64)  # noqa: E731
+    y2, c2 = M.forward(p, x, cfg, training=True, keep_prob=0.5, masks=masks, want_cache=True, quant=q)
+    g2 = M.backward(p, x, t, cfg, c2, y2, quant=q)
+    assert 1e-5 < np.abs(y2 - y0).max() < 2e-2 * np.abs(y0).max()
+    for k in g0:
+        if np.abs(g0[k]).max() > 1e-12:
+            assert np.linalg.norm(g2[k] - g0[k]) < 0.2 * np.linalg.norm(g0[k]), k
