@@ -85,36 +85,43 @@ constexpr int PN_WARPS = 8;
 // NC = number of cameras, compile time: the camera loop is fully unrolled so that every camera parameter is an
 // immediate constant-bank operand of the FFMA that uses it (with a runtime camera index ptxas emits ~30 LDC per
 // camera and the kernel was issue bound: 706 warp instructions per pose pair, SM 85 % busy at 51 % of the HBM
-// roofline).
-template <int NC>
+// roofline).  H2/H3: which outputs are requested (compile time: no per-camera uniform branches).
+constexpr int PN_POSE_PITCH = 100;   // floats between the two poses of a slab: shifts pose 1 by 4 banks (no 2-way conflicts)
+template <int NC, bool H2, bool H3>
 __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
                                                                             float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
-  __shared__ __align__(16) float s_in[PN_WARPS][2 * 96];
-  __shared__ __align__(16) float s_out[PN_WARPS][2][2 * 48];
+  __shared__ __align__(16) float s_in[PN_WARPS][2 * PN_POSE_PITCH];
+  __shared__ __align__(16) float s_out[PN_WARPS][2][2 * 48 + 4];      // +4: dump slot for lanes without a 3D joint
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int lp = lane >> 4, j = lane & 15;
   float* sw = s_in[wib];
   const int j2 = kJoints2D[j];
   const bool has3 = j < a.nj3;
   const int j3 = has3 ? (a.predict_14 ? kJoints3D14[j] : kJoints3D16[j]) : 0;
-  float m2x = a.mean2[2 * j], m2y = a.mean2[2 * j + 1], i2x = a.istd2[2 * j], i2y = a.istd2[2 * j + 1];
-  float m3[3], i3[3];
+  // out = v * istd + (-mean * istd): one FFMA per output
+  float i2x = a.istd2[2 * j], i2y = a.istd2[2 * j + 1];
+  float n2x = -a.mean2[2 * j] * i2x, n2y = -a.mean2[2 * j + 1] * i2y;
+  float n3[3], i3[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { m3[d] = has3 ? a.mean3[3 * j + d] : 0.f; i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; }
+  for (int d = 0; d < 3; ++d) { i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; n3[d] = has3 ? -a.mean3[3 * j + d] * i3[d] : 0.f; }
   // Pin the per-lane constants in registers: left alone, ptxas rematerialises them inside the loop as lane-indexed
   // constant loads (LDC c[0][R+..]), which serialise 16 ways - measured 2.5x slower.
-  PIN(m2x); PIN(m2y); PIN(i2x); PIN(i2y);
+  PIN(n2x); PIN(n2y); PIN(i2x); PIN(i2y);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) { PIN(m3[d]); PIN(i3[d]); }
+  for (int d = 0; d < 3; ++d) { PIN(n3[d]); PIN(i3[d]); }
   const int out3 = a.out3;
+  const int o_off = has3 ? lp * out3 + 3 * j : 2 * 48;   // smem slot of this lane's 3D joint (or the dump slot)
   const int pair_f4 = 2 * out3 / 4;                       // float4s per camera per pose pair (24 or 21)
-  const bool y_vec = y3d && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0) && ((2 * out3) % 4 == 0);
+  const bool y_vec = H3 && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0) && ((2 * out3) % 4 == 0);
   const long long npairs = (N + 1) / 2;
   const long long nwarps = static_cast<long long>(gridDim.x) * PN_WARPS;
   const long long tot_f4 = N * 24;
   const long long x_cam_stride = N * 32, y_cam_stride = N * out3;      // floats between camera planes
   const float4* src = reinterpret_cast<const float4*>(world);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // staging slots: float4 i of the pair (i < 48) -> pose i / 24, padded pose pitch
+  const int st0 = (lane < 24 ? lane : lane + 1);           // float4 index of chunk `lane`
+  const int st1 = 32 + lane + 1;                           // chunk 32 + lane (lane < 16) is always in pose 1
   long long pair = static_cast<long long>(blockIdx.x) * PN_WARPS + wib;
   float4 c0 = zero4, c1 = zero4;
   if (pair < npairs) {
@@ -130,13 +137,13 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
       if (b + lane < tot_f4) n0 = __ldcs(src + b + lane);
       if (lane < 16 && b + 32 + lane < tot_f4) n1 = __ldcs(src + b + 32 + lane);
     }
-    reinterpret_cast<float4*>(sw)[lane] = c0;
-    if (lane < 16) reinterpret_cast<float4*>(sw)[32 + lane] = c1;
+    reinterpret_cast<float4*>(sw)[st0] = c0;
+    if (lane < 16) reinterpret_cast<float4*>(sw)[st1] = c1;
     __syncwarp();
     const long long p = pair * 2 + lp;
     const bool live = p < N;
     const bool full = pair * 2 + 1 < N;
-    const float* w = sw + lp * 96;
+    const float* w = sw + lp * PN_POSE_PITCH;
     const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
     const float qx = w[j3 * 3] - w[0], qy = w[j3 * 3 + 1] - w[1], qz = w[j3 * 3 + 2] - w[2];
     __syncwarp();                                    // slab consumed: the next iteration may overwrite it
@@ -144,30 +151,28 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
     float* yo = y3d + pair * 2 * out3;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (x2d) {
+      if (H2) {
         // cameras.project_point_radial (src/cameras.py:39-51) in fp32
         const float dx = px - a.cam[c].Tr[0], dy = py - a.cam[c].Tr[1], dz = pz - a.cam[c].Tr[2];
         const float X0 = a.cam[c].R[0] * dx + a.cam[c].R[1] * dy + a.cam[c].R[2] * dz;
         const float X1 = a.cam[c].R[3] * dx + a.cam[c].R[4] * dy + a.cam[c].R[5] * dz;
         const float X2 = a.cam[c].R[6] * dx + a.cam[c].R[7] * dy + a.cam[c].R[8] * dz;
-        const float rz = __frcp_rn(X2);
+        const float rz = __fdividef(1.f, X2);          // MUFU.RCP (1 ulp): no slow-path branch
         const float x = X0 * rz, y = X1 * rz;
         const float r2 = x * x + y * y;
         const float radial = 1.f + r2 * (a.cam[c].k[0] + r2 * (a.cam[c].k[1] + r2 * a.cam[c].k[2]));
         const float s = radial + (a.cam[c].p[0] * y + a.cam[c].p[1] * x);
         const float u = a.cam[c].f[0] * (x * s + a.cam[c].p[1] * r2) + a.cam[c].c[0];
         const float v = a.cam[c].f[1] * (y * s + a.cam[c].p[0] * r2) + a.cam[c].c[1];
-        if (live) __stcs(xo, make_float2((u - m2x) * i2x, (v - m2y) * i2y));   // 256 contiguous bytes per warp
+        if (live) __stcs(xo, make_float2(u * i2x + n2x, v * i2y + n2y));   // 256 contiguous bytes per warp
         xo += x_cam_stride / 2;
       }
-      if (y3d) {
+      if (H3) {
         float* so = s_out[wib][buf];
-        if (has3) {
-          float* o = so + lp * out3 + 3 * j;
-          o[0] = ((a.cam[c].R[0] * qx + a.cam[c].R[1] * qy + a.cam[c].R[2] * qz) - m3[0]) * i3[0];
-          o[1] = ((a.cam[c].R[3] * qx + a.cam[c].R[4] * qy + a.cam[c].R[5] * qz) - m3[1]) * i3[1];
-          o[2] = ((a.cam[c].R[6] * qx + a.cam[c].R[7] * qy + a.cam[c].R[8] * qz) - m3[2]) * i3[2];
-        }
+        float* o = so + o_off;
+        o[0] = (a.cam[c].R[0] * qx + a.cam[c].R[1] * qy + a.cam[c].R[2] * qz) * i3[0] + n3[0];
+        o[1] = (a.cam[c].R[3] * qx + a.cam[c].R[4] * qy + a.cam[c].R[5] * qz) * i3[1] + n3[1];
+        o[2] = (a.cam[c].R[6] * qx + a.cam[c].R[7] * qy + a.cam[c].R[8] * qz) * i3[2] + n3[2];
         __syncwarp();
         if (y_vec && full) {
           if (lane < pair_f4) __stcs(reinterpret_cast<float4*>(yo) + lane, reinterpret_cast<const float4*>(so)[lane]);
@@ -181,6 +186,13 @@ __global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(con
     }
     c0 = n0; c1 = n1;
   }
+}
+
+template <int NC>
+static void launch_project_normalize(int grid, cudaStream_t st, const float* world, const FusedArgs& a, float* x2d, float* y3d, long long N) {
+  if (x2d && y3d) project_normalize_kernel<NC, true, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
+  else if (x2d) project_normalize_kernel<NC, true, false><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
+  else project_normalize_kernel<NC, false, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
 }
 
 // ------------------------------------------------------------------ normalise / un-normalise (f64, one array)
@@ -339,7 +351,7 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
   const int grid = nblocks < 148 * 3 ? (int)nblocks : 148 * 3;
   cudaStream_t st = (cudaStream_t)stream;
   switch (ncams) {
-#define P3D_PN_CASE(NC) case NC: project_normalize_kernel<NC><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N); break;
+#define P3D_PN_CASE(NC) case NC: launch_project_normalize<NC>(grid, st, world, a, x2d, y3d, N); break;
     P3D_PN_CASE(1) P3D_PN_CASE(2) P3D_PN_CASE(3) P3D_PN_CASE(4) P3D_PN_CASE(5) P3D_PN_CASE(6) P3D_PN_CASE(7) P3D_PN_CASE(8)
 #undef P3D_PN_CASE
   }

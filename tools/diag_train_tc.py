@@ -24,6 +24,11 @@ def run(cfg, B, keep=0.5):
         m.close()
     y, cache = M.forward(p, x.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True)
     grads = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cache, y)
+    from helpers import bf16_round
+    q = lambda a: bf16_round(a).astype(np.float64)  # noqa: E731
+    yq, cq = M.forward(p, x.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(masks), want_cache=True, quant=q)
+    gq = M.backward(p, x.astype(np.float64), t.astype(np.float64), cfg, cq, yq, quant=q)
+    print(f"   same-rounding oracle: loss {np.mean((yq - t) ** 2):.6f} |y_bf16 - yq|max {np.abs(res['bf16'][1] - yq).max():.2e}")
     print(f"== L={cfg.linear_size} nl={cfg.num_layers} res={cfg.residual} bn={cfg.batch_norm} clip={cfg.max_norm} B={B}: "
           f"loss oracle {np.mean((y - t) ** 2):.6f} fp32 {res['fp32'][0]:.6f} bf16 {res['bf16'][0]:.6f}; "
           f"|y-yref|max fp32 {np.abs(res['fp32'][1] - y).max():.2e} bf16 {np.abs(res['bf16'][1] - y).max():.2e} (|y|max {np.abs(y).max():.2f})")
@@ -35,6 +40,8 @@ def run(cfg, B, keep=0.5):
         for mode in ("fp32", "bf16"):
             d = res[mode][2][name].astype(np.float64) - g
             row += f"  {mode}: max {np.abs(d).max() / sc:.2e} relL2 {np.linalg.norm(d) / np.linalg.norm(g):.2e}"
+        d = res["bf16"][2][name].astype(np.float64) - gq[name]
+        row += f"  bf16 vs same-rounding: max {np.abs(d).max() / np.abs(gq[name]).max():.2e} relL2 {np.linalg.norm(d) / np.linalg.norm(gq[name]):.2e}"
         print(row)
 
 
