@@ -27,6 +27,7 @@ namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cud
                  int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency_cluster(p3d_model*, const float*, float*, cudaStream_t); }
+namespace layered { int forward(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t); }
 namespace train { void free_workspace(p3d_model*); }
 
 constexpr int kSmallBatchMax = 16;   // rows served by the latency (GEMV) path
@@ -258,7 +259,7 @@ void p3d_model_destroy(p3d_model* m) {
   train::free_workspace(m);
   cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
   cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
-  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter);
+  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act);
   for (int i = 0; i < 3; ++i) {
     if (m->pipe_streams[i]) cudaStreamDestroy(m->pipe_streams[i]);
     cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
@@ -326,25 +327,28 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
   if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
-  if (B <= kSmallBatchMax || (m->L % 256) != 0) {
-    if (B <= kSmallBatchMax) {
-      if (B == 1 && m->L == 1024) {                     // single pose: 16-CTA cluster kernel, one launch
-        const int rc = simt::forward_latency_cluster(m, x, y, st);
-        if (rc <= 0) return rc;                          // 1 = cluster of 16 not schedulable here -> per-layer kernels
-      }
-      static const bool coop = getenv("P3D_LAT_COOPGRID") != nullptr;   // experimental grid-barrier variant (slower: ~35 us)
-      if (coop && m->L == 1024) return simt::forward_latency(m, x, y, B, st);
-      return simt::forward_small(m, x, y, B, st);
-    }
-    return simt::forward_fp32(m, x, y, B, st);   // widths the tensor-core tiling does not cover
+  const int L = m->L;
+  if (B == 1 && L == 1024) {                            // single pose: 16-CTA cluster kernel, one launch
+    const int rc = simt::forward_latency_cluster(m, x, y, st);
+    if (rc <= 0) return rc;                              // 1 = cluster of 16 not schedulable here -> fall through
+  }
+  if ((L % 8) != 0) {                                    // widths no tensor-core tiling covers
+    if (B <= kSmallBatchMax) return simt::forward_small(m, x, y, B, st);
+    return simt::forward_fp32(m, x, y, B, st);
   }
   if (m->xb_cap < B) {
     if (m->xb) cudaFree(m->xb);
     m->xb = nullptr; m->xb_cap = 0;
-    P3D_CUDA(cudaMalloc(&m->xb, sizeof(__nv_bfloat16) * 64ull * B));
-    m->xb_cap = B;
+    const int64_t cap = B < 1024 ? 1024 : B;
+    P3D_CUDA(cudaMalloc(&m->xb, sizeof(__nv_bfloat16) * 64ull * cap));
+    m->xb_cap = cap;
   }
   P3D_TRY(prep::pack_input(x, m->xb, B, st));
+  // One tile of the fused persistent kernel takes ~100 us to walk all layers (a single SM pair streams every
+  // weight); below the crossover the per-layer GEMMs, which split each layer over N, are faster.
+  static const int64_t layered_max = [] { const char* e = getenv("P3D_LAYERED_MAX"); return e ? atoll(e) : 4096LL; }();
+  const bool fused_ok = (L % 256) == 0 && L <= 4096;
+  if (!fused_ok || B < layered_max) return layered::forward(m, m->xb, y, B, st);
   return tc::forward_bf16(m, m->xb, y, B, st);
 }
 

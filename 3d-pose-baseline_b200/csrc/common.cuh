@@ -135,7 +135,16 @@ struct GemmArgs {
   int split_k = 0;                    // split K over gridDim.z, fp32 atomics into C (C must hold the addend, e.g. zeros)
   int accumulate = 0;                 // C += (atomics) even when unsplit
   double* colsum = nullptr;           // optional [2][N] (+=): column sums of the result and of its square
+  // bf16 result instead of C (inference layers): out = bf16(relu?(.)), then out = bf16(out + res_bf16)
+  void* out_bf16 = nullptr; int ld_out_bf16 = 0;
+  const void* res_bf16 = nullptr; int ld_res_bf16 = 0;
+  int relu = 0;
 };
+// A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
+// and launched many times while the operand pointers/shapes stay the same.
+struct alignas(64) GemmPlan { unsigned char blob[512]; int valid = 0; };
+int plan(const GemmArgs& g, GemmPlan* out);
+int launch(const GemmPlan& pl, cudaStream_t st);
 int gemm(const GemmArgs& g, cudaStream_t st);
 }  // namespace tcg
 int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st);
@@ -170,6 +179,13 @@ struct p3d_model {
   int act_grid = 0;
   __nv_bfloat16* xb = nullptr;           // packed input [cap][64]
   int64_t xb_cap = 0;
+  // layered (one tcgen05 GEMM per layer) forward for small/medium batches: plans cached per batch size
+  std::vector<p3d::tcg::GemmPlan> lay_plans;
+  int64_t lay_B = -1;
+  const void* lay_y = nullptr;
+  const void* lay_x = nullptr;
+  __nv_bfloat16* lay_act = nullptr;      // [2][lay_cap][L] bf16
+  int64_t lay_cap = 0;
   unsigned long long* lat_counter = nullptr;   // grid-barrier counter of the latency kernel (monotonic)
   unsigned long long lat_base = 0;
   float* f32_a = nullptr;                // fp32-path activations [3][cap][L]

@@ -44,6 +44,10 @@ struct Params {
   float alpha;
   int atomic;               // accumulate into C with fp32 atomics (split-K)
   double* colsum;           // optional [2][N]: column sums of the stored values and of their squares
+  // bf16 output (inference layers): out = bf16(relu?(alpha*acc + bias)); with res_b: out = bf16(out + res_b)
+  __nv_bfloat16* out_b; int ldob;
+  const __nv_bfloat16* res_b; int ldrb;
+  int relu;
 };
 
 // K-major operand, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart
@@ -177,6 +181,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           atomicAdd(p.colsum + p.N + n0 + c0 + lane, static_cast<double>(a2[0]));
         }
       }
+      if (p.out_b) {
+        // bf16 activations of the layered inference path: same rounding points as the fused persistent kernel
+        // (relu(.) rounded to bf16, then the residual added and rounded again)
+        if (m < p.M) {
+          __nv_bfloat16* orow = p.out_b + static_cast<size_t>(m) * p.ldob + n0 + c0;
+          const __nv_bfloat16* rrow = p.res_b ? p.res_b + static_cast<size_t>(m) * p.ldrb + n0 + c0 : nullptr;
+          if (n0 + c0 + 32 <= p.N && (p.ldob & 7) == 0 && (!rrow || (p.ldrb & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float a0 = o[j + 2 * q], a1 = o[j + 2 * q + 1];
+                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                __nv_bfloat162 v = __floats2bfloat162_rn(a0, a1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&v);
+              }
+              if (rrow) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + j);
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[q]));
+                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[q]));
+                  __nv_bfloat162 v = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                  pk[q] = *reinterpret_cast<uint32_t*>(&v);
+                }
+              }
+              *reinterpret_cast<uint4*>(orow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + c0 + j < p.N) {
+                float a0 = p.relu ? fmaxf(o[j], 0.f) : o[j];
+                __nv_bfloat16 v = __float2bfloat16_rn(a0);
+                if (rrow) v = __float2bfloat16_rn(__bfloat162float(v) + __bfloat162float(rrow[j]));
+                orow[j] = v;
+              }
+            }
+          }
+        }
+        continue;
+      }
       if (m < p.M) {
         float* crow = p.C + static_cast<size_t>(m) * p.ldc + n0 + c0;
         const float* rrow = (p.res && first_split) ? p.res + static_cast<size_t>(m) * p.ldres + n0 + c0 : nullptr;
@@ -241,8 +289,11 @@ static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
 }
 
 // A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
-int gemm(const GemmArgs& g, cudaStream_t st) {
-  P3D_REQUIRE(g.M >= 1 && g.N >= 1 && g.K >= 1 && g.A && g.B && g.C, "tc_gemm: bad argument");
+struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; };
+static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
+
+int plan(const GemmArgs& g, GemmPlan* out) {
+  P3D_REQUIRE(g.M >= 1 && g.N >= 1 && g.K >= 1 && g.A && g.B && (g.C || g.out_bf16), "tc_gemm: bad argument");
   const int num_sms = 148;
   const int mt = (g.M + BM - 1) / BM;
   const int n64 = (g.N + 63) / 64 * 64;
@@ -261,25 +312,42 @@ int gemm(const GemmArgs& g, cudaStream_t st) {
   }
   const int kps = ((kblocks + splits - 1) / splits) * BK;
   splits = (g.K + kps - 1) / kps;
-  CUtensorMap ta, tb;
-  if (!g.a_mn) P3D_TRY(make_map(&ta, g.A, g.K, g.M, g.lda, BM));
-  else P3D_TRY(make_map(&ta, g.A, g.M, g.K, g.lda, BK));
-  if (!g.b_mn) P3D_TRY(make_map(&tb, g.B, g.K, g.N, g.ldb, bn));
-  else P3D_TRY(make_map(&tb, g.B, g.N, g.K, g.ldb, BK));
-  Params p;
+  PlanData* d = reinterpret_cast<PlanData*>(out->blob);
+  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, BM));
+  else P3D_TRY(make_map(&d->ta, g.A, g.M, g.K, g.lda, BK));
+  if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn));
+  else P3D_TRY(make_map(&d->tb, g.B, g.N, g.K, g.ldb, BK));
+  Params& p = d->p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.bn = bn; p.k_per_split = kps; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
   p.C = g.C; p.ldc = g.ldc; p.bias = g.bias; p.res = g.res; p.ldres = g.ldres; p.alpha_dev = g.alpha_dev; p.alpha = g.alpha;
   p.atomic = (splits > 1 || g.accumulate) ? 1 : 0;
   p.colsum = g.colsum;
+  p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
+  p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
+  P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
+  d->grid = dim3(nt, mt, splits);
+  out->valid = 1;
+  return P3D_OK;
+}
+
+int launch(const GemmPlan& pl, cudaStream_t st) {
+  P3D_REQUIRE(pl.valid, "tc_gemm: launch of an unplanned GEMM");
+  const PlanData* d = reinterpret_cast<const PlanData*>(pl.blob);
   static bool attr = false;
   if (!attr) {
     P3D_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
-  tc_gemm_kernel<<<dim3(nt, mt, splits), NTHREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  tc_gemm_kernel<<<d->grid, NTHREADS, SMEM_BYTES, st>>>(d->ta, d->tb, d->p);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+int gemm(const GemmArgs& g, cudaStream_t st) {
+  GemmPlan pl;
+  P3D_TRY(plan(g, &pl));
+  return launch(pl, st);
 }
 
 }  // namespace tcg
