@@ -139,6 +139,9 @@ struct GemmArgs {
   void* out_bf16 = nullptr; int ld_out_bf16 = 0;
   const void* res_bf16 = nullptr; int ld_res_bf16 = 0;
   int relu = 0;
+  // programmatic dependent launch: the kernel may start before its stream predecessor has finished; B (weights)
+  // must not depend on that predecessor - its first tiles are fetched ahead of the dependency wait
+  int pdl = 0;
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
 // and launched many times while the operand pointers/shapes stay the same.

@@ -28,6 +28,7 @@ static int build_plans(p3d_model* m, const __nv_bfloat16* xb, float* y, int64_t 
     else { g.A = (l & 1) ? P : Q; g.lda = L; }                       // odd layers read the block input P, even ones Q
     g.B = m->wt_bf16 + static_cast<size_t>(ly.row_off) * kpad; g.ldb = kpad;    // folded W'^T, K-major
     g.bias = m->bias_fold + ly.row_off;
+    g.pdl = 1;                                       // layer l+1 starts (and prefetches its weights) while layer l drains
     if (last) {
       g.C = y; g.ldc = m->out_size;
     } else {

@@ -25,12 +25,14 @@ using namespace ptx;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
 constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box = 8 KB
 constexpr int NTHREADS = 192;
-constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES_MAX) + 256;
+constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256;
+// the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
 
 struct Params {
   int M, N, K;
@@ -48,7 +50,11 @@ struct Params {
   __nv_bfloat16* out_b; int ldob;
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
+  int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
 };
+
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // K-major operand, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t desc_k(uint32_t smem_addr) {
@@ -68,11 +74,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = stages_for(p.bn);
+  const int B_BYTES = p.bn * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES_MAX);
-  uint64_t* empty = full + STAGES;
-  uint64_t* accf = empty + STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* accf = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,22 +100,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_launch_dependents();     // the next kernel of a programmatic-dependent chain may start its prologue now
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    const uint32_t bytes = A_BYTES + p.bn * BK * 2;
+    // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
+    // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
+    const uint32_t bytes = A_BYTES + B_BYTES;
+    auto load_a = [&](int stage, int k0) {
+      uint8_t* a = sA + stage * A_BYTES;
+      if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
+      else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
+    };
+    auto load_b = [&](int stage, int k0) {
+      uint8_t* b = sB + stage * B_BYTES;
+      if (!p.b_mn) tma_load_2d(b, &tm_b, &full[stage], k0, n0);
+      else for (int i = 0; i < p.bn / 64; ++i) tma_load_2d(b + i * BOX_BYTES, &tm_b, &full[stage], n0 + 64 * i, k0);
+    };
+    const int npre = p.b_independent ? (nk < STAGES ? nk : STAGES) : 0;
+    if (elect_one()) {
+      for (int kb = 0; kb < npre; ++kb) {            // ring slots are free on the first pass
+        mbar_arrive_expect_tx(&full[kb], bytes);
+        load_b(kb, kbeg + kb * BK);
+      }
+    }
+    __syncwarp();
+    grid_dependency_wait();
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < nk; ++kb) {
       const int k0 = kbeg + kb * BK;
       mbar_wait(&empty[stage], phase ^ 1, 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        uint8_t* a = sA + stage * A_BYTES;
-        uint8_t* b = sB + stage * B_BYTES_MAX;
-        if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
-        else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
-        if (!p.b_mn) tma_load_2d(b, &tm_b, &full[stage], k0, n0);
-        else for (int i = 0; i < p.bn / 64; ++i) tma_load_2d(b + i * BOX_BYTES, &tm_b, &full[stage], n0 + 64 * i, k0);
+        if (kb >= npre) { mbar_arrive_expect_tx(&full[stage], bytes); load_b(stage, k0); }
+        load_a(stage, k0);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -122,7 +147,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(&full[stage], phase, 2);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t aa = a_base + stage * A_BYTES, bb = b_base + stage * B_BYTES_MAX;
+        const uint32_t aa = a_base + stage * A_BYTES, bb = b_base + stage * B_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
@@ -140,6 +165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int ew = warp & 3;
     const int m = m0 + ew * 32 + lane;
     const bool first_split = (blockIdx.z == 0);
+    grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
     mbar_wait(accf, 0, 3);
     tc_fence_after();
@@ -289,7 +315,7 @@ static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
 }
 
 // A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
-struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; };
+struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; int pdl; };
 static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
 
 int plan(const GemmArgs& g, GemmPlan* out) {
@@ -324,6 +350,8 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.colsum = g.colsum;
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
+  p.b_independent = g.pdl ? 1 : 0;
+  d->pdl = g.pdl;
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
   d->grid = dim3(nt, mt, splits);
@@ -339,7 +367,17 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
     P3D_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
-  tc_gemm_kernel<<<d->grid, NTHREADS, SMEM_BYTES, st>>>(d->ta, d->tb, d->p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  if (d->pdl) {
+    // programmatic dependent launch: this kernel may start while its predecessor in the stream drains; it orders
+    // itself behind the predecessor's memory with griddepcontrol.wait
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs; cfg.numAttrs = 1;
+  }
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, d->ta, d->tb, d->p));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
