@@ -16,6 +16,7 @@ namespace p3d {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+long long launch_count_now();
 
 #define P3D_CUDA(expr)                                                                          \
   do {                                                                                          \
@@ -97,6 +98,13 @@ struct TrainWorkspace {
   __nv_bfloat16* dzb = nullptr;   // [B][L]
   __nv_bfloat16* dyb = nullptr;   // [B][48] (pad columns zero)
   __nv_bfloat16* wb = nullptr;    // weights [K][N] per layer at theta's offsets; W4 rows padded to 48
+  void* tab = nullptr;            // device LayerTabEntry[nlayers]
+  void* sc = nullptr;             // device StepScalars (per-step values: Adam step size, lr, dropout seed/step)
+  // CUDA-graph replay of the step: fixed-address staging of x / t / y / (loss, lr) and one graph per (B, dropout)
+  float* gx = nullptr; float* gt = nullptr; float* gy = nullptr; float* gscal = nullptr;
+  struct GraphEntry { int64_t B; int dropout; int launches; void* exec; };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
 };
 
 // Optional per-launch CUDA-event timing of the dominant kernel (bench.py's roofline figure):
