@@ -15,6 +15,8 @@
 // (L/128)*(L/BN) tiles but K = batch).  Warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> alpha/bias/residual -> global).  Out-of-range rows/cols
 // and the K tail are zero-filled by TMA, so M, N, K need no padding (K=32 input layer, N=48 output).
+#include <cstring>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -161,113 +163,132 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: warp w reads TMEM lanes 32*(w%4)..+31
+    // ------------------------------------------------------------ epilogue: warp w owns TMEM lanes 32*(w%4)..+31
+    // tcgen05.ld hands every lane one ROW (32 consecutive columns).  Storing that directly makes each instruction
+    // touch 32 different lines, 16 bytes each.  Instead the 32 x 32 chunk is transposed through a padded smem tile
+    // (the operand ring is free once the accumulator is complete) so that a lane owns 4 COLUMNS x 8 rows: every
+    // global access (C, residual, bf16 output, fp32 reductions) is then 4 full 128-byte lines per instruction, bias
+    // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
     const int ew = warp & 3;
-    const int m = m0 + ew * 32 + lane;
     const bool first_split = (blockIdx.z == 0);
     grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
     mbar_wait(accf, 0, 3);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && !p.atomic &&
-                        (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
+    constexpr int TP = 36;                                   // tile pitch in floats (144 B): conflict-free both ways
+    float* tile = reinterpret_cast<float*>(smem) + ew * 32 * TP;
+    const int rg = lane >> 3, cq = (lane & 7) * 4;           // row group (rows rg, rg+4, ...), first of this lane's 4 columns
+    const bool c_vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec = p.res && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+    const bool ob_vec = p.out_b && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_b) & 7) == 0);
+    const bool rb_vec = p.res_b && ((p.ldrb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res_b) & 7) == 0);
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       if (n0 + c0 >= p.N) break;     // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32b_x32(taddr + c0, v);
       tmem_ld_wait();
-      float o[32];
+      __syncwarp();                  // the previous chunk's readers are done with the tile
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        float val = alpha * __uint_as_float(v[j]);
-        if (first_split && p.bias && n < p.N) val += __ldg(p.bias + n);
-        o[j] = val;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(tile + lane * TP + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      const int n = n0 + c0 + cq;                            // this lane's columns n .. n+3
+      const bool full4 = n + 3 < p.N;
+      float bias[4] = {0.f, 0.f, 0.f, 0.f};
+      if (first_split && p.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < p.N) bias[j] = __ldg(p.bias + n + j);
       }
-      if (p.colsum) {
-        // column sums over this warp's 32 rows (rows >= M count as zero) by a transposing butterfly: 31 shuffles
-        // leave lane l with the sum of column c0 + l; then one fp64 atomic per column per warp
-        float a1[32], a2[32];
+      float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
+      // residual rows first: 8 independent loads in flight instead of one dependent load per row
+      float4 rres[8];
+      uint2 rresb[8];
+      const bool use_res = p.res && first_split && !p.out_b, use_resb = p.out_b && p.res_b;
+      if (use_res || use_resb) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { a1[j] = (m < p.M) ? o[j] : 0.f; a2[j] = a1[j] * a1[j]; }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int j = 0; j < off; ++j) {
-            const float s1 = upper ? a1[j] : a1[j + off], k1 = upper ? a1[j + off] : a1[j];
-            const float s2 = upper ? a2[j] : a2[j + off], k2 = upper ? a2[j + off] : a2[j];
-            a1[j] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
-            a2[j] = k2 + __shfl_xor_sync(0xffffffffu, s2, off);
-          }
-        }
-        if (n0 + c0 + lane < p.N) {
-          atomicAdd(p.colsum + n0 + c0 + lane, static_cast<double>(a1[0]));
-          atomicAdd(p.colsum + p.N + n0 + c0 + lane, static_cast<double>(a2[0]));
-        }
-      }
-      if (p.out_b) {
-        // bf16 activations of the layered inference path: same rounding points as the fused persistent kernel
-        // (relu(.) rounded to bf16, then the residual added and rounded again)
-        if (m < p.M) {
-          __nv_bfloat16* orow = p.out_b + static_cast<size_t>(m) * p.ldob + n0 + c0;
-          const __nv_bfloat16* rrow = p.res_b ? p.res_b + static_cast<size_t>(m) * p.ldrb + n0 + c0 : nullptr;
-          if (n0 + c0 + 32 <= p.N && (p.ldob & 7) == 0 && (!rrow || (p.ldrb & 7) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float a0 = o[j + 2 * q], a1 = o[j + 2 * q + 1];
-                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                __nv_bfloat162 v = __floats2bfloat162_rn(a0, a1);
-                pk[q] = *reinterpret_cast<uint32_t*>(&v);
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + ew * 32 + i * 4 + rg;
+          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f); rresb[i] = make_uint2(0u, 0u);
+          if (m < p.M) {
+            if (use_res) {
+              const float* rr = p.res + static_cast<size_t>(m) * p.ldres + n;
+              if (r_vec && full4) rres[i] = __ldg(reinterpret_cast<const float4*>(rr));
+              else {
+                if (n < p.N) rres[i].x = __ldg(rr);
+                if (n + 1 < p.N) rres[i].y = __ldg(rr + 1);
+                if (n + 2 < p.N) rres[i].z = __ldg(rr + 2);
+                if (n + 3 < p.N) rres[i].w = __ldg(rr + 3);
               }
-              if (rrow) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rrow + j);
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+            } else {
+              const __nv_bfloat16* rr = p.res_b + static_cast<size_t>(m) * p.ldrb + n;
+              if (rb_vec && full4) rresb[i] = *reinterpret_cast<const uint2*>(rr);
+              else {
+                __nv_bfloat16 tmp[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[q]));
-                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[q]));
-                  __nv_bfloat162 v = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
-                  pk[q] = *reinterpret_cast<uint32_t*>(&v);
-                }
-              }
-              *reinterpret_cast<uint4*>(orow + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + c0 + j < p.N) {
-                float a0 = p.relu ? fmaxf(o[j], 0.f) : o[j];
-                __nv_bfloat16 v = __float2bfloat16_rn(a0);
-                if (rrow) v = __float2bfloat16_rn(__bfloat162float(v) + __bfloat162float(rrow[j]));
-                orow[j] = v;
+                for (int j = 0; j < 4; ++j) tmp[j] = (n + j < p.N) ? rr[j] : __float2bfloat16_rn(0.f);
+                memcpy(&rresb[i], tmp, 8);
               }
             }
           }
         }
-        continue;
       }
-      if (m < p.M) {
-        float* crow = p.C + static_cast<size_t>(m) * p.ldc + n0 + c0;
-        const float* rrow = (p.res && first_split) ? p.res + static_cast<size_t>(m) * p.ldres + n0 + c0 : nullptr;
-        if (vec_ok && n0 + c0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            if (rrow) { const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j)); q.x += r.x; q.y += r.y; q.z += r.z; q.w += r.w; }
-            *reinterpret_cast<float4*>(crow + j) = q;
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rg;
+        const int m = m0 + ew * 32 + r;
+        const float4 t4 = *reinterpret_cast<const float4*>(tile + r * TP + cq);
+        float o[4] = {alpha * t4.x + bias[0], alpha * t4.y + bias[1], alpha * t4.z + bias[2], alpha * t4.w + bias[3]};
+        if (m >= p.M) continue;
+        if (p.colsum) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { cs1[j] += o[j]; cs2[j] += o[j] * o[j]; }
+        }
+        if (p.out_b) {
+          // bf16 activations of the layered inference path: same rounding points as the fused persistent kernel
+          // (relu(.) rounded to bf16, then the residual added and rounded again)
+          __nv_bfloat16 ob[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(p.relu ? fmaxf(o[j], 0.f) : o[j]);
+          if (use_resb) {
+            __nv_bfloat16 rv[4];
+            memcpy(rv, &rresb[i], 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(__bfloat162float(ob[j]) + __bfloat162float(rv[j]));
           }
+          __nv_bfloat16* orow = p.out_b + static_cast<size_t>(m) * p.ldob + n;
+          if (ob_vec && full4) { uint2 q; memcpy(&q, ob, 8); *reinterpret_cast<uint2*>(orow) = q; }
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (n + j < p.N) orow[j] = ob[j];
+          }
+          continue;
+        }
+        if (use_res) { o[0] += rres[i].x; o[1] += rres[i].y; o[2] += rres[i].z; o[3] += rres[i].w; }
+        float* crow = p.C + static_cast<size_t>(m) * p.ldc + n;
+        if (c_vec && full4) {
+          if (p.atomic) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+          else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n0 + c0 + j < p.N) {
-              float val = o[j];
-              if (rrow) val += __ldg(rrow + j);
-              if (p.atomic) atomicAdd(crow + j, val); else crow[j] = val;
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < p.N) { if (p.atomic) atomicAdd(crow + j, o[j]); else crow[j] = o[j]; }
+          }
+        }
+      }
+      if (p.colsum) {
+        // this lane holds 8 of the warp's 32 rows for its 4 columns: fold the 4 row groups, then lanes 0..7 publish
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 8);  cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 8);
+          cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16); cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
+        }
+        if (rg == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j < p.N) {
+              atomicAdd(p.colsum + n + j, static_cast<double>(cs1[j]));
+              atomicAdd(p.colsum + p.N + n + j, static_cast<double>(cs2[j]));
             }
           }
         }
