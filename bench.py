@@ -163,6 +163,79 @@ def pinned_array(lib, shape, dtype=np.float32):
     return arr, ptr
 
 
+def secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr):
+    """The other BASELINE.json configs, measured in the same run (N = 1, rank 0; a few seconds in total):
+    inference batch sweep, training step (batch 64 / 4096, both modes), camera-frame preprocessing and
+    Procrustes/MPJPE evaluation against the HBM roofline.  CUDA events around back-to-back calls."""
+    from oracle import synth
+    from p3d import LinearModel, data_utils
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters          # ms
+
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(7)
+    sweep = []
+    for lg in (0, 3, 6, 8, 10, 12, 14, 16, 18):
+        Bs = 1 << lg
+        xs = torch.randn((Bs, IN), device=dev, generator=g); ys = torch.empty((Bs, OUT), device=dev)
+        ms = timed(lambda: lib.p3d_model_forward(model._handle, xs.data_ptr(), ys.data_ptr(), Bs, sptr), 100 if lg <= 12 else 10)
+        tf = Bs * FLOP_PER_POSE / (ms * 1e-3) / 1e12
+        sweep.append({"batch": Bs, "us_per_call": round(ms * 1e3, 2), "poses_per_s": round(Bs / (ms * 1e-3)),
+                      "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 4)})
+    out["inference_batch_sweep"] = sweep
+
+    train = []
+    for Bt, mode in ((64, "bf16"), (4096, "bf16"), (64, "fp32"), (4096, "fp32")):
+        mt = LinearModel(L, NL, True, True, True, Bt, 1e-3, seed=1, mode=mode)
+        xt = torch.randn((Bt, IN), device=dev, generator=g); tt = torch.randn((Bt, OUT), device=dev, generator=g)
+        ms = timed(lambda: mt.step(None, xt, tt, 0.5, isTraining=True), 20 if mode == "bf16" else 5)
+        train.append({"batch": Bt, "mode": mode, "gemms": "tcgen05 bf16, fp32 master weights" if mode == "bf16" else "fp32 FFMA",
+                      "us_per_step": round(ms * 1e3, 1), "poses_per_s": round(Bt / (ms * 1e-3)),
+                      "tflops": round(Bt * 25_591_808 / (ms * 1e-3) / 1e12, 2)})
+        mt.close()
+    out["training_step"] = {"config": "dropout keep 0.5, max_norm, Adam, BN batch statistics", "runs": train}
+
+    N = 1 << 20
+    cams = synth.cameras(4, seed=3)
+    root = torch.randn((N, 1, 3), device=dev, generator=g) * 500
+    world_p = (root + torch.randn((N, 32, 3), device=dev, generator=g) * 300).reshape(N, 96).contiguous()
+    m2, s2 = np.full(64, 500.0), np.full(64, 150.0)
+    m3, s3 = np.zeros(96), np.full(96, 200.0)
+    ms = timed(lambda: data_utils.camera_frame_dataset(world_p, cams, m2, s2, m3, s3), 10)
+    bts = N * (384 + 512 + 768)
+    out["preprocess"] = {"workload": "project_point_radial + world_to_camera + root-centre + normalise, 2^20 poses x 4 cameras",
+                         "ms": round(ms, 4), "poses_per_s": round(N / (ms * 1e-3)),
+                         "roofline": {"bound": "hbm", "achieved": round(bts / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": round(bts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4), "algorithmic_bytes": bts}}
+    NE = 4 * N
+    gt = torch.randn((NE, 48), device=dev, generator=g)
+    pr = gt + 0.2 * torch.randn((NE, 48), device=dev, generator=g)
+    sums = torch.zeros(18, dtype=torch.float64, device=dev)
+    m3h, s3h = np.ascontiguousarray(m3), np.ascontiguousarray(s3)
+    ev = {}
+    for use_proc in (1, 0):
+        ms = timed(lambda: _lib.check(lib.p3d_procrustes_mpjpe(pr.data_ptr(), gt.data_ptr(), _lib.np_ptr(m3h), _lib.np_ptr(s3h), 0, use_proc,
+                                                               NE, None, sums.data_ptr(), sptr)), 10)
+        bts = NE * 384
+        ev["procrustes_mpjpe" if use_proc else "plain_mpjpe"] = {
+            "ms": round(ms, 4), "poses_per_s": round(NE / (ms * 1e-3)),
+            "roofline": {"bound": "hbm", "achieved": round(bts / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(bts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4), "algorithmic_bytes": bts}}
+    ev["workload"] = "un-normalise + (Procrustes) + MPJPE, 4 x 2^20 poses, fp32 kernel"
+    out["evaluation"] = ev
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -292,6 +365,10 @@ def run_ours(args):
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{sample} of 2^20 poses, fp32 NumPy restatement of the TF graph, {secs:.1f} s"}
 
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr)
+
     if rank == 0:
         k_ms = kms.value / max(1, kn.value)
         achieved = B * FLOP_PER_POSE / (k_ms * 1e-3) / 1e12
@@ -322,6 +399,8 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     lib.p3d_host_free(yh_ptr)
     lib.p3d_host_free(xh_ptr)
@@ -339,6 +418,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the batch sweep / training / preprocessing / evaluation lines")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout: libraries (NCCL's version banner, torchrun notices) also write to
     # fd 1, so fd 1 is pointed at stderr for the duration of the run and the line goes to the saved descriptor.
