@@ -718,13 +718,50 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   return P3D_OK;
 }
 
-// model.step(isTraining=True): per-step scalars -> device, then the body - directly, or (single GPU, generated
-// dropout masks) as a CUDA graph captured on a private stream and replayed on the caller's stream.
-int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float keep, uint64_t seed, const uint8_t* mask_in,
-               int64_t Bg, int64_t row0, float* loss, float* lr_used, float* y, cudaStream_t st) {
-  P3D_TRY(ensure_workspace(m, B));
+// One step on inputs that already sit in the staging buffers (w.gx, w.gt): per-step scalars -> device, then the
+// body as a CUDA graph captured on a private stream and replayed on the caller's stream (first call of a shape runs
+// directly, second captures).  Results land in w.gy / w.gscal.  Single GPU, generated dropout masks.
+static int train_step_staged(p3d_model* m, int64_t B, float keep, uint64_t seed, cudaStream_t st) {
   TrainWorkspace& w = m->tw;
-  const bool dropout = keep < 1.f || mask_in != nullptr;
+  const bool dropout = keep < 1.f;
+  TrainWorkspace::GraphEntry* ge = nullptr;
+  for (auto& g : w.graphs) if (g.B == B && g.dropout == (dropout ? 1 : 0)) ge = &g;
+  if (!ge) { w.graphs.push_back(TrainWorkspace::GraphEntry{B, dropout ? 1 : 0, 0, nullptr}); ge = &w.graphs.back(); }
+  if (ge->exec) {
+    P3D_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(ge->exec), st));
+    count_launch(ge->launches > 0 ? ge->launches : 0);
+    return P3D_OK;
+  }
+  if (ge->launches == 0) {
+    // first step of this shape: run directly (also performs every one-time cudaFuncSetAttribute)
+    const long long before = launch_count_now();
+    const int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, B, 0, w.gscal, w.gscal + 1, w.gy, st);
+    ge->launches = static_cast<int>(launch_count_now() - before);
+    if (ge->launches == 0) ge->launches = -1;
+    return rc;
+  }
+  if (!w.cap_stream) P3D_CUDA(cudaStreamCreateWithFlags(&w.cap_stream, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  P3D_CUDA(cudaStreamBeginCapture(w.cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, B, 0, w.gscal, w.gscal + 1, w.gy, w.cap_stream);
+  const cudaError_t ce = cudaStreamEndCapture(w.cap_stream, &graph);
+  count_launch(-(ge->launches > 0 ? ge->launches : 0));       // the captured launches did not run
+  if (rc != P3D_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == P3D_OK) { set_error("stream capture of the training step failed: %s", cudaGetErrorString(ce)); rc = P3D_ERR_CUDA; }
+    return rc;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return P3D_ERR_CUDA; }
+  ge->exec = exec;
+  P3D_CUDA(cudaGraphLaunch(exec, st));
+  count_launch(ge->launches > 0 ? ge->launches : 0);
+  return P3D_OK;
+}
+
+static int push_scalars(p3d_model* m, float keep, uint64_t seed, cudaStream_t st) {
   // learning-rate schedule (src/linear_model.py:86-90) and TF's bias-corrected step size
   const double tstep = static_cast<double>(m->global_step);
   StepScalars h;
@@ -733,57 +770,75 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   h.alpha = static_cast<float>(static_cast<double>(h.lr_t) * std::sqrt(1.0 - std::pow(0.999, tt)) / (1.0 - std::pow(0.9, tt)));
   h.keep = keep; h.inv_keep = 1.f / keep;
   h.step = static_cast<unsigned>(m->global_step); h.pad = 0; h.seed = seed;
-  set_scalars_kernel<<<1, 1, 0, st>>>(static_cast<StepScalars*>(w.sc), h);
+  set_scalars_kernel<<<1, 1, 0, st>>>(static_cast<StepScalars*>(m->tw.sc), h);
   P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
 
-  static const bool graphs_on = [] { const char* e = getenv("P3D_TRAIN_GRAPH"); return !(e && e[0] == '0'); }();
-  int rc;
-  if (graphs_on && m->world == 1 && mask_in == nullptr) {
-    TrainWorkspace::GraphEntry* ge = nullptr;
-    for (auto& g : w.graphs) if (g.B == B && g.dropout == (dropout ? 1 : 0)) ge = &g;
-    if (!ge) { w.graphs.push_back(TrainWorkspace::GraphEntry{B, dropout ? 1 : 0, 0, nullptr}); ge = &w.graphs.back(); }
+static bool graphs_enabled() {
+  static const bool on = [] { const char* e = getenv("P3D_TRAIN_GRAPH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// model.step(isTraining=True)
+int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float keep, uint64_t seed, const uint8_t* mask_in,
+               int64_t Bg, int64_t row0, float* loss, float* lr_used, float* y, cudaStream_t st) {
+  P3D_TRY(ensure_workspace(m, B));
+  TrainWorkspace& w = m->tw;
+  P3D_TRY(push_scalars(m, keep, seed, st));
+  if (graphs_enabled() && m->world == 1 && mask_in == nullptr) {
     const size_t out = static_cast<size_t>(m->out_size);
     P3D_CUDA(cudaMemcpyAsync(w.gx, x, sizeof(float) * B * kIn, cudaMemcpyDeviceToDevice, st));
     P3D_CUDA(cudaMemcpyAsync(w.gt, t, sizeof(float) * B * out, cudaMemcpyDeviceToDevice, st));
-    if (ge->exec) {
-      P3D_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(ge->exec), st));
-      count_launch(ge->launches);
-      rc = P3D_OK;
-    } else if (ge->launches == 0) {
-      // first step of this shape: run directly (also performs every one-time cudaFuncSetAttribute)
-      const long long before = launch_count_now();
-      rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, Bg, row0, w.gscal, w.gscal + 1, w.gy, st);
-      ge->launches = static_cast<int>(launch_count_now() - before);
-      if (ge->launches == 0) ge->launches = -1;
-    } else {
-      if (!w.cap_stream) P3D_CUDA(cudaStreamCreateWithFlags(&w.cap_stream, cudaStreamNonBlocking));
-      cudaGraph_t graph = nullptr;
-      P3D_CUDA(cudaStreamBeginCapture(w.cap_stream, cudaStreamCaptureModeThreadLocal));
-      rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, Bg, row0, w.gscal, w.gscal + 1, w.gy, w.cap_stream);
-      cudaError_t ce = cudaStreamEndCapture(w.cap_stream, &graph);
-      count_launch(-(ge->launches > 0 ? ge->launches : 0));       // the captured launches did not run
-      if (rc == P3D_OK && ce == cudaSuccess && graph) {
-        cudaGraphExec_t exec = nullptr;
-        ce = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return P3D_ERR_CUDA; }
-        ge->exec = exec;
-        P3D_CUDA(cudaGraphLaunch(exec, st));
-        count_launch(ge->launches > 0 ? ge->launches : 0);
-      } else {
-        if (graph) cudaGraphDestroy(graph);
-        if (rc == P3D_OK) { set_error("stream capture of the training step failed: %s", cudaGetErrorString(ce)); rc = P3D_ERR_CUDA; }
-      }
-    }
-    if (rc != P3D_OK) return rc;
+    P3D_TRY(train_step_staged(m, B, keep, seed, st));
     P3D_CUDA(cudaMemcpyAsync(y, w.gy, sizeof(float) * B * out, cudaMemcpyDeviceToDevice, st));
     if (loss) P3D_CUDA(cudaMemcpyAsync(loss, w.gscal, sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (lr_used) P3D_CUDA(cudaMemcpyAsync(lr_used, w.gscal + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
-    rc = train_body(m, x, t, B, dropout, mask_in, Bg, row0, loss, lr_used, y, st);
-    if (rc != P3D_OK) return rc;
+    const bool dropout = keep < 1.f || mask_in != nullptr;
+    P3D_TRY(train_body(m, x, t, B, dropout, mask_in, Bg, row0, loss, lr_used, y, st));
   }
   m->global_step += 1;
+  m->pack_valid = false;
+  return P3D_OK;
+}
+
+// rows perm[start + i] (or start + i) of X / T -> the staging buffers; publishes the previous step's loss
+__global__ void gather_batch_kernel(const float* __restrict__ X, const float* __restrict__ T, const long long* __restrict__ perm,
+                                    long long start, int B, int out, float* __restrict__ gx, float* __restrict__ gt) {
+  const int per_row = kIn + out;
+  const long long total = static_cast<long long>(B) * per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / per_row), c = static_cast<int>(i - static_cast<long long>(r) * per_row);
+    const long long src = perm ? perm[start + r] : start + r;
+    if (c < kIn) gx[r * kIn + c] = X[src * kIn + c];
+    else gt[r * out + (c - kIn)] = T[src * out + (c - kIn)];
+  }
+}
+__global__ void store_loss_kernel(const float* gscal, float* losses, long long idx, float* lr_last) {
+  losses[idx] = gscal[0];
+  if (lr_last) *lr_last = gscal[1];
+}
+
+// The batch loop of predict_3dpose.train() (src/predict_3dpose.py:231-259) over a device-resident training set.
+int train_epoch(p3d_model* m, const float* X, const float* T, int64_t n, const long long* perm, int64_t B, float keep, uint64_t seed,
+                float* losses, float* lr_last, cudaStream_t st) {
+  P3D_REQUIRE(m->world == 1, "train_epoch: data-parallel models step through p3d_model_train_step");
+  P3D_TRY(ensure_workspace(m, B));
+  TrainWorkspace& w = m->tw;
+  const int64_t nb = n / B;                                   // the n % B tail is dropped (linear_model.py:311-313)
+  int g = static_cast<int>((B * (kIn + m->out_size) + 255) / 256);
+  if (g > 148 * 4) g = 148 * 4;
+  for (int64_t b = 0; b < nb; ++b) {
+    P3D_TRY(push_scalars(m, keep, seed, st));
+    gather_batch_kernel<<<g, 256, 0, st>>>(X, T, perm, b * B, static_cast<int>(B), m->out_size, w.gx, w.gt);
+    P3D_LAUNCH_CHECK();
+    if (graphs_enabled()) P3D_TRY(train_step_staged(m, B, keep, seed, st));
+    else P3D_TRY(train_body(m, w.gx, w.gt, B, keep < 1.f, nullptr, B, 0, w.gscal, w.gscal + 1, w.gy, st));
+    store_loss_kernel<<<1, 1, 0, st>>>(w.gscal, losses, b, lr_last);
+    P3D_LAUNCH_CHECK();
+    m->global_step += 1;
+  }
   m->pack_valid = false;
   return P3D_OK;
 }
@@ -805,6 +860,16 @@ int p3d_model_train_step(p3d_model* m, const float* x, const float* t, int64_t B
   P3D_REQUIRE(m->world > 1 || global_B == B, "train_step: global_B != B without a communicator");
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   return train::train_step(m, x, t, B, keep_prob, seed, mask_or_null, global_B, row0, loss, lr_used, y, static_cast<cudaStream_t>(stream));
+}
+
+int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t n, const int64_t* perm_or_null, int64_t batch_size,
+                          float keep_prob, uint64_t seed, float* losses, float* lr_last_or_null, void* stream) {
+  P3D_REQUIRE(m && X && T && losses, "train_epoch: null argument");
+  P3D_REQUIRE(batch_size >= 1 && n >= 0, "train_epoch: bad sizes");
+  P3D_REQUIRE(keep_prob > 0.f && keep_prob <= 1.f, "train_epoch: dropout_keep_prob must be in (0,1]");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  return train::train_epoch(m, X, T, n, reinterpret_cast<const long long*>(perm_or_null), batch_size, keep_prob, seed, losses,
+                            lr_last_or_null, static_cast<cudaStream_t>(stream));
 }
 
 int p3d_nccl_unique_id(uint8_t* id_host) {

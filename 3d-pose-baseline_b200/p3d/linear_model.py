@@ -290,6 +290,41 @@ class LinearModel(object):
             return (np.float32(s[0]), Summary("loss/loss", np.float32(s[0])),
                     Summary("learning_rate/learning_rate", np.float32(s[1])), y.cpu().numpy())
 
+    def train_epoch(self, encoder_inputs, decoder_outputs, dropout_keep_prob, shuffle=True, perm=None):
+        """The batch loop of the reference's train() (src/predict_3dpose.py:231-259) without the host in it:
+        `encoder_inputs` [n,32] / `decoder_outputs` [n,out] are the concatenated training set (what
+        get_all_batches builds, linear_model.py:266-300; NumPy or torch CUDA), permuted (np.random.permutation
+        as in :309 unless `perm` is given or shuffle=False), cut into n // batch_size batches (the tail is
+        dropped, :311-313) and stepped on the device, one replayed CUDA graph per batch.
+        Returns (losses[n_batches], last learning rate) - NumPy for NumPy inputs, torch otherwise."""
+        torch = _lib.require_cuda()
+        if self.world > 1:
+            raise RuntimeError("train_epoch is single-GPU; data-parallel training steps through step()")
+        is_torch = hasattr(encoder_inputs, "is_cuda")
+        dev = torch.device("cuda", self.device)
+        with torch.cuda.device(self.device):
+            X = (encoder_inputs if is_torch else torch.from_numpy(np.ascontiguousarray(encoder_inputs, dtype=np.float32))).to(dev, torch.float32).contiguous()
+            T = (decoder_outputs if is_torch else torch.from_numpy(np.ascontiguousarray(decoder_outputs, dtype=np.float32))).to(dev, torch.float32).contiguous()
+            n = int(X.shape[0])
+            if X.dim() != 2 or X.shape[1] != self.input_size or T.shape != (n, self.output_size):
+                raise ValueError("expected [n,%d] inputs and [n,%d] outputs" % (self.input_size, self.output_size))
+            nb = n // self.batch_size
+            pd = None
+            if perm is not None:
+                pd = torch.as_tensor(np.asarray(perm, dtype=np.int64)).to(dev)
+            elif shuffle:
+                pd = torch.from_numpy(np.random.permutation(n).astype(np.int64)).to(dev)
+            losses = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)
+            lr = torch.zeros(1, dtype=torch.float32, device=dev)
+            if nb:
+                check(lib.p3d_model_train_epoch(self._handle, X.data_ptr(), T.data_ptr(), n, pd.data_ptr() if pd is not None else None,
+                                                self.batch_size, float(dropout_keep_prob), C.c_uint64(self._seed & 0xFFFFFFFFFFFFFFFF),
+                                                losses.data_ptr(), lr.data_ptr(), _lib.current_stream()))
+            losses = losses[:nb]
+        if is_torch:
+            return losses, lr[0]
+        return losses.cpu().numpy(), float(lr.item())
+
     # ------------------------------------------------------------------ batching (host side, linear_model.py:247-300)
     def get_all_batches(self, data_x, data_y, camera_frame, training=True):
         """Obtain a list of all the batches, randomly permuted when training (linear_model.py:247-300)."""

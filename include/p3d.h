@@ -101,6 +101,15 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
 int p3d_model_train_step(p3d_model* m, const float* x, const float* t, int64_t B, float keep_prob,
                          uint64_t seed, const uint8_t* mask_or_null, int64_t global_B, int64_t row0,
                          float* loss, float* lr_used, float* y, void* stream);
+
+/* The batch loop of predict_3dpose.train() (src/predict_3dpose.py:231-259) over a DEVICE-resident training set:
+ * X[n,32] / T[n,out] are what LinearModel.get_all_batches concatenates (src/linear_model.py:266-300),
+ * perm_or_null[n] its np.random.permutation (int64, device; NULL = natural order), the n % batch_size tail is
+ * dropped (:311-313).  Every batch is gathered on the device and stepped as a replayed CUDA graph - no host
+ * synchronisation inside.  losses[n / batch_size] (device) receives each step's loss, lr_last_or_null the last
+ * learning rate.  Single GPU (data-parallel models call p3d_model_train_step per batch). */
+int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t n, const int64_t* perm_or_null, int64_t batch_size,
+                          float keep_prob, uint64_t seed, float* losses, float* lr_last_or_null, void* stream);
 /* Data parallel: a NCCL communicator owned by the library (SyncBN statistics + one gradient
  * all-reduce per step).  id_host = 128-byte ncclUniqueId made by rank 0 and broadcast by the caller. */
 int p3d_nccl_unique_id(uint8_t* id_host /*[128]*/);

@@ -248,3 +248,32 @@ def test_checkpoint_roundtrip(tmp_path):
     with pytest.raises(ValueError):
         m2.restore(str(tmp_path / "checkpoint-2.npz"))
     m.close(); m2.close()
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_train_epoch_equals_stepping_through_the_batches(mode):
+    """p3d_model_train_epoch (device-side gather + one replayed CUDA graph per batch) == the reference's loop
+    `for i in range(nbatches): model.step(sess, enc[i], dec[i], keep, isTraining=True)` (predict_3dpose.py:242-249)
+    over the same permutation; the ragged tail is dropped like get_all_batches does (linear_model.py:311-313)."""
+    cfg = M.Config(256, 1, True, True, True)
+    n, B, keep = 1000, 64, 0.7
+    x, t = synth.mlp_inputs(n, seed=12)
+    perm = np.random.RandomState(3).permutation(n)
+    ma, _ = make_model(cfg, seed=5, bn="fresh", mode=mode, batch_size=B)
+    mb, _ = make_model(cfg, seed=5, bn="fresh", mode=mode, batch_size=B)
+    losses, lr = ma.train_epoch(x, t, keep, perm=perm)
+    assert losses.shape == (n // B,) and int(ma.global_step) == n // B
+    ref = []
+    for b in range(n // B):
+        idx = perm[b * B:(b + 1) * B]
+        loss, _, lrs, _ = mb.step(None, x[idx], t[idx], keep, isTraining=True)
+        ref.append(float(loss))
+    np.testing.assert_allclose(losses, np.array(ref), rtol=2e-4, atol=1e-6)
+    assert abs(lr - float(lrs.value)) < 1e-9
+    va, vb = ma.get_variables(), mb.get_variables()
+    for k in va:
+        assert np.abs(va[k] - vb[k]).max() <= 2e-3 * max(np.abs(vb[k]).max(), 1e-3), k    # Adam amplifies last-bit differences of atomics
+    # torch in -> torch out, natural order
+    lt, _ = ma.train_epoch(torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda(), 1.0, shuffle=False)
+    assert lt.is_cuda and lt.shape == (n // B,) and torch.isfinite(lt).all()
+    ma.close(); mb.close()
