@@ -81,6 +81,9 @@ struct FusedArgs {
 //                            float4 stores (384 contiguous bytes per warp per camera)
 // The camera-frame root-centred joint is R(q - hip): T cancels, so the hip is subtracted once in world space.
 constexpr int PN_WARPS = 8;
+#ifndef PN_BLOCKS
+#define PN_BLOCKS 4
+#endif
 #define PIN(v) asm volatile("" : "+f"(v))
 // NC = number of cameras, compile time: the camera loop is fully unrolled so that every camera parameter is an
 // immediate constant-bank operand of the FFMA that uses it (with a runtime camera index ptxas emits ~30 LDC per
@@ -88,7 +91,7 @@ constexpr int PN_WARPS = 8;
 // roofline).  H2/H3: which outputs are requested (compile time: no per-camera uniform branches).
 constexpr int PN_POSE_PITCH = 100;   // floats between the two poses of a slab: shifts pose 1 by 4 banks (no 2-way conflicts)
 template <int NC, bool H2, bool H3>
-__global__ void __launch_bounds__(PN_WARPS * 32, 3) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
+__global__ void __launch_bounds__(PN_WARPS * 32, PN_BLOCKS) project_normalize_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
                                                                             float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
   __shared__ __align__(16) float s_in[PN_WARPS][2 * PN_POSE_PITCH];
   __shared__ __align__(16) float s_out[PN_WARPS][2][2 * 48 + 4];      // +4: dump slot for lanes without a 3D joint
@@ -348,7 +351,7 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
     for (int d = 0; d < n; ++d) { a.mean3[d] = (float)mean3d[use[d]]; a.istd3[d] = (float)(1.0 / std3d[use[d]]); }
   }
   const long long nblocks = ((N + 1) / 2 + PN_WARPS - 1) / PN_WARPS;
-  const int grid = nblocks < 148 * 3 ? (int)nblocks : 148 * 3;
+  const int grid = nblocks < 148 * PN_BLOCKS ? (int)nblocks : 148 * PN_BLOCKS;
   cudaStream_t st = (cudaStream_t)stream;
   switch (ncams) {
 #define P3D_PN_CASE(NC) case NC: launch_project_normalize<NC>(grid, st, world, a, x2d, y3d, N); break;

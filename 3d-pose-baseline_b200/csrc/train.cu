@@ -151,8 +151,15 @@ __global__ void clipdot_kernel(const float* __restrict__ theta, const float* __r
   const float* w = theta + e.off_w;
   const float* g = grad + e.off_w;
   double acc = 0.0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-    acc += static_cast<double>(w[i]) * g[i];
+  if ((n & 3) == 0 && (e.off_w & 3) == 0) {
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+      const float4 a = *reinterpret_cast<const float4*>(w + i), b = *reinterpret_cast<const float4*>(g + i);
+      acc += static_cast<double>(a.x) * b.x + static_cast<double>(a.y) * b.y + static_cast<double>(a.z) * b.z + static_cast<double>(a.w) * b.w;
+    }
+  } else {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+      acc += static_cast<double>(w[i]) * g[i];
+  }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __shared__ double part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
@@ -427,13 +434,35 @@ __global__ void adam_clip_kernel(float* __restrict__ theta, float* __restrict__ 
     beg = n_w; end = n_train;
   }
   const float alpha = sc->alpha;
-  for (long long i = beg + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < end; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float g = grad[i];
-    if (pull) { g = (g - theta[i] * cd) * cs; grad[i] = g; }     // model.gradients exposes the pulled-back gradient
-    const float mi = m[i] + (g - m[i]) * 0.1f;
-    const float vi = v[i] + (g * g - v[i]) * 0.001f;
-    m[i] = mi; v[i] = vi;
-    theta[i] -= alpha * mi / (sqrtf(vi) + 1e-8f);
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x, nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (((beg | (end - beg)) & 3) == 0) {
+    for (long long i = beg + tid * 4; i < end; i += nth * 4) {
+      float4 g4 = *reinterpret_cast<const float4*>(grad + i);
+      float4 t4 = *reinterpret_cast<const float4*>(theta + i);
+      float4 m4 = *reinterpret_cast<const float4*>(m + i);
+      float4 v4 = *reinterpret_cast<const float4*>(v + i);
+      float g[4] = {g4.x, g4.y, g4.z, g4.w}, th[4] = {t4.x, t4.y, t4.z, t4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (pull) g[j] = (g[j] - th[j] * cd) * cs;
+        mm[j] = mm[j] + (g[j] - mm[j]) * 0.1f;
+        vv[j] = vv[j] + (g[j] * g[j] - vv[j]) * 0.001f;
+        th[j] -= alpha * mm[j] / (sqrtf(vv[j]) + 1e-8f);
+      }
+      if (pull) *reinterpret_cast<float4*>(grad + i) = make_float4(g[0], g[1], g[2], g[3]);   // model.gradients exposes the pulled-back gradient
+      *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(theta + i) = make_float4(th[0], th[1], th[2], th[3]);
+    }
+  } else {
+    for (long long i = beg + tid; i < end; i += nth) {
+      float g = grad[i];
+      if (pull) { g = (g - theta[i] * cd) * cs; grad[i] = g; }
+      const float mi = m[i] + (g - m[i]) * 0.1f;
+      const float vi = v[i] + (g * g - v[i]) * 0.001f;
+      m[i] = mi; v[i] = vi;
+      theta[i] -= alpha * mi / (sqrtf(vi) + 1e-8f);
+    }
   }
 }
 
@@ -545,7 +574,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   if (clip || tc) {
     // one launch over all layers: ||W||_F^2 (clip_by_norm) and, on the tensor-core path, this step's bf16 copy of
     // W in its natural [K][N] layout (W4 rows padded to kOutPad)
-    wprep_kernel<<<dim3(64, nlay), 256, 0, st>>>(m->theta, tab, tc ? w.wb : nullptr, clip ? m->norm2 : nullptr);
+    wprep_kernel<<<dim3(148, nlay), 256, 0, st>>>(m->theta, tab, tc ? w.wb : nullptr, clip ? m->norm2 : nullptr);
     P3D_LAUNCH_CHECK();
   }
   if (clip) {
@@ -706,13 +735,13 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   // ---------------------------------------------------------------- gradient exchange + update
   P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
   if (clip) {
-    clipdot_kernel<<<dim3(64, nlay), 256, 0, st>>>(m->theta, m->grad, tab, dots);
+    clipdot_kernel<<<dim3(148, nlay), 256, 0, st>>>(m->theta, m->grad, tab, dots);
     P3D_LAUNCH_CHECK();
   }
   finish_step_scalars_kernel<<<1, 1, 0, st>>>(lossacc, static_cast<double>(Bg) * out, sc, loss, lr_used);
   P3D_LAUNCH_CHECK();
   const long long n_w = static_cast<long long>(m->layers[nh].off_w) + static_cast<long long>(m->layers[nh].K) * m->layers[nh].N;
-  adam_clip_kernel<<<dim3(64, nlay + 1), 256, 0, st>>>(m->theta, m->grad, m->adam_m, m->adam_v, tab, nlay, n_w,
+  adam_clip_kernel<<<dim3(296, nlay + 1), 256, 0, st>>>(m->theta, m->grad, m->adam_m, m->adam_v, tab, nlay, n_w,
                                                       static_cast<long long>(m->n_train), sc, dots, m->norm2, clip ? 1 : 0);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
