@@ -150,6 +150,7 @@ struct GemmArgs {
   // programmatic dependent launch: the kernel may start before its stream predecessor has finished; B (weights)
   // must not depend on that predecessor - its first tiles are fetched ahead of the dependency wait
   int pdl = 0;
+  void* dbg = nullptr;                // diagnostics: [ctas][8] globaltimer stamps
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
 // and launched many times while the operand pointers/shapes stay the same.

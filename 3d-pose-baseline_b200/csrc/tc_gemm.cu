@@ -30,9 +30,10 @@ constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box = 8 KB
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int EPI_THREADS = 256;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
 __host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
 
@@ -53,7 +54,10 @@ struct Params {
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
+  unsigned long long* dbg;  // optional [ctas][8] globaltimer stamps (diagnostics)
 };
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -72,6 +76,20 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// shared-space accessors: the tile pointer is derived from the aligned dynamic-smem base by integer arithmetic, which
+// makes the compiler fall back to GENERIC ld/st (long-scoreboard latency) - say the address space explicitly
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// OUT: 0 = fp32 store, 1 = fp32 reduction (split-K / accumulate), 2 = bf16 (relu, residual in bf16)
+// RES: a residual operand is added;  CS: column sums of the result and its square are accumulated
+template <int OUT, bool RES, bool CS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -84,8 +102,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* accf = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+  float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + 256);
+  float* scol = sbias + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) P3D_STAMP(0);
   const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
@@ -103,6 +124,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_launch_dependents();     // the next kernel of a programmatic-dependent chain may start its prologue now
+  if (warp == 0) P3D_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -139,6 +161,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    P3D_STAMP(2);
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
@@ -147,6 +170,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(&full[stage], phase, 2);
+      if (kb == 0) P3D_STAMP(3);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t aa = a_base + stage * A_BYTES, bb = b_base + stage * B_BYTES;
@@ -162,6 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    P3D_STAMP(4);
   } else {
     // ------------------------------------------------------------ epilogue: warp w owns TMEM lanes 32*(w%4)..+31
     // tcgen05.ld hands every lane one ROW (32 consecutive columns).  Storing that directly makes each instruction
@@ -169,134 +194,155 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // (the operand ring is free once the accumulator is complete) so that a lane owns 4 COLUMNS x 8 rows: every
     // global access (C, residual, bf16 output, fp32 reductions) is then 4 full 128-byte lines per instruction, bias
     // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
-    const int ew = warp & 3;
+    // The epilogue variant is a template parameter and the bias sits in smem before the accumulator is complete:
+    // the first version (runtime flags, generic smem accesses, bias re-loaded per chunk) spent 11 of the 20 us of a
+    // 4096 x 1024 x 1024 GEMM here, one warp per scheduler crawling through ~2800 SASS instructions of branches.
+    const int ew = warp & 3;                     // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;            // which half of the tile's columns
+    const int cbeg = half * (p.bn / 2), cend = cbeg + p.bn / 2;
     const bool first_split = (blockIdx.z == 0);
     grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
+    const int et = (warp - 2) * 32 + lane;       // 0..255
+    for (int j = et; j < p.bn; j += EPI_THREADS) {
+      sbias[j] = (first_split && p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+    }
+    named_bar_sync(1, EPI_THREADS);
+    constexpr int TP = 36;                                   // tile pitch in floats (144 B): conflict-free both ways
+    const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
+    const uint32_t sbias_s = smem_u32(sbias);
+    const int rg = lane >> 3, cq = (lane & 7) * 4;           // row group (rows rg, rg+4, ...), first of this lane's 4 columns
+    const int mrow0 = m0 + ew * 32 + rg;                     // this lane's rows: mrow0 + 4 i
+    const bool use_res = RES && (OUT == 2 || first_split);
+    // fast path: the whole tile is inside N and every pointer/pitch allows vector accesses
+    bool fast = (n0 + p.bn <= p.N);
+    if (OUT == 2) fast = fast && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_b) & 7) == 0) &&
+                         (!RES || (((p.ldrb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res_b) & 7) == 0)));
+    else fast = fast && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!RES || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)));
     mbar_wait(accf, 0, 3);
+    if (warp == 2) P3D_STAMP(5);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    constexpr int TP = 36;                                   // tile pitch in floats (144 B): conflict-free both ways
-    float* tile = reinterpret_cast<float*>(smem) + ew * 32 * TP;
-    const int rg = lane >> 3, cq = (lane & 7) * 4;           // row group (rows rg, rg+4, ...), first of this lane's 4 columns
-    const bool c_vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    const bool r_vec = p.res && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
-    const bool ob_vec = p.out_b && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_b) & 7) == 0);
-    const bool rb_vec = p.res_b && ((p.ldrb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res_b) & 7) == 0);
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+    uint32_t v[32];
+    if (n0 + cbeg < p.N) tmem_ld_32x32b_x32(taddr + cbeg, v);
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       if (n0 + c0 >= p.N) break;     // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + c0, v);
+      const bool more = (c0 + 32 < cend) && (n0 + c0 + 32 < p.N);
       tmem_ld_wait();
       __syncwarp();                  // the previous chunk's readers are done with the tile
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(tile + lane * TP + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 32; j += 4) sts128(tile_s + (lane * TP + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
+      if (more) tmem_ld_32x32b_x32(taddr + c0 + 32, v);      // in flight while this chunk is processed
       const int n = n0 + c0 + cq;                            // this lane's columns n .. n+3
-      const bool full4 = n + 3 < p.N;
-      float bias[4] = {0.f, 0.f, 0.f, 0.f};
-      if (first_split && p.bias) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (n + j < p.N) bias[j] = __ldg(p.bias + n + j);
-      }
+      const float4 b4 = lds128(sbias_s + (c0 + cq) * 4);
       float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
-      // residual rows first: 8 independent loads in flight instead of one dependent load per row
-      float4 rres[8];
-      uint2 rresb[8];
-      const bool use_res = p.res && first_split && !p.out_b, use_resb = p.out_b && p.res_b;
-      if (use_res || use_resb) {
+      if (fast) {
+        float4 t4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t4[i] = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
+        float4 r4[8];
+        uint2 rb[8];
+        if (use_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            r4[i] = make_float4(0.f, 0.f, 0.f, 0.f); rb[i] = make_uint2(0u, 0u);
+            if (m < p.M) {
+              if (OUT == 2) rb[i] = *reinterpret_cast<const uint2*>(p.res_b + static_cast<size_t>(m) * p.ldrb + n);
+              else r4[i] = __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(m) * p.ldres + n));
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int m = m0 + ew * 32 + i * 4 + rg;
-          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f); rresb[i] = make_uint2(0u, 0u);
-          if (m < p.M) {
-            if (use_res) {
-              const float* rr = p.res + static_cast<size_t>(m) * p.ldres + n;
-              if (r_vec && full4) rres[i] = __ldg(reinterpret_cast<const float4*>(rr));
-              else {
-                if (n < p.N) rres[i].x = __ldg(rr);
-                if (n + 1 < p.N) rres[i].y = __ldg(rr + 1);
-                if (n + 2 < p.N) rres[i].z = __ldg(rr + 2);
-                if (n + 3 < p.N) rres[i].w = __ldg(rr + 3);
-              }
-            } else {
-              const __nv_bfloat16* rr = p.res_b + static_cast<size_t>(m) * p.ldrb + n;
-              if (rb_vec && full4) rresb[i] = *reinterpret_cast<const uint2*>(rr);
-              else {
-                __nv_bfloat16 tmp[4];
+          const int m = mrow0 + 4 * i;
+          const bool live = m < p.M;
+          float o[4] = {alpha * t4[i].x + b4.x, alpha * t4[i].y + b4.y, alpha * t4[i].z + b4.z, alpha * t4[i].w + b4.w};
+          if (CS) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) tmp[j] = (n + j < p.N) ? rr[j] : __float2bfloat16_rn(0.f);
-                memcpy(&rresb[i], tmp, 8);
-              }
+            for (int j = 0; j < 4; ++j) { const float q = live ? o[j] : 0.f; cs1[j] += q; cs2[j] += q * q; }
+          }
+          if (OUT == 2) {
+            // bf16 activations of the layered inference path: same rounding points as the fused persistent kernel
+            // (relu(.) rounded to bf16, then the residual added and rounded again)
+            __nv_bfloat16 ob[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(p.relu ? fmaxf(o[j], 0.f) : o[j]);
+            if (use_res) {
+              __nv_bfloat16 rv[4];
+              memcpy(rv, &rb[i], 8);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(__bfloat162float(ob[j]) + __bfloat162float(rv[j]));
+            }
+            uint2 q; memcpy(&q, ob, 8);
+            if (live) *reinterpret_cast<uint2*>(p.out_b + static_cast<size_t>(m) * p.ldob + n) = q;
+          } else {
+            if (use_res) { o[0] += r4[i].x; o[1] += r4[i].y; o[2] += r4[i].z; o[3] += r4[i].w; }
+            float* crow = p.C + static_cast<size_t>(m) * p.ldc + n;
+            if (live) {
+              if (OUT == 1) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+              else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      } else {
+        // ragged / unaligned tile (N = 48 or 42 output layer, odd pitches): element by element, not unrolled
+        const float bias[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int m = mrow0 + 4 * i;
+          if (m >= p.M) continue;
+          const float4 t = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
+          const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            if (n + j >= p.N) break;
+            float o = alpha * tv[j] + bias[j];
+            if (CS) { cs1[j] += o; cs2[j] += o * o; }
+            if (OUT == 2) {
+              __nv_bfloat16 ob = __float2bfloat16_rn(p.relu ? fmaxf(o, 0.f) : o);
+              if (use_res) ob = __float2bfloat16_rn(__bfloat162float(ob) + __bfloat162float(p.res_b[static_cast<size_t>(m) * p.ldrb + n + j]));
+              p.out_b[static_cast<size_t>(m) * p.ldob + n + j] = ob;
+            } else {
+              if (use_res) o += __ldg(p.res + static_cast<size_t>(m) * p.ldres + n + j);
+              float* c = p.C + static_cast<size_t>(m) * p.ldc + n + j;
+              if (OUT == 1) atomicAdd(c, o); else *c = o;
             }
           }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rg;
-        const int m = m0 + ew * 32 + r;
-        const float4 t4 = *reinterpret_cast<const float4*>(tile + r * TP + cq);
-        float o[4] = {alpha * t4.x + bias[0], alpha * t4.y + bias[1], alpha * t4.z + bias[2], alpha * t4.w + bias[3]};
-        if (m >= p.M) continue;
-        if (p.colsum) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { cs1[j] += o[j]; cs2[j] += o[j] * o[j]; }
-        }
-        if (p.out_b) {
-          // bf16 activations of the layered inference path: same rounding points as the fused persistent kernel
-          // (relu(.) rounded to bf16, then the residual added and rounded again)
-          __nv_bfloat16 ob[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(p.relu ? fmaxf(o[j], 0.f) : o[j]);
-          if (use_resb) {
-            __nv_bfloat16 rv[4];
-            memcpy(rv, &rresb[i], 8);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ob[j] = __float2bfloat16_rn(__bfloat162float(ob[j]) + __bfloat162float(rv[j]));
-          }
-          __nv_bfloat16* orow = p.out_b + static_cast<size_t>(m) * p.ldob + n;
-          if (ob_vec && full4) { uint2 q; memcpy(&q, ob, 8); *reinterpret_cast<uint2*>(orow) = q; }
-          else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (n + j < p.N) orow[j] = ob[j];
-          }
-          continue;
-        }
-        if (use_res) { o[0] += rres[i].x; o[1] += rres[i].y; o[2] += rres[i].z; o[3] += rres[i].w; }
-        float* crow = p.C + static_cast<size_t>(m) * p.ldc + n;
-        if (c_vec && full4) {
-          if (p.atomic) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
-          else *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j < p.N) { if (p.atomic) atomicAdd(crow + j, o[j]); else crow[j] = o[j]; }
-          }
-        }
-      }
-      if (p.colsum) {
+      if (CS) {
         // this lane holds 8 of the warp's 32 rows for its 4 columns: fold the 4 row groups, then lanes 0..7 publish
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 8);  cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 8);
           cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16); cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
         }
-        if (rg == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j < p.N) {
-              atomicAdd(p.colsum + n + j, static_cast<double>(cs1[j]));
-              atomicAdd(p.colsum + p.N + n + j, static_cast<double>(cs2[j]));
-            }
-          }
+        if (rg == 0) {            // this quadrant's partial sums -> smem (plain stores: one writer per slot)
+          float* q1 = scol + ew * 512 + c0 + cq;
+          *reinterpret_cast<float4*>(q1) = make_float4(cs1[0], cs1[1], cs1[2], cs1[3]);
+          *reinterpret_cast<float4*>(q1 + 256) = make_float4(cs2[0], cs2[1], cs2[2], cs2[3]);
+        }
+      }
+    }
+    if (CS) {
+      named_bar_sync(1, EPI_THREADS);
+      for (int j = et; j < p.bn; j += EPI_THREADS) {        // one global fp64 atomic per column per CTA
+        if (n0 + j < p.N) {
+          const float s1 = (scol[j] + scol[512 + j]) + (scol[1024 + j] + scol[1536 + j]);
+          const float s2 = (scol[256 + j] + scol[768 + j]) + (scol[1280 + j] + scol[1792 + j]);
+          atomicAdd(p.colsum + n0 + j, static_cast<double>(s1));
+          atomicAdd(p.colsum + p.N + n0 + j, static_cast<double>(s2));
         }
       }
     }
   }
+  if (warp == 2) P3D_STAMP(6);
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) P3D_STAMP(7);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
 }
 
@@ -372,6 +418,7 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
   p.b_independent = g.pdl ? 1 : 0;
+  p.dbg = static_cast<unsigned long long*>(g.dbg);
   d->pdl = g.pdl;
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
@@ -383,9 +430,23 @@ int plan(const GemmArgs& g, GemmPlan* out) {
 int launch(const GemmPlan& pl, cudaStream_t st) {
   P3D_REQUIRE(pl.valid, "tc_gemm: launch of an unplanned GEMM");
   const PlanData* d = reinterpret_cast<const PlanData*>(pl.blob);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Params);
+  const Params& q = d->p;
+  const int out = q.out_b ? 2 : (q.atomic ? 1 : 0);
+  const bool res = q.out_b ? (q.res_b != nullptr) : (q.res != nullptr), cs = q.colsum != nullptr;
+  KernelFn fn = nullptr;
+#define P3D_TCG_PICK(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S>;
+  P3D_TCG_PICK(0, false, false) P3D_TCG_PICK(0, false, true) P3D_TCG_PICK(0, true, false) P3D_TCG_PICK(0, true, true)
+  P3D_TCG_PICK(1, false, false) P3D_TCG_PICK(1, true, false)
+  P3D_TCG_PICK(2, false, false) P3D_TCG_PICK(2, true, false)
+#undef P3D_TCG_PICK
+  P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
   static bool attr = false;
   if (!attr) {
-    P3D_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    KernelFn all[] = {tc_gemm_kernel<0, false, false>, tc_gemm_kernel<0, false, true>, tc_gemm_kernel<0, true, false>,
+                      tc_gemm_kernel<0, true, true>, tc_gemm_kernel<1, false, false>, tc_gemm_kernel<1, true, false>,
+                      tc_gemm_kernel<2, false, false>, tc_gemm_kernel<2, true, false>};
+    for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -398,7 +459,7 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs; cfg.numAttrs = 1;
   }
-  P3D_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, d->ta, d->tb, d->p));
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->p));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
