@@ -235,8 +235,13 @@ P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
   float B[3][3], V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
   P3D_UNROLL
   for (int i = 0; i < 3; ++i) { B[i][0] = A[i * 3]; B[i][1] = A[i * 3 + 1]; B[i][2] = A[i * 3 + 2]; }
+  // Three sweeps reach fp32 accuracy on every test set (random, mirrored, nearly planar, near-identity); a fourth
+  // runs only for a pose whose third sweep still rotated by more than ~1e-3 rad (quadratic convergence).
+  bool again = true;
   P3D_UNROLL
-  for (int sweep = 0; sweep < 4; ++sweep) {   // 3 already converge to fp32 accuracy on every test set
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    if (sweep == 3 && !again) break;
+    float tmax = 0.f;
     P3D_UNROLL
     for (int r = 0; r < 3; ++r) {
       const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
@@ -250,6 +255,7 @@ P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
         const float t = (zeta >= 0.f ? 1.f : -1.f) * p3d_rcp_fast(fabsf(zeta) + p3d_sqrt_fast(zeta * zeta + 1.f));
         c = p3d_rsqrt(t * t + 1.f);
         s = t * c;
+        tmax = fmaxf(tmax, fabsf(t));
       }
       P3D_UNROLL
       for (int k = 0; k < 3; ++k) {
@@ -259,6 +265,7 @@ P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
         V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
       }
     }
+    again = tmax > 1e-3f;
   }
   float l0 = B[0][0] * B[0][0] + B[1][0] * B[1][0] + B[2][0] * B[2][0];
   float l1 = B[0][1] * B[0][1] + B[1][1] * B[1][1] + B[2][1] * B[2][1];
@@ -306,21 +313,22 @@ P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
 
 // Per-pose errors of predict_3dpose.evaluate_batches (src/predict_3dpose.py:399-442) in fp32.
 //   W, J0        : row width (48 or 42) and 1 when the implicit hip joint is part of the error (W = 48)
-//   g(k), p(k)   : normalised ground truth / prediction, k in [0, W)
+//   g[k], p[k]   : normalised ground truth / prediction, k in [0, W) - OVERWRITTEN with the centred un-normalised
+//                  coordinates (the arrays live in registers in the kernel; pass 3 reuses them)
 //   sd[k]        : data_std_3d gathered to the used dims
 //   mc[k]        : data_mean_3d gathered, minus the mean over the J joints of the un-normalised MEAN pose
 //                  (so that centred coordinates come out of one fma and stay small)
 //   hipc[3]      : same for the hip joint (un-normalised hip = data_mean_3d[0:3] for both poses)
 // Centred joint: x_c = g*sd + mc - (sum_k g_k sd_k)/J.   Aligned error: b (y_c T) - x_c  (= b y T + c - x).
-template <int W, int J0, class LDG, class LDP>
-P3D_HD void pose_errors_f32(LDG g, LDP p, const float* sd, const float* mc, const float* hipc, int use_procrustes, float* dj) {
+template <int W, int J0>
+P3D_HD void pose_errors_f32(float (&g)[W], float (&p)[W], const float* sd, const float* mc, const float* hipc, int use_procrustes, float* dj) {
   constexpr int J = W / 3 + J0;
   if (!use_procrustes) {
     if (J0) dj[0] = 0.f;
     P3D_UNROLL
     for (int j = J0; j < J; ++j) {
       const int k = (j - J0) * 3;
-      const float e0 = (p(k) - g(k)) * sd[k], e1 = (p(k + 1) - g(k + 1)) * sd[k + 1], e2 = (p(k + 2) - g(k + 2)) * sd[k + 2];
+      const float e0 = (p[k] - g[k]) * sd[k], e1 = (p[k + 1] - g[k + 1]) * sd[k + 1], e2 = (p[k + 2] - g[k + 2]) * sd[k + 2];
       dj[j] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
     }
     return;
@@ -329,34 +337,33 @@ P3D_HD void pose_errors_f32(LDG g, LDP p, const float* sd, const float* mc, cons
   P3D_UNROLL
   for (int k = 0; k < W; k += 3) {
     P3D_UNROLL
-    for (int d = 0; d < 3; ++d) { sx[d] += g(k + d) * sd[k + d]; sy[d] += p(k + d) * sd[k + d]; }
+    for (int d = 0; d < 3; ++d) { sx[d] += g[k + d] * sd[k + d]; sy[d] += p[k + d] * sd[k + d]; }
   }
   const float invJ = 1.0f / static_cast<float>(J);
   P3D_UNROLL
   for (int d = 0; d < 3; ++d) { sx[d] *= invJ; sy[d] *= invJ; }
   float ssx = 0.f, ssy = 0.f, A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float hx[3] = {0.f, 0.f, 0.f}, hy[3] = {0.f, 0.f, 0.f};
   if (J0) {
-    float x[3], y[3];
     P3D_UNROLL
-    for (int d = 0; d < 3; ++d) { x[d] = hipc[d] - sx[d]; y[d] = hipc[d] - sy[d]; ssx += x[d] * x[d]; ssy += y[d] * y[d]; }
+    for (int d = 0; d < 3; ++d) { hx[d] = hipc[d] - sx[d]; hy[d] = hipc[d] - sy[d]; ssx += hx[d] * hx[d]; ssy += hy[d] * hy[d]; }
     P3D_UNROLL
     for (int r = 0; r < 3; ++r)
       P3D_UNROLL
-      for (int s = 0; s < 3; ++s) A[r * 3 + s] += x[r] * y[s];
+      for (int s = 0; s < 3; ++s) A[r * 3 + s] += hx[r] * hy[s];
   }
   P3D_UNROLL
   for (int k = 0; k < W; k += 3) {
-    float x[3], y[3];
     P3D_UNROLL
     for (int d = 0; d < 3; ++d) {
-      x[d] = (g(k + d) * sd[k + d] + mc[k + d]) - sx[d];
-      y[d] = (p(k + d) * sd[k + d] + mc[k + d]) - sy[d];
-      ssx += x[d] * x[d]; ssy += y[d] * y[d];
+      g[k + d] = (g[k + d] * sd[k + d] + mc[k + d]) - sx[d];
+      p[k + d] = (p[k + d] * sd[k + d] + mc[k + d]) - sy[d];
+      ssx += g[k + d] * g[k + d]; ssy += p[k + d] * p[k + d];
     }
     P3D_UNROLL
     for (int r = 0; r < 3; ++r)
       P3D_UNROLL
-      for (int s = 0; s < 3; ++s) A[r * 3 + s] += x[r] * y[s];
+      for (int s = 0; s < 3; ++s) A[r * 3 + s] += g[k + r] * p[k + s];
   }
   const float inv = p3d_rsqrt(ssx * ssy);
   P3D_UNROLL
@@ -367,26 +374,17 @@ P3D_HD void pose_errors_f32(LDG g, LDP p, const float* sd, const float* mc, cons
   P3D_UNROLL
   for (int i = 0; i < 9; ++i) T[i] *= b;
   if (J0) {
-    float x[3], y[3];
-    P3D_UNROLL
-    for (int d = 0; d < 3; ++d) { x[d] = hipc[d] - sx[d]; y[d] = hipc[d] - sy[d]; }
-    const float e0 = (y[0] * T[0] + y[1] * T[3] + y[2] * T[6]) - x[0];
-    const float e1 = (y[0] * T[1] + y[1] * T[4] + y[2] * T[7]) - x[1];
-    const float e2 = (y[0] * T[2] + y[1] * T[5] + y[2] * T[8]) - x[2];
+    const float e0 = (hy[0] * T[0] + hy[1] * T[3] + hy[2] * T[6]) - hx[0];
+    const float e1 = (hy[0] * T[1] + hy[1] * T[4] + hy[2] * T[7]) - hx[1];
+    const float e2 = (hy[0] * T[2] + hy[1] * T[5] + hy[2] * T[8]) - hx[2];
     dj[0] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
   }
   P3D_UNROLL
   for (int j = J0; j < J; ++j) {
     const int k = (j - J0) * 3;
-    float x[3], y[3];
-    P3D_UNROLL
-    for (int d = 0; d < 3; ++d) {
-      x[d] = (g(k + d) * sd[k + d] + mc[k + d]) - sx[d];
-      y[d] = (p(k + d) * sd[k + d] + mc[k + d]) - sy[d];
-    }
-    const float e0 = (y[0] * T[0] + y[1] * T[3] + y[2] * T[6]) - x[0];
-    const float e1 = (y[0] * T[1] + y[1] * T[4] + y[2] * T[7]) - x[1];
-    const float e2 = (y[0] * T[2] + y[1] * T[5] + y[2] * T[8]) - x[2];
+    const float e0 = (p[k] * T[0] + p[k + 1] * T[3] + p[k + 2] * T[6]) - g[k];
+    const float e1 = (p[k] * T[1] + p[k + 1] * T[4] + p[k + 2] * T[7]) - g[k + 1];
+    const float e2 = (p[k] * T[2] + p[k + 1] * T[5] + p[k + 2] * T[8]) - g[k + 2];
     dj[j] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
   }
 }

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 3) mpjpe_f32_kernel(const float
     const long long pose = tile * 32 + lane;
     const bool live = pose < N;
     float dj[J];
-    pose_errors_f32<W, J0>([&](int k) { return g[k]; }, [&](int k) { return p[k]; }, a.sd, a.mc, a.hipc, a.use_procrustes, dj);
+    pose_errors_f32<W, J0>(g, p, a.sd, a.mc, a.hipc, a.use_procrustes, dj);
     if (dists && live) {
       float* dp = dists + pose * J;
 #pragma unroll

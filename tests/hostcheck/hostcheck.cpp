@@ -39,12 +39,14 @@ void hc_pose_errors_f32(const float* gt, const float* pred, const float* sd, con
                         int use_procrustes, float* dists, int n) {
   const int J = (W == 48) ? 17 : 14;
   for (int i = 0; i < n; ++i) {
-    const float* g = gt + (long long)i * W;
-    const float* p = pred + (long long)i * W;
-    auto lg = [g](int k) { return g[k]; };
-    auto lp = [p](int k) { return p[k]; };
-    if (W == 48) p3d::pose_errors_f32<48, 1>(lg, lp, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
-    else p3d::pose_errors_f32<42, 0>(lg, lp, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
+    float g[48], p[48];
+    for (int k = 0; k < W; ++k) { g[k] = gt[(long long)i * W + k]; p[k] = pred[(long long)i * W + k]; }
+    if (W == 48) p3d::pose_errors_f32<48, 1>(g, p, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
+    else {
+      float g2[42], p2[42];
+      for (int k = 0; k < 42; ++k) { g2[k] = g[k]; p2[k] = p[k]; }
+      p3d::pose_errors_f32<42, 0>(g2, p2, sd, mc, hipc, use_procrustes, dists + (long long)i * J);
+    }
   }
 }
 }
