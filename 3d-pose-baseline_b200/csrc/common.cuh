@@ -130,6 +130,23 @@ int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, co
           int ldc, const Epilogue& e, cudaStream_t st);
 }  // namespace simt
 namespace tcg {
+// Extra operands of the small-batch (M <= 128: the whole batch is one tile, so per-column batch statistics are
+// CTA-local) fused training epilogues of tc_gemm.cu.
+//   mode 3, forward : acc = h_in W;  z = alpha acc + bias -> C;  BN batch statistics over the rows (mean / rstd /
+//                     moving averages written), ReLU, dropout (Philox or injected mask), + residual -> h, hb, mask
+//   mode 4, backward: acc = dz_next W^T;  dh = alpha acc (+ res) (-> dh_out);  da = dh * dropout * relu';  BN backward
+//                     with CTA-local column sums -> dzb (bf16), dgamma / dbeta (or the bias gradient without BN)
+struct FusedTrain {
+  const void* sc = nullptr;               // train::StepScalars (device)
+  const float* gamma = nullptr; const float* beta = nullptr;
+  float* mean = nullptr; float* rstd = nullptr;            // [N] written by mode 3, read by mode 4
+  float* mov_mean = nullptr; float* mov_var = nullptr;     // mode 3
+  float* h = nullptr; void* hb = nullptr; uint8_t* mask = nullptr; const uint8_t* mask_in = nullptr; const float* hres = nullptr;   // mode 3, [M][N]
+  const float* z = nullptr; float* dh_out = nullptr; void* dzb = nullptr;                                                       // mode 4, [M][N]
+  float* ggamma = nullptr; float* gbeta = nullptr; float* gbias = nullptr;                                                      // mode 4, [N]
+  int has_bn = 0, dropout = 0, layer = 0;
+  float invB = 1.f;
+};
 // tcgen05 GEMM (tc_gemm.cu): C[M,N] (+)= alpha * A B^T-form product of bf16 operands, fp32 result.
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
@@ -151,10 +168,12 @@ struct GemmArgs {
   // must not depend on that predecessor - its first tiles are fetched ahead of the dependency wait
   int pdl = 0;
   void* dbg = nullptr;                // diagnostics: [ctas][8] globaltimer stamps
+  int fused_mode = 0;                 // 0, or 3 / 4: small-batch fused training epilogue (needs M <= 128, unsplit K)
+  FusedTrain fused;
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
 // and launched many times while the operand pointers/shapes stay the same.
-struct alignas(64) GemmPlan { unsigned char blob[512]; int valid = 0; };
+struct alignas(64) GemmPlan { unsigned char blob[768]; int valid = 0; };
 int plan(const GemmArgs& g, GemmPlan* out);
 int launch(const GemmPlan& pl, cudaStream_t st);
 int gemm(const GemmArgs& g, cudaStream_t st);

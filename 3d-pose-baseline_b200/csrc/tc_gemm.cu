@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "train_common.cuh"
 
 namespace p3d {
 namespace tcg {
@@ -35,7 +36,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
 constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
-__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }   // BN = 32 also 8 (barrier slots)
 
 struct Params {
   int M, N, K;
@@ -53,8 +54,10 @@ struct Params {
   __nv_bfloat16* out_b; int ldob;
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
+  int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
   unsigned long long* dbg;  // optional [ctas][8] globaltimer stamps (diagnostics)
+  FusedTrain ft;            // OUT = 3 / 4 only
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
@@ -130,7 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ------------------------------------------------------------ TMA producer
     // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
-    const uint32_t bytes = A_BYTES + B_BYTES;
+    const uint32_t bytes = p.a_bytes + B_BYTES;
     auto load_a = [&](int stage, int k0) {
       uint8_t* a = sA + stage * A_BYTES;
       if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
@@ -194,12 +197,233 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // (the operand ring is free once the accumulator is complete) so that a lane owns 4 COLUMNS x 8 rows: every
     // global access (C, residual, bf16 output, fp32 reductions) is then 4 full 128-byte lines per instruction, bias
     // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
+    if constexpr (OUT == 3 || OUT == 4) {
+      // ------------------------------------------------------------ small-batch fused training epilogues
+      // M <= 128: this CTA holds ALL rows of its columns, so the batch statistics of BatchNorm (forward) and the
+      // column sums of its backward pass are CTA-local: two passes over the TMEM accumulator with a named barrier
+      // in between replace the GEMM + statistics + finalize + activation kernels (3 launches -> 1, both directions).
+      const int ew = warp & 3, half = (warp - 2) >> 2;
+      const int hw = p.bn >= 64 ? p.bn / 2 : 32;
+      const int cbeg = half * hw, cend = (cbeg + hw < p.bn) ? cbeg + hw : p.bn;
+      const train::StepScalars* sc = static_cast<const train::StepScalars*>(p.ft.sc);
+      grid_dependency_wait();
+      const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
+      const int et = (warp - 2) * 32 + lane;
+      for (int j = et; j < p.bn; j += EPI_THREADS) sbias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      named_bar_sync(1, EPI_THREADS);
+      constexpr int TP = 36;
+      const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
+      const uint32_t sbias_s = smem_u32(sbias);
+      const int rg = lane >> 3, cq = (lane & 7) * 4;
+      const int mrow0 = ew * 32 + rg;                          // m0 == 0
+      const float keep = sc->keep, inv_keep = sc->inv_keep;
+      mbar_wait(accf, 0, 3);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      // accumulator chunk -> this lane's 4 columns x 8 rows (rows mrow0 + 4 i), as alpha * acc + bias
+      auto chunk = [&](int c0, float (&o)[8][4]) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) sts128(tile_s + (lane * TP + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const float4 b4 = lds128(sbias_s + (c0 + cq) * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
+          o[i][0] = alpha * t.x + b4.x; o[i][1] = alpha * t.y + b4.y; o[i][2] = alpha * t.z + b4.z; o[i][3] = alpha * t.w + b4.w;
+        }
+      };
+      auto publish = [&](int c0, float (&s1)[4], float (&s2)[4]) {     // fold the 4 row groups, quadrant partial -> smem
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+        }
+        if (rg == 0) {
+          float* q1 = scol + ew * 512 + c0 + cq;
+          *reinterpret_cast<float4*>(q1) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+          *reinterpret_cast<float4*>(q1 + 256) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+        }
+      };
+      auto totals = [&](int c0, float (&S1)[4], float (&S2)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + cq + j;
+          S1[j] = (scol[c] + scol[512 + c]) + (scol[1024 + c] + scol[1536 + c]);
+          S2[j] = (scol[256 + c] + scol[768 + c]) + (scol[1280 + c] + scol[1792 + c]);
+        }
+      };
+      const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
+      const float invB = p.ft.invB;
+      if constexpr (OUT == 3) {
+        // ---- forward: z = alpha acc + bias; batch statistics; BN, ReLU, dropout, residual
+        if (has_bn) {
+          for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+            float o[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+            chunk(c0, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool live = mrow0 + 4 * i < p.M;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float q = live ? o[i][j] : 0.f; s1[j] += q; s2[j] += q * q; }
+            }
+            publish(c0, s1, s2);
+          }
+        }
+        named_bar_sync(1, EPI_THREADS);
+        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+          float o[8][4];
+          chunk(c0, o);
+          const int n = n0 + c0 + cq;
+          float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+          if (has_bn) {
+            float S1[4], S2[4];
+            totals(c0, S1, S2);
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+            float var[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mu[j] = S1[j] * invB;
+              var[j] = fmaxf(S2[j] * invB - mu[j] * mu[j], 0.f);        // biased, as TF's non-fused path
+              rs[j] = 1.f / sqrtf(var[j] + kBnEps);
+            }
+            if (ew == 0 && rg == 0) {                                   // one writer per column
+              *reinterpret_cast<float4*>(p.ft.mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+              *reinterpret_cast<float4*>(p.ft.rstd + n) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+              float4 mm = *reinterpret_cast<const float4*>(p.ft.mov_mean + n), mv = *reinterpret_cast<const float4*>(p.ft.mov_var + n);
+              mm.x = mm.x * kBnMomentum + mu[0] * (1.f - kBnMomentum); mm.y = mm.y * kBnMomentum + mu[1] * (1.f - kBnMomentum);
+              mm.z = mm.z * kBnMomentum + mu[2] * (1.f - kBnMomentum); mm.w = mm.w * kBnMomentum + mu[3] * (1.f - kBnMomentum);
+              mv.x = mv.x * kBnMomentum + var[0] * (1.f - kBnMomentum); mv.y = mv.y * kBnMomentum + var[1] * (1.f - kBnMomentum);
+              mv.z = mv.z * kBnMomentum + var[2] * (1.f - kBnMomentum); mv.w = mv.w * kBnMomentum + var[3] * (1.f - kBnMomentum);
+              *reinterpret_cast<float4*>(p.ft.mov_mean + n) = mm;
+              *reinterpret_cast<float4*>(p.ft.mov_var + n) = mv;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            if (m >= p.M) continue;
+            const size_t off = static_cast<size_t>(m) * p.N + n;
+            *reinterpret_cast<float4*>(p.C + off) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);      // z, for the backward pass
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = has_bn ? ga[j] * ((o[i][j] - mu[j]) * rs[j]) + be[j] : o[i][j];
+              r[j] = fmaxf(a, 0.f);
+            }
+            if (dropout) {
+              uint8_t kb[4];
+              if (p.ft.mask_in) {
+                const uchar4 mi = *reinterpret_cast<const uchar4*>(p.ft.mask_in + off);
+                kb[0] = mi.x; kb[1] = mi.y; kb[2] = mi.z; kb[3] = mi.w;
+              } else {
+                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer), static_cast<uint32_t>(m), static_cast<uint32_t>(n >> 2));
+                kb[0] = train::keep_bit(w4.x, keep); kb[1] = train::keep_bit(w4.y, keep); kb[2] = train::keep_bit(w4.z, keep); kb[3] = train::keep_bit(w4.w, keep);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r[j] = kb[j] ? r[j] * inv_keep : 0.f;
+              *reinterpret_cast<uchar4*>(p.ft.mask + off) = make_uchar4(kb[0], kb[1], kb[2], kb[3]);
+            }
+            if (p.ft.hres) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(p.ft.hres + off));
+              r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+            }
+            *reinterpret_cast<float4*>(p.ft.h + off) = make_float4(r[0], r[1], r[2], r[3]);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.ft.hb) + off) = pk;
+          }
+        }
+      } else {
+        // ---- backward: dh = alpha acc (+ res); da = dh * dropout * relu'(act); BN backward with CTA-local sums
+        auto da_of = [&](int c0, float (&o)[8][4], float (&xh)[8][4], const float (&mu)[4], const float (&rs)[4], const float (&ga)[4],
+                         const float (&be)[4], bool store_dh) {
+          const int n = n0 + c0 + cq;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const bool live = m < p.M;
+            const size_t off = static_cast<size_t>(live ? m : 0) * p.N + n;
+            if (p.res) { const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + off)); o[i][0] += q.x; o[i][1] += q.y; o[i][2] += q.z; o[i][3] += q.w; }
+            if (store_dh && p.ft.dh_out && live) *reinterpret_cast<float4*>(p.ft.dh_out + off) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.ft.z + off));
+            uchar4 mk = make_uchar4(1, 1, 1, 1);
+            if (dropout) mk = *reinterpret_cast<const uchar4*>(p.ft.mask + off);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+            const unsigned char kk[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              xh[i][j] = has_bn ? (zz[j] - mu[j]) * rs[j] : 0.f;
+              const float act = has_bn ? ga[j] * xh[i][j] + be[j] : zz[j];
+              float gr = o[i][j];
+              if (dropout) gr = kk[j] ? gr * inv_keep : 0.f;
+              o[i][j] = (live && act > 0.f) ? gr : 0.f;            // da
+            }
+          }
+        };
+        auto bn_consts = [&](int c0, float (&mu)[4], float (&rs)[4], float (&ga)[4], float (&be)[4]) {
+          const int n = n0 + c0 + cq;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { mu[j] = 0.f; rs[j] = 1.f; ga[j] = 1.f; be[j] = 0.f; }
+          if (has_bn) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
+            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+          }
+        };
+        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          chunk(c0, o);
+          bn_consts(c0, mu, rs, ga, be);
+          da_of(c0, o, xh, mu, rs, ga, be, true);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1[j] += o[i][j]; s2[j] += o[i][j] * xh[i][j]; }
+          publish(c0, s1, s2);
+        }
+        named_bar_sync(1, EPI_THREADS);
+        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4], P[4], Q[4];
+          chunk(c0, o);
+          bn_consts(c0, mu, rs, ga, be);
+          da_of(c0, o, xh, mu, rs, ga, be, false);
+          totals(c0, P, Q);
+          const int n = n0 + c0 + cq;
+          if (ew == 0 && rg == 0) {                                     // one writer per column
+            if (has_bn) {
+              *reinterpret_cast<float4*>(p.ft.gbeta + n) = make_float4(P[0], P[1], P[2], P[3]);
+              *reinterpret_cast<float4*>(p.ft.ggamma + n) = make_float4(Q[0], Q[1], Q[2], Q[3]);
+            } else {
+              *reinterpret_cast<float4*>(p.ft.gbias + n) = make_float4(P[0], P[1], P[2], P[3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            if (m >= p.M) continue;
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = has_bn ? ga[j] * rs[j] * (o[i][j] - P[j] * invB - xh[i][j] * (Q[j] * invB)) : o[i][j];
+            __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.ft.dzb) + static_cast<size_t>(m) * p.N + n) = pk;
+          }
+        }
+      }
+    } else {
     // The epilogue variant is a template parameter and the bias sits in smem before the accumulator is complete:
     // the first version (runtime flags, generic smem accesses, bias re-loaded per chunk) spent 11 of the 20 us of a
     // 4096 x 1024 x 1024 GEMM here, one warp per scheduler crawling through ~2800 SASS instructions of branches.
     const int ew = warp & 3;                     // TMEM lane quadrant of this warp
     const int half = (warp - 2) >> 2;            // which half of the tile's columns
-    const int cbeg = half * (p.bn / 2), cend = cbeg + p.bn / 2;
+    const int hw = p.bn >= 64 ? p.bn / 2 : 32;                       // columns per half (BN = 32: the second half idles)
+    const int cbeg = half * hw, cend = (cbeg + hw < p.bn) ? cbeg + hw : p.bn;
     const bool first_split = (blockIdx.z == 0);
     grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
@@ -225,7 +449,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     uint32_t v[32];
-    if (n0 + cbeg < p.N) tmem_ld_32x32b_x32(taddr + cbeg, v);
+    if (cbeg < cend && n0 + cbeg < p.N) tmem_ld_32x32b_x32(taddr + cbeg, v);
     for (int c0 = cbeg; c0 < cend; c0 += 32) {
       if (n0 + c0 >= p.N) break;     // warp-uniform
       const bool more = (c0 + 32 < cend) && (n0 + c0 + 32 < p.N);
@@ -338,6 +562,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     }
+    }   // plain epilogues
   }
   if (warp == 2) P3D_STAMP(6);
   tc_fence_before();
@@ -382,7 +607,7 @@ static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
 }
 
 // A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
-struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; int pdl; };
+struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; int pdl; int fused_mode; };
 static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
 
 int plan(const GemmArgs& g, GemmPlan* out) {
@@ -395,6 +620,11 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   // wide tile (better MMA efficiency) and fills the machine through gridDim.z instead
   int bn = 256;
   while (bn > 64 && (bn > n64 || (!g.split_k && mt * ((g.N + bn - 1) / bn) < 100))) bn >>= 1;
+  // a split-K problem whose K is only a few blocks long (weight gradients of a small batch) is all epilogue:
+  // narrow tiles spread it over the machine instead
+  if (g.split_k && kblocks <= 4) { while (bn > 64 && mt * ((g.N + bn - 1) / bn) < 100) bn >>= 1; }
+  // one short M tile (small-batch inference): 32-wide tiles put twice as many SMs on the weight stream
+  if (bn == 64 && !g.b_mn && !g.split_k && mt == 1 && g.N >= 256 && (g.N % 32) == 0) bn = 32;
   const int nt = (g.N + bn - 1) / bn;
   int splits = 1;
   if (g.split_k) {
@@ -406,7 +636,10 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   const int kps = ((kblocks + splits - 1) / splits) * BK;
   splits = (g.K + kps - 1) / kps;
   PlanData* d = reinterpret_cast<PlanData*>(out->blob);
-  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, BM));
+  // K-major A of a short problem: fetch only the rows that exist (the MMA still reads 128 smem rows; what it makes
+  // of the stale ones lands in accumulator rows >= M, which are never stored)
+  const int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
+  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows));
   else P3D_TRY(make_map(&d->ta, g.A, g.M, g.K, g.lda, BK));
   if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn));
   else P3D_TRY(make_map(&d->tb, g.B, g.N, g.K, g.ldb, BK));
@@ -417,9 +650,18 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.colsum = g.colsum;
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
+  p.a_bytes = a_rows * BK * 2;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
   d->pdl = g.pdl;
+  p.ft = g.fused;
+  d->fused_mode = g.fused_mode;
+  if (g.fused_mode) {
+    P3D_REQUIRE(g.fused_mode == 3 || g.fused_mode == 4, "tc_gemm: unknown fused mode %d", g.fused_mode);
+    P3D_REQUIRE(mt == 1 && splits == 1 && (g.N % 32) == 0 && g.ldc == g.N && !g.out_bf16 && !g.colsum,
+                "tc_gemm: fused training epilogues need M <= 128, N %% 32 == 0, unsplit K, dense C");
+    P3D_REQUIRE(!g.res || g.ldres == g.N, "tc_gemm: fused epilogue residual must be dense");
+  }
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
   d->grid = dim3(nt, mt, splits);
@@ -440,12 +682,15 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   P3D_TCG_PICK(1, false, false) P3D_TCG_PICK(1, true, false)
   P3D_TCG_PICK(2, false, false) P3D_TCG_PICK(2, true, false)
 #undef P3D_TCG_PICK
+  if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, false>;
+  if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, false>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
   static bool attr = false;
   if (!attr) {
     KernelFn all[] = {tc_gemm_kernel<0, false, false>, tc_gemm_kernel<0, false, true>, tc_gemm_kernel<0, true, false>,
                       tc_gemm_kernel<0, true, true>, tc_gemm_kernel<1, false, false>, tc_gemm_kernel<1, true, false>,
-                      tc_gemm_kernel<2, false, false>, tc_gemm_kernel<2, true, false>};
+                      tc_gemm_kernel<2, false, false>, tc_gemm_kernel<2, true, false>,
+                      tc_gemm_kernel<3, false, false>, tc_gemm_kernel<4, false, false>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }

@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "train_common.cuh"
 
 namespace p3d {
 
@@ -64,42 +65,10 @@ static int allreduce(p3d_model* m, void* buf, size_t n, ncclDataType_t dt, cudaS
   return P3D_OK;
 }
 
-// ------------------------------------------------------------------ Philox4x32-10 dropout mask
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0; k.y += W1;
-  }
-  return c;
-}
-// counter = (global_row, col/4, layer, step), key = (seed_lo, seed_hi); word col%4 -> u = w * 2^-32;
-// keep iff floor(keep_prob + u) >= 1   (tf.nn.dropout's  floor(keep_prob + random_uniform))
-__device__ __forceinline__ uint4 dropout_words(uint64_t seed, uint32_t step, uint32_t layer, uint32_t grow, uint32_t c4) {
-  return philox4x32_10(make_uint4(grow, c4, layer, step), make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-}
-__device__ __forceinline__ uint8_t keep_bit(uint32_t w, float keep) {
-  const float u = static_cast<float>(w) * 2.3283064365386963e-10f;
-  return floorf(keep + u) >= 1.f ? 1 : 0;
-}
-
 // ------------------------------------------------------------------ kernels
 constexpr int RCH = 256;   // rows per block in the column-reduction kernels (block = 32 cols x 8 row lanes)
 constexpr int RCH4 = 64;   // rows per block of the float4 column-reduction kernels (block = 32 x 4 cols, 8 row lanes)
 
-// Everything that changes from step to step lives in device memory (written by set_scalars_kernel, whose
-// arguments travel by value), so that the rest of the step is a replayable CUDA graph.
-struct StepScalars {
-  float alpha;        // TF-Adam step size lr_t * sqrt(1-b2^t) / (1-b1^t)
-  float lr_t;         // decayed learning rate
-  float keep, inv_keep;
-  unsigned step;      // global_step: part of the Philox counter
-  unsigned pad;
-  unsigned long long seed;
-};
 __global__ void set_scalars_kernel(StepScalars* dst, const StepScalars v) { *dst = v; }
 
 // per-layer table for the kernels that sweep all weight matrices in one launch (gridDim.y = layer)
@@ -511,7 +480,7 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
     // bf16 operands of the tcgen05 GEMMs, all in their natural row-major layouts
     P3D_CUDA(cudaMalloc(&w.xb, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kIn));
     P3D_CUDA(cudaMalloc(&w.hb, sizeof(__nv_bfloat16) * bl * nh));
-    P3D_CUDA(cudaMalloc(&w.dzb, sizeof(__nv_bfloat16) * bl));
+    P3D_CUDA(cudaMalloc(&w.dzb, sizeof(__nv_bfloat16) * bl * 2));     // two: the fused backward ping-pongs
     P3D_CUDA(cudaMalloc(&w.dyb, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kOutPad));
     P3D_CUDA(cudaMemset(w.dyb, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(B) * kOutPad));   // pad columns stay zero
     if (!w.wb) {
@@ -544,8 +513,123 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
   return P3D_OK;
 }
 
+static bool fused_enabled() {
+  static const bool on = [] { const char* e = getenv("P3D_TRAIN_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static inline dim3 colgrid(int cols, int64_t B) { return dim3((cols + 31) / 32, static_cast<unsigned>((B + RCH - 1) / RCH)); }
 static inline int egrid(long long n) { long long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; return static_cast<int>(g < 1 ? 1 : g); }
+
+// Forward + backward of a small batch (B <= 128, one GPU) with the BatchNorm / ReLU / dropout math fused into the
+// GEMM epilogues (tc_gemm.cu modes 3 and 4): the whole batch is one M tile, so the per-column batch statistics and
+// the column sums of the BN backward are CTA-local.  Per hidden layer: 1 forward launch (was GEMM + finalize +
+// activation) and 2 backward launches (weight gradient; data gradient fused with the previous layer's activation /
+// BN backward - was 4).
+static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, const uint8_t* mask_in, float* y, cudaStream_t st) {
+  using tcg::GemmArgs;
+  TrainWorkspace& w = m->tw;
+  const StepScalars* sc = static_cast<const StepScalars*>(w.sc);
+  const int L = m->L, nlay = static_cast<int>(m->layers.size()), nh = nlay - 1, out = m->out_size;
+  const size_t bl = static_cast<size_t>(B) * L;
+  const bool clip = m->cfg.max_norm != 0, residual = m->cfg.residual != 0;
+  float* scale = w.scal;
+  double* lossacc = w.red + 2ull * nh * L + nlay;
+  const float invB = 1.f / static_cast<float>(B);
+  const int Bi = static_cast<int>(B);
+  // ---------------------------------------------------------------- forward
+  for (int li = 0; li < nh; ++li) {
+    const Layer& ly = m->layers[li];
+    GemmArgs g;
+    g.M = Bi; g.N = L; g.K = ly.K;
+    g.A = li == 0 ? w.xb : w.hb + (li - 1) * bl; g.lda = li == 0 ? kIn : L;
+    g.B = w.wb + ly.off_w; g.ldb = L; g.b_mn = 1;
+    g.C = w.z + li * bl; g.ldc = L; g.bias = m->theta + ly.off_b; g.alpha_dev = clip ? scale + li : nullptr;
+    g.fused_mode = 3;
+    tcg::FusedTrain& f = g.fused;
+    f.sc = sc; f.has_bn = ly.has_bn; f.dropout = dropout; f.layer = li; f.invB = invB;
+    if (ly.has_bn) {
+      f.gamma = m->theta + ly.off_gamma; f.beta = m->theta + ly.off_beta;
+      f.mean = w.mean + static_cast<size_t>(li) * L; f.rstd = w.rstd + static_cast<size_t>(li) * L;
+      f.mov_mean = m->moving + ly.off_mm; f.mov_var = m->moving + ly.off_mv;
+    }
+    f.h = w.h + li * bl; f.hb = w.hb + li * bl; f.mask = w.maskbuf + li * bl; f.mask_in = mask_in ? mask_in + li * bl : nullptr;
+    f.hres = (residual && li >= 2 && (li % 2) == 0) ? w.h + (li - 2) * bl : nullptr;
+    P3D_TRY(tcg::gemm(g, st));
+  }
+  {
+    const Layer& ly = m->layers[nh];
+    GemmArgs g;
+    g.M = Bi; g.N = out; g.K = L;
+    g.A = w.hb + (nh - 1) * bl; g.lda = L;
+    g.B = w.wb + ly.off_w; g.ldb = kOutPad; g.b_mn = 1;
+    g.C = y; g.ldc = out; g.bias = m->theta + ly.off_b; g.alpha_dev = clip ? scale + nh : nullptr;
+    P3D_TRY(tcg::gemm(g, st));
+  }
+  const size_t ny = static_cast<size_t>(B) * out;
+  loss_dy_kernel<<<egrid(static_cast<long long>(ny)), 256, 0, st>>>(y, t, ny, 2.0f * invB / out, w.dy, lossacc, w.dyb, out, kOutPad);
+  P3D_LAUNCH_CHECK();
+  // ---------------------------------------------------------------- backward
+  __nv_bfloat16* dzb[2] = {w.dzb, w.dzb + bl};
+  float* DH[2] = {w.dh, w.dres};
+  int db = 0, keep = -1;
+  // data gradient of layer `li` (li == nh: the output layer) fused with the activation / BN backward of layer t = li - 1
+  auto fused_dgrad = [&](int li, const __nv_bfloat16* A, int lda, int K, int ldb, __nv_bfloat16* dz_out) -> int {
+    const int tl = li - 1;
+    const Layer& lw = m->layers[li];
+    const Layer& lt = m->layers[tl];
+    const bool add = residual && li < nh && (li % 2) == 1 && keep >= 0;      // the gradient that bypassed the block
+    const bool save = residual && tl >= 2 && (tl % 2) == 0;                   // d(h[tl]) also flows to h[tl-2]
+    const int slot = (keep >= 0) ? 1 - keep : 0;
+    GemmArgs g;
+    g.M = Bi; g.N = L; g.K = K;
+    g.A = A; g.lda = lda;
+    g.B = w.wb + lw.off_w; g.ldb = ldb;
+    g.C = w.dz; g.ldc = L; g.alpha_dev = clip ? scale + li : nullptr;
+    if (add) { g.res = DH[keep]; g.ldres = L; }
+    g.fused_mode = 4;
+    tcg::FusedTrain& f = g.fused;
+    f.sc = sc; f.has_bn = lt.has_bn; f.dropout = dropout; f.layer = tl; f.invB = invB;
+    f.z = w.z + tl * bl; f.mask = w.maskbuf + tl * bl; f.dzb = dz_out;
+    f.dh_out = save ? DH[slot] : nullptr;
+    if (lt.has_bn) {
+      f.gamma = m->theta + lt.off_gamma; f.beta = m->theta + lt.off_beta;
+      f.mean = w.mean + static_cast<size_t>(tl) * L; f.rstd = w.rstd + static_cast<size_t>(tl) * L;
+      f.ggamma = m->grad + lt.off_gamma; f.gbeta = m->grad + lt.off_beta;
+    } else {
+      f.gbias = m->grad + lt.off_b;
+    }
+    P3D_TRY(tcg::gemm(g, st));
+    if (add) keep = -1;
+    if (save) keep = slot;
+    return P3D_OK;
+  };
+  {
+    const Layer& ly = m->layers[nh];
+    GemmArgs gw;   // dW4 = h^T dy
+    gw.M = L; gw.N = out; gw.K = Bi;
+    gw.A = w.hb + (nh - 1) * bl; gw.lda = L; gw.a_mn = 1;
+    gw.B = w.dyb; gw.ldb = kOutPad; gw.b_mn = 1;
+    gw.C = m->grad + ly.off_w; gw.ldc = out; gw.split_k = 1;
+    P3D_TRY(tcg::gemm(gw, st));
+    colsum_kernel<<<colgrid(out, B), dim3(32, 8), 0, st>>>(w.dy, B, out, m->grad + ly.off_b);
+    P3D_LAUNCH_CHECK();
+    P3D_TRY(fused_dgrad(nh, w.dyb, kOutPad, out, kOutPad, dzb[db]));
+  }
+  for (int li = nh - 1; li >= 0; --li) {
+    const Layer& ly = m->layers[li];
+    GemmArgs gw;   // dW = in^T dz
+    gw.M = ly.K; gw.N = L; gw.K = Bi;
+    gw.A = li == 0 ? w.xb : w.hb + (li - 1) * bl; gw.lda = li == 0 ? kIn : L; gw.a_mn = 1;
+    gw.B = dzb[db]; gw.ldb = L; gw.b_mn = 1;
+    gw.C = m->grad + ly.off_w; gw.ldc = L; gw.split_k = 1;
+    P3D_TRY(tcg::gemm(gw, st));
+    if (li > 0) {
+      P3D_TRY(fused_dgrad(li, dzb[db], L, L, L, dzb[1 - db]));
+      db ^= 1;
+    }
+  }
+  return P3D_OK;
+}
 
 // The step proper: every launch below depends only on (model, B, Bg, row0, dropout on/off, pointers) - all per-step
 // values come from the device StepScalars - so the sequence can be captured once and replayed as a CUDA graph.
@@ -585,6 +669,10 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     to_bf16_kernel<<<egrid(static_cast<long long>(B) * kIn / 4 + 1), 256, 0, st>>>(x, w.xb, B, kIn, kIn);
     P3D_LAUNCH_CHECK();
   }
+  const bool fused = tc && m->world == 1 && B <= 128 && (L % 32) == 0 && fused_enabled();
+  if (fused) {
+    P3D_TRY(fwd_bwd_fused(m, t, B, dropout, mask_in, y, st));
+  } else {
   // ---------------------------------------------------------------- forward
   for (int li = 0; li < nh; ++li) {
     const Layer& ly = m->layers[li];
@@ -732,6 +820,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       cur = nxt;
     }
   }
+  }   // unfused path
   // ---------------------------------------------------------------- gradient exchange + update
   P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
   if (clip) {

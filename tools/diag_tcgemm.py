@@ -94,6 +94,9 @@ if __name__ == "__main__":
         dict(M=4096, N=1024, K=1024, a_mn=0, b_mn=0, res=True, time_it=True),
         dict(M=1024, N=1024, K=4096, a_mn=1, b_mn=1, split_k=1, time_it=True),
         dict(M=4096, N=48, K=1024, a_mn=0, b_mn=1, bias=True, time_it=True),
+        dict(M=2, N=1024, K=1024, a_mn=0, b_mn=0, bias=True),                              # inference layers: BN=32, 8-row A box
+        dict(M=61, N=1024, K=1024, a_mn=0, b_mn=0, bias=True, res=True),
+        dict(M=100, N=1024, K=64, a_mn=0, b_mn=0, bias=True),
         dict(M=1000, N=1024, K=1024, a_mn=0, b_mn=1, bias=True, colsum=True),              # ragged M
         dict(M=1024, N=1024, K=1000, a_mn=1, b_mn=1, split_k=1),                           # ragged K (batch)
     ]
