@@ -105,6 +105,9 @@ struct TrainWorkspace {
   struct GraphEntry { int64_t B; int dropout; int launches; void* exec; };
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
+  // the weight-gradient GEMMs of the fused small-batch step run on a side stream (a parallel branch of the graph)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev[16] = {};
 };
 
 // Optional per-launch CUDA-event timing of the dominant kernel (bench.py's roofline figure):

@@ -303,6 +303,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               *reinterpret_cast<float4*>(p.ft.mov_var + n) = mv;
             }
           }
+          float4 hr[8];
+          uchar4 mi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const size_t off = static_cast<size_t>(m < p.M ? m : 0) * p.N + n;
+            hr[i] = p.ft.hres ? __ldg(reinterpret_cast<const float4*>(p.ft.hres + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mi[i] = (dropout && p.ft.mask_in) ? *reinterpret_cast<const uchar4*>(p.ft.mask_in + off) : make_uchar4(1, 1, 1, 1);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
@@ -316,11 +325,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               r[j] = fmaxf(a, 0.f);
             }
             if (dropout) {
-              uint8_t kb[4];
-              if (p.ft.mask_in) {
-                const uchar4 mi = *reinterpret_cast<const uchar4*>(p.ft.mask_in + off);
-                kb[0] = mi.x; kb[1] = mi.y; kb[2] = mi.z; kb[3] = mi.w;
-              } else {
+              uint8_t kb[4] = {mi[i].x, mi[i].y, mi[i].z, mi[i].w};
+              if (!p.ft.mask_in) {
                 const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer), static_cast<uint32_t>(m), static_cast<uint32_t>(n >> 2));
                 kb[0] = train::keep_bit(w4.x, keep); kb[1] = train::keep_bit(w4.y, keep); kb[2] = train::keep_bit(w4.z, keep); kb[3] = train::keep_bit(w4.w, keep);
               }
@@ -328,10 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               for (int j = 0; j < 4; ++j) r[j] = kb[j] ? r[j] * inv_keep : 0.f;
               *reinterpret_cast<uchar4*>(p.ft.mask + off) = make_uchar4(kb[0], kb[1], kb[2], kb[3]);
             }
-            if (p.ft.hres) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(p.ft.hres + off));
-              r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
-            }
+            r[0] += hr[i].x; r[1] += hr[i].y; r[2] += hr[i].z; r[3] += hr[i].w;
             *reinterpret_cast<float4*>(p.ft.h + off) = make_float4(r[0], r[1], r[2], r[3]);
             __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -343,18 +346,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         auto da_of = [&](int c0, float (&o)[8][4], float (&xh)[8][4], const float (&mu)[4], const float (&rs)[4], const float (&ga)[4],
                          const float (&be)[4], bool store_dh) {
           const int n = n0 + c0 + cq;
+          // all global operands of the 8 rows first (independent loads in flight), then the arithmetic
+          float4 z4[8], r4[8];
+          uchar4 mk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const size_t off = static_cast<size_t>(m < p.M ? m : 0) * p.N + n;
+            z4[i] = __ldg(reinterpret_cast<const float4*>(p.ft.z + off));
+            mk[i] = dropout ? *reinterpret_cast<const uchar4*>(p.ft.mask + off) : make_uchar4(1, 1, 1, 1);
+            r4[i] = p.res ? __ldg(reinterpret_cast<const float4*>(p.res + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
             const bool live = m < p.M;
-            const size_t off = static_cast<size_t>(live ? m : 0) * p.N + n;
-            if (p.res) { const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + off)); o[i][0] += q.x; o[i][1] += q.y; o[i][2] += q.z; o[i][3] += q.w; }
-            if (store_dh && p.ft.dh_out && live) *reinterpret_cast<float4*>(p.ft.dh_out + off) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-            const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.ft.z + off));
-            uchar4 mk = make_uchar4(1, 1, 1, 1);
-            if (dropout) mk = *reinterpret_cast<const uchar4*>(p.ft.mask + off);
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-            const unsigned char kk[4] = {mk.x, mk.y, mk.z, mk.w};
+            o[i][0] += r4[i].x; o[i][1] += r4[i].y; o[i][2] += r4[i].z; o[i][3] += r4[i].w;
+            if (store_dh && p.ft.dh_out && live)
+              *reinterpret_cast<float4*>(p.ft.dh_out + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            const float zz[4] = {z4[i].x, z4[i].y, z4[i].z, z4[i].w};
+            const unsigned char kk[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               xh[i][j] = has_bn ? (zz[j] - mu[j]) * rs[j] : 0.f;

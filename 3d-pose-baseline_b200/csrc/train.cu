@@ -444,6 +444,8 @@ void free_workspace(p3d_model* m) {
   cudaFree(w.tab); cudaFree(w.sc); cudaFree(w.gx); cudaFree(w.gt); cudaFree(w.gy); cudaFree(w.gscal);
   for (auto& ge : w.graphs) if (ge.exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(ge.exec));
   if (w.cap_stream) cudaStreamDestroy(w.cap_stream);
+  if (w.side_stream) cudaStreamDestroy(w.side_stream);
+  for (auto& e : w.ev) if (e) cudaEventDestroy(e);
   w = TrainWorkspace();
   if (m->nccl_comm && nccl()) { nccl()->CommDestroy(static_cast<ncclComm_t>(m->nccl_comm)); m->nccl_comm = nullptr; }
 }
@@ -499,6 +501,8 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
     P3D_CUDA(cudaMalloc(&w.rstd, sizeof(float) * static_cast<size_t>(nh) * L));
     P3D_CUDA(cudaMalloc(&w.scal, sizeof(float) * (nl + 8)));
     P3D_CUDA(cudaMalloc(&w.gscal, sizeof(float) * 2));
+    P3D_CUDA(cudaStreamCreateWithFlags(&w.side_stream, cudaStreamNonBlocking));
+    for (auto& e : w.ev) P3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     P3D_CUDA(cudaMalloc(&w.sc, sizeof(StepScalars)));
     std::vector<LayerTabEntry> tab(nl);
     for (int l = 0; l < nl; ++l) {
@@ -603,6 +607,21 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
     if (save) keep = slot;
     return P3D_OK;
   };
+  // The weight gradients only feed the optimizer: they run on a side stream (a parallel branch of the captured graph),
+  // off the critical path  loss -> dgrad chain -> Adam.  Events: e_dz[k] = "dz of step k is ready", e_wg[k] = "its
+  // weight gradient has read it" (the dz ping-pong buffer may then be overwritten).
+  cudaStream_t side = w.side_stream;
+  int ne = 0;
+  auto fork_wgrad = [&](const GemmArgs& gw, cudaEvent_t* done) -> int {
+    cudaEvent_t ready = w.ev[ne++ % 16];
+    P3D_CUDA(cudaEventRecord(ready, st));
+    P3D_CUDA(cudaStreamWaitEvent(side, ready, 0));
+    P3D_TRY(tcg::gemm(gw, side));
+    *done = w.ev[ne++ % 16];
+    P3D_CUDA(cudaEventRecord(*done, side));
+    return P3D_OK;
+  };
+  cudaEvent_t wg_done[2] = {nullptr, nullptr};   // per dz ping-pong buffer: the weight gradient that last read it
   {
     const Layer& ly = m->layers[nh];
     GemmArgs gw;   // dW4 = h^T dy
@@ -610,7 +629,8 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
     gw.A = w.hb + (nh - 1) * bl; gw.lda = L; gw.a_mn = 1;
     gw.B = w.dyb; gw.ldb = kOutPad; gw.b_mn = 1;
     gw.C = m->grad + ly.off_w; gw.ldc = out; gw.split_k = 1;
-    P3D_TRY(tcg::gemm(gw, st));
+    cudaEvent_t e4;
+    P3D_TRY(fork_wgrad(gw, &e4));
     colsum_kernel<<<colgrid(out, B), dim3(32, 8), 0, st>>>(w.dy, B, out, m->grad + ly.off_b);
     P3D_LAUNCH_CHECK();
     P3D_TRY(fused_dgrad(nh, w.dyb, kOutPad, out, kOutPad, dzb[db]));
@@ -622,11 +642,17 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
     gw.A = li == 0 ? w.xb : w.hb + (li - 1) * bl; gw.lda = li == 0 ? kIn : L; gw.a_mn = 1;
     gw.B = dzb[db]; gw.ldb = L; gw.b_mn = 1;
     gw.C = m->grad + ly.off_w; gw.ldc = L; gw.split_k = 1;
-    P3D_TRY(tcg::gemm(gw, st));
+    P3D_TRY(fork_wgrad(gw, &wg_done[db]));
     if (li > 0) {
+      if (wg_done[1 - db]) P3D_CUDA(cudaStreamWaitEvent(st, wg_done[1 - db], 0));   // the buffer about to be overwritten is free
       P3D_TRY(fused_dgrad(li, dzb[db], L, L, L, dzb[1 - db]));
       db ^= 1;
     }
+  }
+  {   // join: the optimizer needs every weight gradient
+    cudaEvent_t joined = w.ev[ne++ % 16];
+    P3D_CUDA(cudaEventRecord(joined, side));
+    P3D_CUDA(cudaStreamWaitEvent(st, joined, 0));
   }
   return P3D_OK;
 }
