@@ -50,6 +50,33 @@ l2, _, _, _ = model.step(None, x, t, keep, isTraining=True)
 lt = torch.tensor([float(l2)], device="cuda"); l0 = lt.clone(); dist.broadcast(l0, 0)
 ok &= bool(torch.equal(lt, l0))
 
+# the tensor-core (bf16) step under data parallelism: SyncBN sums come out of the GEMM epilogues, are all-reduced, and
+# the step must reproduce the single-device oracle restated with the same rounding points
+from helpers import bf16_round  # noqa: E402
+qf = lambda a: bf16_round(a).astype(np.float64)  # noqa: E731
+pb = {k: v.astype(np.float32) for k, v in M.init_params(256, 2, seed=6, bn="trained").items()}
+mb = LinearModel(256, 2, True, True, True, 64, 1e-3, mode="bf16", device=local, seed=7, dist=dist)
+mb.set_variables(pb)
+pb64 = {k: v.astype(np.float64) for k, v in pb.items()}
+xb_, tb_ = synth.mlp_inputs(B, seed=31)
+mk = (rng.uniform(size=(nh, B, 256)) < keep).astype(np.uint8)
+lb, _, _, yb = mb.step(None, xb_, tb_, keep, isTraining=True, dropout_mask=mk)
+yq, cq_ = M.forward(pb64, xb_.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(mk), want_cache=True, quant=qf)
+gq = M.backward(pb64, xb_.astype(np.float64), tb_.astype(np.float64), cfg, cq_, yq, quant=qf)
+ok_b = abs(float(lb) - M.loss_fn(yq, tb_.astype(np.float64))) <= 1e-4 * max(1.0, float(lb))
+ok_b &= np.abs(yb - yq).max() <= 3e-3 * max(np.abs(yq).max(), 1.0)
+gb = mb.get_gradients()
+for name, gref in gq.items():
+    if np.abs(gref).max() > 1e-12:
+        ok_b &= np.linalg.norm(gb[name] - gref) <= 5e-2 * np.linalg.norm(gref)
+wb_ = torch.from_numpy(mb.get_variables()["linear_model/w1"]).cuda()
+wb0 = wb_.clone(); dist.broadcast(wb0, 0)
+ok_b &= bool(torch.equal(wb_, wb0))
+if not ok_b and rank == 0:
+    print("bf16 data-parallel step FAILED", float(lb), M.loss_fn(yq, tb_.astype(np.float64)))
+ok &= bool(ok_b)
+mb.close()
+
 # sharded evaluation
 N = 10007
 gt96, pr96 = synth.eval_pairs(N, seed=4)
