@@ -28,15 +28,16 @@ using namespace ptx;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 16;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box = 8 KB
 constexpr int NTHREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int EPI_THREADS = 256;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
+constexpr int BAR_BYTES = 512;               // full[16] | empty[16] | accf | tmem slot
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
-__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }   // BN = 32 also 8 (barrier slots)
+
 
 struct Params {
   int M, N, K;
@@ -54,6 +55,7 @@ struct Params {
   __nv_bfloat16* out_b; int ldob;
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
+  int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
   unsigned long long* dbg;  // optional [ctas][8] globaltimer stamps (diagnostics)
@@ -97,15 +99,17 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int STAGES = stages_for(p.bn);
+  // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
+  const int STAGES = p.stages;
   const int B_BYTES = p.bn * BK * 2;
+  const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sB = smem + STAGES * A_SLOT;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* accf = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
-  float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + 256);
+  float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES);
   float* scol = sbias + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,7 +139,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const uint32_t bytes = p.a_bytes + B_BYTES;
     auto load_a = [&](int stage, int k0) {
-      uint8_t* a = sA + stage * A_BYTES;
+      uint8_t* a = sA + stage * A_SLOT;
       if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
       else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
     };
@@ -176,7 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (kb == 0) P3D_STAMP(3);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t aa = a_base + stage * A_BYTES, bb = b_base + stage * B_BYTES;
+        const uint32_t aa = a_base + stage * A_SLOT, bb = b_base + stage * B_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
@@ -662,6 +666,8 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
   p.a_bytes = a_rows * BK * 2;
+  p.stages = RING_BYTES / (p.a_bytes + bn * BK * 2);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
   d->pdl = g.pdl;
