@@ -55,6 +55,7 @@ struct Params {
   __nv_bfloat16* out_b; int ldob;
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
+  int cn;                   // cluster size along N (1, 2, 4): the CTAs of one M tile share A - each fetches 1/cn of its rows and multicasts
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
@@ -113,6 +114,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   float* scol = sbias + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = p.cn > 1 ? cluster_ctarank() : 0u;
   if (warp == 0) P3D_STAMP(0);
   const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
   const int kbeg = blockIdx.z * p.k_per_split;
@@ -121,13 +123,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // a ring slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.cn); }
     mbar_init(accf, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
   tc_fence_before();
-  __syncthreads();
+  if (p.cn > 1) cluster_sync(); else __syncthreads();     // peers must see initialised barriers before the first multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_launch_dependents();     // the next kernel of a programmatic-dependent chain may start its prologue now
@@ -140,7 +143,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint32_t bytes = p.a_bytes + B_BYTES;
     auto load_a = [&](int stage, int k0) {
       uint8_t* a = sA + stage * A_SLOT;
-      if (!p.a_mn) tma_load_2d(a, &tm_a, &full[stage], k0, m0);
+      if (!p.a_mn) {
+        if (p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
+          const int part = p.a_bytes / p.cn, rows = part / (BK * 2);
+          tma_load_2d_mcast(a + crank * part, &tm_a, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>((1u << p.cn) - 1u));
+        } else {
+          tma_load_2d(a, &tm_a, &full[stage], k0, m0);
+        }
+      }
       else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
     };
     auto load_b = [&](int stage, int k0) {
@@ -187,7 +197,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint64_t bd = p.b_mn ? desc_mn(bb + k * b_step) : desc_k(bb + k * b_step);
           umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);
+        if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
+        else umma_commit(&empty[stage]);
         if (kb == nk - 1) umma_commit(accf);
       }
       __syncwarp();
@@ -581,7 +592,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   if (warp == 2) P3D_STAMP(6);
   tc_fence_before();
-  __syncthreads();
+  if (p.cn > 1) cluster_sync(); else __syncthreads();     // no CTA may leave while a peer can still arrive on its barriers
   if (warp == 0) P3D_STAMP(7);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
 }
@@ -653,8 +664,16 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   PlanData* d = reinterpret_cast<PlanData*>(out->blob);
   // K-major A of a short problem: fetch only the rows that exist (the MMA still reads 128 smem rows; what it makes
   // of the stale ones lands in accumulator rows >= M, which are never stored)
-  const int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
-  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows));
+  // The CTAs of one M tile (adjacent N tiles) read the same A tile: in a cluster of cn of them each fetches 1/cn of
+  // the rows and TMA-multicasts it to all.  Measured on B200 (M=64, N=K=1024): the mainloop got SLOWER (5.7 -> 6.2 us)
+  // although every CTA fetches half the bytes - a k-block costs ~0.2 us + 0.5 ns per 128-byte row whatever its size,
+  // so bytes are not what bounds a short-M GEMM.  Kept behind P3D_GEMM_MCAST=1 for the large-M experiments of round 2.
+  int cn = 1;
+  static const bool mcast = [] { const char* e = getenv("P3D_GEMM_MCAST"); return e && e[0] == '1'; }();
+  if (!g.a_mn && mcast) cn = (nt % 4 == 0) ? 4 : ((nt % 2 == 0) ? 2 : 1);
+  int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
+  if (cn > 1) a_rows = (a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn);     // every share is whole 8-row swizzle groups
+  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows / cn));
   else P3D_TRY(make_map(&d->ta, g.A, g.M, g.K, g.lda, BK));
   if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn));
   else P3D_TRY(make_map(&d->tb, g.B, g.N, g.K, g.ldb, BK));
@@ -665,6 +684,7 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.colsum = g.colsum;
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
+  p.cn = cn;
   p.a_bytes = a_rows * BK * 2;
   p.stages = RING_BYTES / (p.a_bytes + bn * BK * 2);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -713,13 +733,18 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
+  if (d->p.cn > 1) {
+    attrs[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cn; attrs[cfg.numAttrs].val.clusterDim.y = 1; attrs[cfg.numAttrs].val.clusterDim.z = 1;
+    cfg.attrs = attrs; ++cfg.numAttrs;
+  }
   if (d->pdl) {
     // programmatic dependent launch: this kernel may start while its predecessor in the stream drains; it orders
     // itself behind the predecessor's memory with griddepcontrol.wait
-    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attrs; cfg.numAttrs = 1;
+    attrs[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs; ++cfg.numAttrs;
   }
   P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->p));
   P3D_LAUNCH_CHECK();
