@@ -28,6 +28,7 @@ namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cud
                  int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency_cluster(p3d_model*, const float*, float*, cudaStream_t); }
+namespace tcg { int mma_rate(int, int, long long*, cudaStream_t); }
 namespace layered { int forward(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t); }
 namespace train { void free_workspace(p3d_model*); }
 
@@ -446,6 +447,11 @@ int p3d_debug_tc_gemm(const void* A, int lda, int a_mn, const void* B, int ldb, 
   g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.a_mn = a_mn; g.B = B; g.ldb = ldb; g.b_mn = b_mn; g.C = C; g.ldc = ldc;
   g.bias = bias; g.res = res; g.ldres = ldc; g.alpha = alpha; g.split_k = split_k; g.colsum = colsum;
   return tcg::gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int p3d_debug_mma_rate(int N, int iters, int64_t* out_dev, void* stream) {
+  P3D_REQUIRE(out_dev, "debug_mma_rate: null argument");
+  return tcg::mma_rate(N, iters, reinterpret_cast<long long*>(out_dev), static_cast<cudaStream_t>(stream));
 }
 
 int p3d_debug_umma_gemm(const void* A, const void* W, float* C, int N, int K, void* stream) {

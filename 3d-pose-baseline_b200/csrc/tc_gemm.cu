@@ -597,6 +597,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
 }
 
+// ----------------------------------------------------------------------------- MMA issue-rate probe
+// One CTA, operands resident in shared memory (zeros), `iters` back-to-back tcgen05.mma 128 x N x 16 into one
+// accumulator, timed with clock64 from the first issue to the completion of the commit: cycles per MMA as a function
+// of N (what a k-block of four MMAs costs when nothing else is in the way).
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  if (threadIdx.x < 32) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16_f32(128, N);
+    const uint64_t ad = desc_k(smem_u32(smem)), bd = desc_k(smem_u32(smem + 16 * 1024));
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) umma_bf16_ss(tmem, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, i ? 1u : 0u);
+    umma_commit(bar);
+    const long long t1 = clock64();
+    mbar_wait(bar, 0, 9);
+    const long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+int mma_rate(int N, int iters, long long* out_dev, cudaStream_t st) {
+  P3D_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 1, "mma_rate: bad argument");
+  const int smem = 1024 + 48 * 1024 + 64;
+  P3D_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<<<1, 128, smem, st>>>(N, iters, out_dev);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

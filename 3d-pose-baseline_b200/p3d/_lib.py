@@ -88,6 +88,7 @@ PROTOTYPES = {
                                       c_void_p, c_void_p, c_void_p]),
     "p3d_debug_tc_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "p3d_debug_mma_rate": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "p3d_debug_umma_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 

@@ -194,6 +194,20 @@ def secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr):
                       "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 4)})
     out["inference_batch_sweep"] = sweep
 
+    # BASELINE configs[4]: width-scaled stress variant, linear_size=4096, num_layers=4 (269 MB of bf16 weights > L2);
+    # per-GPU share of the 8-GPU run = 2^21 poses, timed here on 2^18
+    ms_model = LinearModel(4096, 4, True, True, True, 64, 1e-3, seed=3, mode="bf16")
+    Bs = 1 << 18
+    xs = torch.randn((Bs, IN), device=dev, generator=g); ys = torch.empty((Bs, OUT), device=dev)
+    ms = timed(lambda: lib.p3d_model_forward(ms_model._handle, xs.data_ptr(), ys.data_ptr(), Bs, sptr), 3, warm=2)
+    flop = 2 * (IN * 4096 + 2 * 4 * 4096 * 4096 + 4096 * OUT)
+    out["stress_width4096"] = {"config": "linear_size=4096, num_layers=4, residual, batch_norm, max_norm; batch 2^18 on one GPU",
+                               "ms": round(ms, 3), "poses_per_s": round(Bs / (ms * 1e-3)),
+                               "tflops": round(Bs * flop / (ms * 1e-3) / 1e12, 1),
+                               "frac_of_bf16_peak": round(Bs * flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], 4)}
+    ms_model.close()
+    del xs, ys
+
     train = []
     for Bt, mode in ((64, "bf16"), (4096, "bf16"), (64, "fp32"), (4096, "fp32")):
         mt = LinearModel(L, NL, True, True, True, Bt, 1e-3, seed=1, mode=mode)

@@ -194,6 +194,9 @@ int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n);
  * zeroed); colsum (optional, [2][N] doubles, +=) receives the column sums of C and C^2. */
 int p3d_debug_tc_gemm(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
                       const float* bias, const float* res, float alpha, int split_k, double* colsum, void* stream);
+/* Diagnostics: cycles of `iters` back-to-back tcgen05.mma 128 x N x 16 on resident shared-memory operands (one CTA).
+ * out_dev[0] = cycles to issue, out_dev[1] = cycles until the commit completes. */
+int p3d_debug_mma_rate(int N, int iters, int64_t* out_dev, void* stream);
 int p3d_debug_umma_gemm(const void* A_bf16, const void* W_bf16, float* C, int N, int K, void* stream);
 
 #ifdef __cplusplus

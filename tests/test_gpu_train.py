@@ -277,3 +277,29 @@ def test_train_epoch_equals_stepping_through_the_batches(mode):
     lt, _ = ma.train_epoch(torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda(), 1.0, shuffle=False)
     assert lt.is_cuda and lt.shape == (n // B,) and torch.isfinite(lt).all()
     ma.close(); mb.close()
+
+
+@pytest.mark.parametrize("mode,B", [("bf16", 64), ("bf16", 200), ("fp32", 64)])
+def test_predict_14_training_step(mode, B):
+    """predict_14 (output width 42, linear_model.py:69): the output layer's bf16 operands are padded to a 48-wide
+    pitch for TMA; loss, outputs and the w4/b4 gradients must still match the oracle (fused route at B=64, unfused at 200)."""
+    from helpers import bf16_round
+    cfg = M.Config(256, 1, True, True, True, out_size=42)
+    m, p = make_model(cfg, seed=17, bn="trained", mode=mode, predict_14=True)
+    x, _ = synth.mlp_inputs(B, seed=5)
+    t = np.random.RandomState(1).standard_normal((B, 42)).astype(np.float32)
+    masks = (np.random.RandomState(2).uniform(size=(3, B, 256)) < 0.8).astype(np.uint8)
+    loss, _, _, y = m.step(None, x, t, 0.8, isTraining=True, dropout_mask=masks)
+    got = m.get_gradients()
+    m.close()
+    q = (lambda a: bf16_round(a).astype(np.float64)) if mode == "bf16" else None
+    x64, t64 = x.astype(np.float64), t.astype(np.float64)
+    yr, cache = M.forward(p, x64, cfg, training=True, keep_prob=0.8, masks=list(masks), want_cache=True, quant=q)
+    gr = M.backward(p, x64, t64, cfg, cache, yr, quant=q)
+    tol_y, tol_g = (3e-3, 5e-2) if mode == "bf16" else (2e-4, 1e-3)
+    assert y.shape == (B, 42)
+    assert abs(float(loss) - M.loss_fn(yr, t64)) <= 1e-3 * max(1.0, float(loss))
+    assert np.abs(y - yr).max() <= tol_y * max(np.abs(yr).max(), 1.0)
+    for name in ("linear_model/w4", "linear_model/b4", "linear_model/w1", "linear_model/two_linear_0/w3_0"):
+        d = got[name].astype(np.float64) - gr[name]
+        assert np.linalg.norm(d) <= tol_g * np.linalg.norm(gr[name]), (name, np.linalg.norm(d) / np.linalg.norm(gr[name]))
