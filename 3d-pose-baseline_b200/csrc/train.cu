@@ -218,7 +218,7 @@ __global__ void fwd_act_kernel(const ActArgs a) {
       const float4 rr = *reinterpret_cast<const float4*>(a.res + r * a.L + c);
       v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
     }
-    *reinterpret_cast<float4*>(a.h + r * a.L + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.h) *reinterpret_cast<float4*>(a.h + r * a.L + c) = make_float4(v[0], v[1], v[2], v[3]);
     if (a.hb) {      // operand of the next layer's tcgen05 GEMMs (forward and weight gradient)
       __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
       uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) bwd_act_kernel(const BwdArgs a) {
         da[j] = act > 0.f ? gr : 0.f;
         p[j] += da[j]; q[j] += static_cast<double>(da[j]) * xh;
       }
-      *reinterpret_cast<float4*>(a.dz + o) = make_float4(da[0], da[1], da[2], da[3]);
+      if (a.dz) *reinterpret_cast<float4*>(a.dz + o) = make_float4(da[0], da[1], da[2], da[3]);
       if (a.dzb) {       // final dz only when the layer has no BN
         __nv_bfloat162 lo = __floats2bfloat162_rn(da[0], da[1]), hi = __floats2bfloat162_rn(da[2], da[3]);
         uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -331,26 +331,46 @@ __global__ void __launch_bounds__(256) bwd_act_kernel(const BwdArgs a) {
 __global__ void bwd_bn_kernel(float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ mean,
                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                               const double* __restrict__ sums, float invB, long long B, int L, __nv_bfloat16* __restrict__ dzb,
-                              int write_f32, double pg_scale, float* __restrict__ ggamma, float* __restrict__ gbeta) {
+                              int write_f32, double pg_scale, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                              const float* __restrict__ dh, const uint8_t* __restrict__ mask, const float* __restrict__ beta,
+                              const StepScalars* __restrict__ sc) {
+  // dh != null: da is recomputed from (dh, z, mask) instead of being read back - pass A then never stores it
   const int L4 = L / 4;
   const long long total = B * L4;
+  const float inv_keep = sc->inv_keep;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / L4;
     const int c = static_cast<int>(i - r * L4) * 4;
     const size_t o = static_cast<size_t>(r) * L + c;
     const float4 z4 = *reinterpret_cast<const float4*>(z + o);
-    const float4 d4 = *reinterpret_cast<const float4*>(dz + o);
+    const float4 d4 = *reinterpret_cast<const float4*>((dh ? dh : dz) + o);
     const float4 m4 = *reinterpret_cast<const float4*>(mean + c), r4 = *reinterpret_cast<const float4*>(rstd + c);
     const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
-    const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    float dd[4] = {d4.x, d4.y, d4.z, d4.w};
     const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float xh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xh[j] = (zz[j] - mu[j]) * rs[j];
+    if (dh) {
+      const float4 b4 = *reinterpret_cast<const float4*>(beta + c);
+      const float be[4] = {b4.x, b4.y, b4.z, b4.w};
+      uchar4 mk = make_uchar4(1, 1, 1, 1);
+      if (mask) mk = *reinterpret_cast<const uchar4*>(mask + o);
+      const unsigned char kk[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gr = dd[j];
+        if (mask) gr = kk[j] ? gr * inv_keep : 0.f;
+        dd[j] = (gg[j] * xh[j] + be[j] > 0.f) ? gr : 0.f;
+      }
+    }
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float xh = (zz[j] - mu[j]) * rs[j];
       const float m1 = static_cast<float>(sums[c + j]) * invB, m2 = static_cast<float>(sums[L + c + j]) * invB;
-      v[j] = gg[j] * rs[j] * (dd[j] - m1 - xh * m2);
+      v[j] = gg[j] * rs[j] * (dd[j] - m1 - xh[j] * m2);
     }
     if (write_f32) *reinterpret_cast<float4*>(dz + o) = make_float4(v[0], v[1], v[2], v[3]);
     if (dzb) {
@@ -733,7 +753,9 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     a.z = z; a.mean = mean; a.rstd = rstd;
     a.gamma = ly.has_bn ? m->theta + ly.off_gamma : nullptr; a.beta = ly.has_bn ? m->theta + ly.off_beta : nullptr;
     a.res = (residual && li >= 2 && (li % 2) == 0) ? w.h + (li - 2) * bl : nullptr;
-    a.h = w.h + li * bl; a.hb = tc ? w.hb + li * bl : nullptr; a.mask = maskbuf + li * bl; a.mask_in = mask_in ? mask_in + li * bl : nullptr;
+    // on the tensor-core path the fp32 copy of h is only read back as a residual (by layer li + 2)
+    const bool h_needed = !tc || (residual && (li % 2) == 0 && li + 2 < nh);
+    a.h = h_needed ? w.h + li * bl : nullptr; a.hb = tc ? w.hb + li * bl : nullptr; a.mask = maskbuf + li * bl; a.mask_in = mask_in ? mask_in + li * bl : nullptr;
     a.sc = sc; a.layer = li;
     a.row0 = row0; a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
     fwd_act_kernel<<<egrid(static_cast<long long>(bl / 4)), 256, 0, st>>>(a);
@@ -794,7 +816,8 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     BwdArgs a;
     a.dh = G[cur]; a.z = w.z + li * bl; a.mean = w.mean + static_cast<size_t>(li) * L; a.rstd = w.rstd + static_cast<size_t>(li) * L;
     a.gamma = ly.has_bn ? m->theta + ly.off_gamma : nullptr; a.beta = ly.has_bn ? m->theta + ly.off_beta : nullptr;
-    a.mask = maskbuf + li * bl; a.dz = w.dz; a.dzb = (tc && !ly.has_bn) ? w.dzb : nullptr; a.sums = w.red + 2ull * li * L; a.sc = sc;
+    a.mask = maskbuf + li * bl; a.dz = (tc && ly.has_bn) ? nullptr : w.dz;   // tensor-core + BN: pass B recomputes da
+    a.dzb = (tc && !ly.has_bn) ? w.dzb : nullptr; a.sums = w.red + 2ull * li * L; a.sc = sc;
     a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
     bwd_act_kernel<<<dim3((L / 4 + 31) / 32, static_cast<unsigned>((B + RCH4 - 1) / RCH4)), dim3(32, 8), 0, st>>>(a);
     P3D_LAUNCH_CHECK();
@@ -805,7 +828,8 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       // restores them exactly once.
       bwd_bn_kernel<<<egrid(static_cast<long long>(bl / 4)), 256, 0, st>>>(w.dz, a.z, a.mean, a.rstd, a.gamma, a.sums, static_cast<float>(invBg), B, L,
                                                                            tc ? w.dzb : nullptr, tc ? 0 : 1, 1.0 / m->world,
-                                                                           m->grad + ly.off_gamma, m->grad + ly.off_beta);
+                                                                           m->grad + ly.off_gamma, m->grad + ly.off_beta,
+                                                                           tc ? a.dh : nullptr, dropout ? a.mask : nullptr, a.beta, sc);
       P3D_LAUNCH_CHECK();
       // the bias feeding a BN layer has an exactly-zero gradient (it is removed by the mean subtraction)
     } else {
