@@ -59,11 +59,11 @@ struct Params {
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
-  unsigned long long* dbg;  // optional [ctas][8] globaltimer stamps (diagnostics)
+  unsigned long long* dbg;  // optional [ctas][16] globaltimer stamps (diagnostics)
   FusedTrain ft;            // OUT = 3 / 4 only
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
+#define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -141,29 +141,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const uint32_t bytes = p.a_bytes + B_BYTES;
-    auto load_a = [&](int stage, int k0) {
-      uint8_t* a = sA + stage * A_SLOT;
-      if (!p.a_mn) {
-        if (p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
+    // Every TMA operation of a stage belongs to its own lane and all of them leave in ONE instruction: issuing them
+    // one after the other from a single thread costs ~0.12 us each, which is what bounded short-M GEMMs (16 serial
+    // k-blocks x 2 operations = 4.3 us of a 7.6 us kernel).  Lanes [0, na) fetch A boxes, lanes [na, na + nb) B boxes.
+    const int na = p.a_mn ? 2 : 1, nb = p.b_mn ? p.bn / 64 : 1;
+    const bool is_a = lane < na, is_b = lane >= na && lane < na + nb;
+    const int bi = lane - na;                                         // B box index of this lane
+    const CUtensorMap* my_map = is_a ? &tm_a : &tm_b;
+    const bool my_mn = is_a ? (p.a_mn != 0) : (p.b_mn != 0);
+    const int my_box = is_a ? lane : bi;
+    const int my_row0 = is_a ? m0 : n0;
+    const uint32_t a_mask = static_cast<uint16_t>((1u << p.cn) - 1u);
+    auto issue = [&](int stage, int k0, bool with_a, bool with_b) {
+      if ((is_a && with_a) || (is_b && with_b)) {
+        uint8_t* dst = (is_a ? sA + stage * A_SLOT : sB + stage * B_BYTES) + my_box * BOX_BYTES;
+        const int c0 = my_mn ? my_row0 + 64 * my_box : k0, c1 = my_mn ? k0 : my_row0;
+        if (is_a && p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
           const int part = p.a_bytes / p.cn, rows = part / (BK * 2);
-          tma_load_2d_mcast(a + crank * part, &tm_a, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>((1u << p.cn) - 1u));
+          tma_load_2d_mcast(dst + crank * part, my_map, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>(a_mask));
         } else {
-          tma_load_2d(a, &tm_a, &full[stage], k0, m0);
+          tma_load_2d(dst, my_map, &full[stage], c0, c1);
         }
       }
-      else { tma_load_2d(a, &tm_a, &full[stage], m0, k0); tma_load_2d(a + BOX_BYTES, &tm_a, &full[stage], m0 + 64, k0); }
     };
-    auto load_b = [&](int stage, int k0) {
-      uint8_t* b = sB + stage * B_BYTES;
-      if (!p.b_mn) tma_load_2d(b, &tm_b, &full[stage], k0, n0);
-      else for (int i = 0; i < p.bn / 64; ++i) tma_load_2d(b + i * BOX_BYTES, &tm_b, &full[stage], n0 + 64 * i, k0);
-    };
+    // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
+    // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const int npre = p.b_independent ? (nk < STAGES ? nk : STAGES) : 0;
-    if (elect_one()) {
-      for (int kb = 0; kb < npre; ++kb) {            // ring slots are free on the first pass
-        mbar_arrive_expect_tx(&full[kb], bytes);
-        load_b(kb, kbeg + kb * BK);
-      }
+    for (int kb = 0; kb < npre; ++kb) {              // ring slots are free on the first pass
+      if (lane == 0) mbar_arrive_expect_tx(&full[kb], bytes);
+      __syncwarp();
+      issue(kb, kbeg + kb * BK, false, true);
     }
     __syncwarp();
     grid_dependency_wait();
@@ -171,11 +178,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int kb = 0; kb < nk; ++kb) {
       const int k0 = kbeg + kb * BK;
       mbar_wait(&empty[stage], phase ^ 1, 1);
-      if (elect_one()) {
-        if (kb >= npre) { mbar_arrive_expect_tx(&full[stage], bytes); load_b(stage, k0); }
-        load_a(stage, k0);
-      }
+      if (kb >= npre && lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
       __syncwarp();
+      issue(stage, k0, true, kb >= npre);
+      if (kb == 3) P3D_STAMP(8);
+      if (kb == 7) P3D_STAMP(9);
+      if (kb == 11) P3D_STAMP(10);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     P3D_STAMP(2);
@@ -188,6 +196,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(&full[stage], phase, 2);
       if (kb == 0) P3D_STAMP(3);
+      if (kb == 4) P3D_STAMP(11);
+      if (kb == 8) P3D_STAMP(12);
+      if (kb == 12) P3D_STAMP(13);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t aa = a_base + stage * A_SLOT, bb = b_base + stage * B_BYTES;

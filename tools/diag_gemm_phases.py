@@ -10,7 +10,7 @@ def run(M, N, K, a_mn, b_mn, split_k=0, colsum=False, res=False):
     C = torch.zeros((M, N), device="cuda")
     cs = torch.zeros(2 * N, dtype=torch.float64, device="cuda") if colsum else None
     rv = torch.randn((M, N), device="cuda") if res else None
-    dbg = torch.zeros((4096, 8), dtype=torch.int64, device="cuda")
+    dbg = torch.zeros((4096, 16), dtype=torch.int64, device="cuda")
     def call():
         _lib.check(_lib.lib.p3d_debug_tc_gemm(A.data_ptr(), A.shape[1], a_mn, B.data_ptr(), B.shape[1], b_mn, C.data_ptr(), N, M, N, K,
                                               None, rv.data_ptr() if res else None, 1.0, split_k, cs.data_ptr() if colsum else None, None))
@@ -22,9 +22,11 @@ def run(M, N, K, a_mn, b_mn, split_k=0, colsum=False, res=False):
     d = d[d[:, 0] > 0]
     t0 = d[:, 0].min()
     rel = d - t0
-    names = ["entry", "setup done", "producer issued all", "first tile landed", "all MMAs issued", "accumulator complete", "epilogue done", "block end"]
+    names = ["entry", "setup done", "producer issued all", "first tile landed", "all MMAs issued", "accumulator complete", "epilogue done", "block end",
+             "producer issued kb 3", "producer issued kb 7", "producer issued kb 11", "tile 4 landed+MMA free", "tile 8 landed+MMA free", "tile 12 landed+MMA free"]
     print(f"M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} split={split_k} colsum={colsum} res={res}: {len(d)} CTAs; kernel span {(d[:,7].max()-t0)/1e3:.1f} us")
     for i, n in enumerate(names):
+        if rel[:, i].max() < 0: continue
         print(f"   {n:22s} mean {rel[:, i].mean()/1e3:6.2f} us   min {rel[:, i].min()/1e3:6.2f}   max {rel[:, i].max()/1e3:6.2f}")
 run(4096, 1024, 1024, 0, 1, colsum=True)
 run(4096, 1024, 1024, 0, 0, res=True)
