@@ -6,11 +6,13 @@
 // stage is  h' = relu(h W' + b') (+ residual)  and the last one  y = h W' + b'.
 //
 // One persistent CTA per SM walks 128-pose row tiles through ALL layers:
-//   warp 0   TMA producer : A tile [128 x 64] bf16 of the current activations and the matching
-//                           W' tile [256 x 64] into a 4-stage smem ring (128B swizzle)
+//   warp 0   TMA producer A: A tile [128 x 64] bf16 of the current activations (gated by the slab barriers of the
+//                           previous layer) into the smem ring (128B swizzle)
+//   warp 2   TMEM allocator, then TMA producer B: the matching W' tile; weights depend on nothing, so this warp
+//                           runs ahead of the layer chain by up to a full ring (+10 % at 16 K poses, where the
+//                           layer transitions are a larger share)
 //   warp 1   MMA issuer   : tcgen05.mma 128x256x16 (one elected lane, warp-uniform operands), fp32
 //                           accumulators in TMEM, 2 x 256 columns double buffered against the epilogue
-//   warp 2   TMEM allocator
 //   warps 4-7 epilogue    : tcgen05.ld -> +bias -> ReLU -> bf16 -> swizzled smem tile -> TMA store
 //                           (cp.reduce.async.bulk .add when the block's residual is added: the L2
 //                           performs  P += tile  so the residual is never re-read by the SM), or fp32 y
@@ -109,7 +111,8 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_act); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_wout);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // full: one arrival per producer warp (A = activations, B = weights) of the leader's accounting
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * CG); }
     mbar_init(stg_full, 4); mbar_init(stg_free, 1);
     for (int c = 0; c < MAX_SLABS; ++c) mbar_init(&slab_done[c], 1);
@@ -129,8 +132,12 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   const int nk_hidden = L / BK;
   const int nchunks_hidden = L / BN;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (warp-uniform loop)
+  if (warp == 0 || warp == 2) {
+    // ------------------------------------------------------------ TMA producers (warp-uniform loops)
+    // warp 0 fetches the A tiles (activations: gated by the slab barriers of the previous layer), warp 2 - idle after
+    // the TMEM allocation - the W' tiles, which depend on nothing and may run ahead of the layer chain by a full ring.
+    // Each arrives on full[stage] with its own byte count.
+    const bool prodA = (warp == 0);
     int stage = 0; uint32_t phase = 0; uint32_t dep_layers = 0;
     for (int gt = group_id; gt < ngtiles; gt += ngroups) {
       const int tile = gt * CG + static_cast<int>(rank);
@@ -142,24 +149,24 @@ mlp_forward_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int a_row = first ? tile * BM
                                 : static_cast<int>(((l & 1) ? 0 : p.act_half_rows) + static_cast<long long>(blockIdx.x) * BM);
         const int b_rows = last ? p.out_n / CG : T::B_ROWS;
-        const uint32_t bytes = A_BYTES + b_rows * BK * 2;
+        const uint32_t bytes = prodA ? A_BYTES : b_rows * BK * 2;
         for (int c = 0; c < nchunks; ++c) {
           const int b_row = (last ? 0 : l * L + c * BN) + static_cast<int>(rank) * b_rows;
           for (int ks = 0; ks < nk; ++ks) {
             // K slice ks reads columns [64ks, 64ks+64) = slab ks of the previous layer (this CTA's rows), written
             // by TMA stores (async proxy, completed before the arrive): no proxy fence needed
-            if (!first && c == 0) mbar_wait(&slab_done[ks], dep_layers & 1, 100 + l);
+            if (prodA && !first && c == 0) mbar_wait(&slab_done[ks], dep_layers & 1, 100 + l);
             mbar_wait(&empty[stage], phase ^ 1, 1);
             if (elect_one()) {
               if (CG == 1) {
                 mbar_arrive_expect_tx(&full[stage], bytes);
-                tma_load_2d_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
-                tma_load_2d_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
+                if (prodA) tma_load_2d_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
+                else       tma_load_2d_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
               } else {
                 // both CTAs' bytes are accounted on the leader's barrier
                 if (leader) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
-                tma_load_2d_2sm_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
-                tma_load_2d_2sm_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
+                if (prodA) tma_load_2d_2sm_hint(sA + stage * A_BYTES, tmA, &full[stage], ks * BK, a_row, first ? kEvictFirst : kEvictLast);
+                else       tma_load_2d_2sm_hint(sB + stage * B_BYTES, last ? &tm_wout : &tm_w, &full[stage], ks * BK, b_row, kEvictLast);
               }
             }
             __syncwarp();
