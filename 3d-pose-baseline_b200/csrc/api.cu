@@ -347,8 +347,9 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
   }
   P3D_TRY(prep::pack_input(x, m->xb, B, st));
   // One tile of the fused persistent kernel takes ~100 us to walk all layers (a single SM pair streams every
-  // weight); below the crossover the per-layer GEMMs, which split each layer over N, are faster.
-  static const int64_t layered_max = [] { const char* e = getenv("P3D_LAYERED_MAX"); return e ? atoll(e) : 4096LL; }();
+  // weight); below the crossover (measured: 77 vs 97 us at 4096 poses, 135 vs 101 us at 8192) the per-layer GEMMs,
+  // which split each layer over N, are faster.
+  static const int64_t layered_max = [] { const char* e = getenv("P3D_LAYERED_MAX"); return e ? atoll(e) : 6144LL; }();
   const bool fused_ok = (L % 256) == 0 && L <= 4096;
   if (!fused_ok || B < layered_max) return layered::forward(m, m->xb, y, B, st);
   return tc::forward_bf16(m, m->xb, y, B, st);

@@ -1,4 +1,4 @@
-// Layered inference forward for small and medium batches (2 <= B < ~4096) and for widths the fused
+// Layered inference forward for small and medium batches (2 <= B < ~6144) and for widths the fused
 // persistent kernel does not tile (linear_size % 256 != 0): one tcgen05 GEMM per layer (tc_gemm.cu),
 // bias + ReLU (+ residual) fused in the epilogue, bf16 activations ping-ponging between two L2-resident
 // buffers.  Same graph as mlp_tc.cu (src/linear_model.py:102-125,154-201 at isTraining=False) and the same
