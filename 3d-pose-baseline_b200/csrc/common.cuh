@@ -102,7 +102,7 @@ struct TrainWorkspace {
   void* sc = nullptr;             // device StepScalars (per-step values: Adam step size, lr, dropout seed/step)
   // CUDA-graph replay of the step: fixed-address staging of x / t / y / (loss, lr) and one graph per (B, dropout)
   float* gx = nullptr; float* gt = nullptr; float* gy = nullptr; float* gscal = nullptr;
-  struct GraphEntry { int64_t B; int dropout; int launches; void* exec; };
+  struct GraphEntry { int64_t B; int dropout; int launches; void* exec; int64_t Bg; int64_t row0; };
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   // the weight-gradient GEMMs of the fused small-batch step run on a side stream (a parallel branch of the graph)

@@ -889,12 +889,13 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
 // One step on inputs that already sit in the staging buffers (w.gx, w.gt): per-step scalars -> device, then the
 // body as a CUDA graph captured on a private stream and replayed on the caller's stream (first call of a shape runs
 // directly, second captures).  Results land in w.gy / w.gscal.  Single GPU, generated dropout masks.
-static int train_step_staged(p3d_model* m, int64_t B, float keep, uint64_t seed, cudaStream_t st) {
+static int train_step_staged(p3d_model* m, int64_t B, float keep, uint64_t seed, cudaStream_t st, int64_t Bg = 0, int64_t row0 = 0) {
+  if (Bg <= 0) Bg = B;
   TrainWorkspace& w = m->tw;
   const bool dropout = keep < 1.f;
   TrainWorkspace::GraphEntry* ge = nullptr;
-  for (auto& g : w.graphs) if (g.B == B && g.dropout == (dropout ? 1 : 0)) ge = &g;
-  if (!ge) { w.graphs.push_back(TrainWorkspace::GraphEntry{B, dropout ? 1 : 0, 0, nullptr}); ge = &w.graphs.back(); }
+  for (auto& g : w.graphs) if (g.B == B && g.dropout == (dropout ? 1 : 0) && g.Bg == Bg && g.row0 == row0) ge = &g;
+  if (!ge) { w.graphs.push_back(TrainWorkspace::GraphEntry{B, dropout ? 1 : 0, 0, nullptr, Bg, row0}); ge = &w.graphs.back(); }
   if (ge->exec) {
     P3D_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(ge->exec), st));
     count_launch(ge->launches > 0 ? ge->launches : 0);
@@ -903,7 +904,7 @@ static int train_step_staged(p3d_model* m, int64_t B, float keep, uint64_t seed,
   if (ge->launches == 0) {
     // first step of this shape: run directly (also performs every one-time cudaFuncSetAttribute)
     const long long before = launch_count_now();
-    const int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, B, 0, w.gscal, w.gscal + 1, w.gy, st);
+    const int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, Bg, row0, w.gscal, w.gscal + 1, w.gy, st);
     ge->launches = static_cast<int>(launch_count_now() - before);
     if (ge->launches == 0) ge->launches = -1;
     return rc;
@@ -911,7 +912,7 @@ static int train_step_staged(p3d_model* m, int64_t B, float keep, uint64_t seed,
   if (!w.cap_stream) P3D_CUDA(cudaStreamCreateWithFlags(&w.cap_stream, cudaStreamNonBlocking));
   cudaGraph_t graph = nullptr;
   P3D_CUDA(cudaStreamBeginCapture(w.cap_stream, cudaStreamCaptureModeThreadLocal));
-  int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, B, 0, w.gscal, w.gscal + 1, w.gy, w.cap_stream);
+  int rc = train_body(m, w.gx, w.gt, B, dropout, nullptr, Bg, row0, w.gscal, w.gscal + 1, w.gy, w.cap_stream);
   const cudaError_t ce = cudaStreamEndCapture(w.cap_stream, &graph);
   count_launch(-(ge->launches > 0 ? ge->launches : 0));       // the captured launches did not run
   if (rc != P3D_OK || ce != cudaSuccess || !graph) {
@@ -954,11 +955,13 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   P3D_TRY(ensure_workspace(m, B));
   TrainWorkspace& w = m->tw;
   P3D_TRY(push_scalars(m, keep, seed, st));
-  if (graphs_enabled() && m->world == 1 && mask_in == nullptr) {
+  // data parallel: the NCCL all-reduces (SyncBN sums, gradient) are captured into the graph with everything else
+  static const bool dp_graph = [] { const char* e = getenv("P3D_TRAIN_GRAPH_DP"); return !(e && e[0] == '0'); }();
+  if (graphs_enabled() && (m->world == 1 || dp_graph) && mask_in == nullptr) {
     const size_t out = static_cast<size_t>(m->out_size);
     P3D_CUDA(cudaMemcpyAsync(w.gx, x, sizeof(float) * B * kIn, cudaMemcpyDeviceToDevice, st));
     P3D_CUDA(cudaMemcpyAsync(w.gt, t, sizeof(float) * B * out, cudaMemcpyDeviceToDevice, st));
-    P3D_TRY(train_step_staged(m, B, keep, seed, st));
+    P3D_TRY(train_step_staged(m, B, keep, seed, st, Bg, row0));
     P3D_CUDA(cudaMemcpyAsync(y, w.gy, sizeof(float) * B * out, cudaMemcpyDeviceToDevice, st));
     if (loss) P3D_CUDA(cudaMemcpyAsync(loss, w.gscal, sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (lr_used) P3D_CUDA(cudaMemcpyAsync(lr_used, w.gscal + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
