@@ -132,6 +132,11 @@ struct Epilogue {
 int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
           int ldc, const Epilogue& e, cudaStream_t st);
 }  // namespace simt
+namespace p2p {
+bool ready(const p3d_model* m);
+int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st);
+void destroy(p3d_model* m);
+}  // namespace p2p
 namespace tcg {
 // Extra operands of the small-batch (M <= 128: the whole batch is one tile, so per-column batch statistics are
 // CTA-local) fused training epilogues of tc_gemm.cu.
@@ -238,4 +243,5 @@ struct p3d_model {
   p3d::TrainWorkspace tw;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  void* p2p_state = nullptr;          // peer-memory exchange buffers of the small all-reduces (p2p.cu)
 };

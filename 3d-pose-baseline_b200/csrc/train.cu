@@ -61,6 +61,8 @@ static NcclApi* nccl() {
 
 static int allreduce(p3d_model* m, void* buf, size_t n, ncclDataType_t dt, cudaStream_t st) {
   if (m->world <= 1) return P3D_OK;
+  // the latency-bound reductions (SyncBN sums, loss) go over NVLink peer memory in one kernel each (p2p.cu)
+  if (dt == ncclDouble && n <= 8192 && p2p::ready(m)) return p2p::allreduce_small(m, static_cast<double*>(buf), n, st);
   P3D_NCCL(nccl()->AllReduce(buf, buf, n, dt, ncclSum, static_cast<ncclComm_t>(m->nccl_comm), st));
   return P3D_OK;
 }
@@ -467,6 +469,7 @@ void free_workspace(p3d_model* m) {
   if (w.side_stream) cudaStreamDestroy(w.side_stream);
   for (auto& e : w.ev) if (e) cudaEventDestroy(e);
   w = TrainWorkspace();
+  p2p::destroy(m);
   if (m->nccl_comm && nccl()) { nccl()->CommDestroy(static_cast<ncclComm_t>(m->nccl_comm)); m->nccl_comm = nullptr; }
 }
 

@@ -84,6 +84,8 @@ PROTOTYPES = {
     "p3d_similarity_transform_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
     "p3d_debug_latency_stamps": (c_int, [c_void_p, c_void_p, c_int]),
+    "p3d_model_p2p_handle": (c_int, [c_void_p, c_void_p]),
+    "p3d_model_p2p_attach": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "p3d_model_train_epoch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, C.c_uint64,
                                       c_void_p, c_void_p, c_void_p]),
     "p3d_debug_tc_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,

@@ -210,6 +210,21 @@ class LinearModel(object):
             self.set_variable(name, v.cpu().numpy())
         check(lib.p3d_model_attach_nccl(self._handle, _lib.np_ptr(ident), self.rank, self.world))
         self._dist = dist
+        # single node: the small SyncBN / loss reductions go over NVLink peer memory (CUDA IPC); NCCL otherwise
+        self.p2p = False
+        if os.environ.get("P3D_P2P", "1") != "0" and int(os.environ.get("LOCAL_WORLD_SIZE", self.world)) == self.world:
+            mine = np.zeros(64, dtype=np.uint8)
+            check(lib.p3d_model_p2p_handle(self._handle, _lib.np_ptr(mine)))
+            hs = [torch.zeros(64, dtype=torch.uint8, device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
+                  for _ in range(self.world)]
+            src = torch.from_numpy(mine)
+            dist.all_gather(hs, src.cuda(self.device) if dist.get_backend() == "nccl" else src)
+            allh = np.ascontiguousarray(np.concatenate([h.cpu().numpy() for h in hs]))
+            self.p2p = lib.p3d_model_p2p_attach(self._handle, _lib.np_ptr(allh), self.rank, self.world) == 0
+            ok = torch.tensor([1 if self.p2p else 0], device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
+            if int(ok.item()) == 0 and self.p2p:
+                raise RuntimeError("peer-memory attach succeeded on some ranks only; set P3D_P2P=0")
 
     # ------------------------------------------------------------------ step
     def step(self, session, encoder_inputs, decoder_outputs, dropout_keep_prob, isTraining=True, *,

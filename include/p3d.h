@@ -114,6 +114,13 @@ int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t 
  * all-reduce per step).  id_host = 128-byte ncclUniqueId made by rank 0 and broadcast by the caller. */
 int p3d_nccl_unique_id(uint8_t* id_host /*[128]*/);
 int p3d_model_attach_nccl(p3d_model* m, const uint8_t* id_host, int rank, int world);
+
+/* Optional, after attach_nccl, ranks of ONE node: the eleven latency-bound reductions of a data-parallel step (SyncBN
+ * sums, loss) then run as single kernels over NVLink peer memory instead of NCCL calls.  Every rank exports the CUDA
+ * IPC handle of its exchange buffer (64 bytes), the host layer all-gathers them, every rank attaches all `world`
+ * handles (rank-major, 64 bytes each).  If a peer is not reachable attach fails and the step keeps using NCCL. */
+int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle64_host);
+int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, int world);
 int64_t p3d_model_global_step(p3d_model* m);
 
 /* ---------------------------------------------------------------- cameras ---------------------

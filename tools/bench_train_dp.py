@@ -16,7 +16,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-for B in (64, 4096, 32768):
+for B in [int(b) for b in (sys.argv[1:] or [64, 4096, 32768])]:
     for mode in ("bf16",):
         m = LinearModel(1024, 2, True, True, True, B, 1e-3, mode=mode, device=local, seed=1, dist=dist if world > 1 else None)
         g = torch.Generator(device=dev).manual_seed(0)
@@ -38,7 +38,7 @@ for B in (64, 4096, 32768):
         if rank == 0:
             print(json.dumps({"workload": "data-parallel training step (dropout 0.5, max_norm, Adam, SyncBN)", "n_gpus": world, "global_batch": B,
                               "rows_per_gpu": B // world, "mode": mode, "us_per_step": round(float(ms.item()) * 1e3, 1),
-                              "poses_per_s": round(B / (float(ms.item()) * 1e-3)), "loss": round(float(loss), 4)}))
+                              "poses_per_s": round(B / (float(ms.item()) * 1e-3)), "loss": round(float(loss), 4), "peer_memory_reductions": bool(getattr(m, "p2p", False))}))
         m.close()
 if world > 1:
     dist.destroy_process_group()
