@@ -433,6 +433,36 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
   return P3D_OK;
 }
 
+// CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), slice-by-8 on the host: the checksum of TensorFlow's
+// checkpoint files (p3d/checkpoint.py).  `init` is the CRC of the bytes that came before (0 to start).
+uint32_t p3d_crc32c(const void* data_host, size_t n, uint32_t init) {
+  static uint32_t T[8][256];
+  static const bool ready = [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+    return true;
+  }();
+  (void)ready;
+  const uint8_t* p = static_cast<const uint8_t*>(data_host);
+  uint32_t c = ~init;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF]; --n; }
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = T[7][w & 0xFF] ^ T[6][(w >> 8) & 0xFF] ^ T[5][(w >> 16) & 0xFF] ^ T[4][(w >> 24) & 0xFF] ^
+        T[3][(w >> 32) & 0xFF] ^ T[2][(w >> 40) & 0xFF] ^ T[1][(w >> 48) & 0xFF] ^ T[0][(w >> 56) & 0xFF];
+    p += 8; n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xFF];
+  return ~c;
+}
+
 int p3d_debug_latency_stamps(p3d_model* m, uint64_t* out_host, int n) {
   P3D_REQUIRE(m && out_host && n >= 1 && n <= 24, "latency_stamps: bad argument");
   P3D_REQUIRE(m->lat_counter, "latency_stamps: the batch-1 kernel has not run (set P3D_LAT_STAMPS=1)");

@@ -132,9 +132,36 @@ struct Epilogue {
 int sgemm(bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
           int ldc, const Epilogue& e, cudaStream_t st);
 }  // namespace simt
+namespace rt {
+// Realtime front-end / back-end around the lifter (src/openpose_3dpose_sandbox_realtime.py:137-171): device tables.
+struct Tables {
+  double mu2[32], sd2[32];      // data_mean_2d[dim_to_use_2d], data_std_2d[dim_to_use_2d]
+  int use2[32];                 // dim_to_use_2d (coordinate index into the 64-vector)
+  double mu3[96], sd3[96];      // data_mean_3d, data_std_3d (all 96 dims)
+  int use3[48];                 // dim_to_use_3d (first `out` entries)
+  int pos3[96];                 // inverse: network output column of full dim j, or -1 (ignored dim)
+  int out;
+};
+// Extra operands of the batch-1 cluster kernel when it runs the whole realtime step in one launch.
+struct Fused {
+  const Tables* tab = nullptr;                  // nullptr = plain forward
+  const double* kp = nullptr;                   // [36] keypoints (host-mapped or device memory)
+  float* enc = nullptr;                         // [32] normalised network input
+  double* pose = nullptr;                       // [96] un-normalised prediction (only the used dims are written)
+  unsigned long long* flag = nullptr;           // completion flag (host-mapped), set to seq after all outputs
+  unsigned long long seq = 0;
+};
+}  // namespace rt
+namespace simt {
+int forward_latency_cluster_rt(p3d_model* m, const rt::Fused& f, float* y, cudaStream_t st);
+}
 namespace p2p {
 bool ready(const p3d_model* m);
-int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st);
+struct BnFinalize {                 // optional fused tail: BatchNorm statistics from the reduced [sum | sumsq]
+  double invB = 0.0;
+  float* mean = nullptr; float* rstd = nullptr; float* mm = nullptr; float* mv = nullptr;
+};
+int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st, const BnFinalize* fin = nullptr);
 void destroy(p3d_model* m);
 }  // namespace p2p
 namespace tcg {

@@ -389,4 +389,30 @@ P3D_HD void pose_errors_f32(float (&g)[W], float (&p)[W], const float* sd, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Realtime front-end (src/openpose_3dpose_sandbox_realtime.py:20,137-163).
+// kp36 = the first 18 OpenPose/COCO keypoints as (x, y) pairs.  The reference scatters keypoint i into H3.6M joint
+// order[i] (order = [15,12,25,26,27,17,18,19,1,2,3,6,7,8], :20,:144-147), then synthesises
+//   Hip       (joint 0)  = (RHip(1) + LHip(6)) / 2                      (:150)
+//   Neck/Nose (joint 14) = (Head(15) + Spine(12)) / 2                   (:152)
+//   Thorax    (joint 13) = 2 * Spine(12) - Neck/Nose(14)                (:154)
+// This returns coordinate d (= joint * 2 + xy) of that 64-vector; joints the scatter never writes are 0 (the
+// reference's first-frame value; none of them is in dim_to_use_2d).
+P3D_HD int openpose_index_of_h36m_joint(int j) {
+  switch (j) {
+    case 15: return 0;  case 12: return 1;  case 25: return 2;  case 26: return 3;  case 27: return 4;
+    case 17: return 5;  case 18: return 6;  case 19: return 7;  case 1:  return 8;  case 2:  return 9;
+    case 3:  return 10; case 6:  return 11; case 7:  return 12; case 8:  return 13;
+    default: return -1;
+  }
+}
+P3D_HD double openpose_h36m_coord(const double* kp36, int d) {
+  const int j = d >> 1, c = d & 1;
+  if (j == 0) return (kp36[8 * 2 + c] + kp36[11 * 2 + c]) / 2;
+  if (j == 14) return (kp36[0 * 2 + c] + kp36[1 * 2 + c]) / 2;
+  if (j == 13) return 2 * kp36[1 * 2 + c] - (kp36[0 * 2 + c] + kp36[1 * 2 + c]) / 2;
+  const int i = openpose_index_of_h36m_joint(j);
+  return i >= 0 ? kp36[i * 2 + c] : 0.0;
+}
+
 }  // namespace p3d

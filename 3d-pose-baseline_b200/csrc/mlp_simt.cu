@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "math_hd.h"
 
 namespace p3d {
 namespace simt {
@@ -209,6 +210,7 @@ struct LatArgs {
   unsigned long long* counter; unsigned long long base;   // barrier counter value at kernel entry
   unsigned long long* stamps;                              // optional [16] globaltimer stamps (debug)
   int rows, L, nlayers, out, kpad, residual;
+  rt::Fused rt;                                            // realtime front-end / back-end fused into the cluster kernel
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
@@ -434,7 +436,22 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
     for (int p = 0; p < LSLOTS && p < nparts; ++p) bulk_load(ring + p * LPART_BYTES, part_src(p), LPART_BYTES, &wfull[p], 4);
   }
   // x -> sQ[0..31] (layer 0 reads "Q"); layer 0 weights (K = 32: lanes 0..7, 4 bf16 each) straight from L2
-  if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
+  if (a.rt.tab == nullptr) {
+    if (threadIdx.x < kIn) sQ[threadIdx.x] = __ldg(a.x + threadIdx.x);
+  } else {
+    // realtime step: keypoints (one coalesced read of 36 doubles per CTA, possibly across PCIe from mapped host
+    // memory) -> H3.6M order, synthesised hip / neck / thorax, (x - mu) / sigma in fp64, fp32 feed
+    double* skp = reinterpret_cast<double*>(sQ + 64);      // scratch no other CTA writes before the first cluster barrier
+    if (threadIdx.x < 36) skp[threadIdx.x] = *reinterpret_cast<const volatile double*>(a.rt.kp + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x < kIn) {
+      const rt::Tables* tb = a.rt.tab;
+      const double v = (openpose_h36m_coord(skp, tb->use2[threadIdx.x]) - tb->mu2[threadIdx.x]) / tb->sd2[threadIdx.x];
+      const float vf = static_cast<float>(v);
+      sQ[threadIdx.x] = vf;
+      if (rank == 0 && a.rt.enc) a.rt.enc[threadIdx.x] = vf;
+    }
+  }
   uint2 w0[LOPW]; float b0[LOPW];
 #pragma unroll
   for (int o = 0; o < LOPW; ++o) {
@@ -527,13 +544,27 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
         acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
       }
       for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-      if (lane == 0) a.y[g] = acc + __ldg(a.bias + l * L + g);
+      if (lane == 0) {
+        const float yv = acc + __ldg(a.bias + l * L + g);
+        a.y[g] = yv;
+        if (a.rt.tab) {                                    // data_utils.unNormalizeData (:299-311): fp32 value, fp64 scale
+          const int j = a.rt.tab->use3[g];
+          a.rt.pose[j] = __dadd_rn(__dmul_rn(static_cast<double>(yv), a.rt.tab->sd3[j]), a.rt.tab->mu3[j]);
+        }
+      }
     }
+  }
+  if (a.rt.flag) {
+    // every output store is ordered before the cluster barrier (release) and the flag store after it (acquire +
+    // system-scope release): a host that polls the mapped flag sees complete outputs without a stream synchronise
+    cl_sync();
+    if (rank == 0 && threadIdx.x == 0)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.rt.flag), "l"(a.rt.seq) : "memory");
   }
   LAT_STAMP(a.nlayers);
 }
 
-int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) {
+static int launch_latency_cluster(p3d_model* m, const float* x, float* y, const rt::Fused* f, cudaStream_t st) {
   static int ok = -1;
   if (ok < 0) {
     ok = 0;
@@ -556,6 +587,7 @@ int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t
     P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long) * 32));
     P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long) * 32));
   }
+  if (f) a.rt = *f;
   a.rows = 1; a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.hP = a.hQ = nullptr; a.counter = nullptr; a.base = 0;
   a.stamps = getenv("P3D_LAT_STAMPS") ? m->lat_counter + 8 : nullptr;
   a.L = m->L; a.nlayers = static_cast<int>(m->layers.size()); a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
@@ -567,6 +599,13 @@ int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t
   P3D_CUDA(cudaLaunchKernelEx(&cfg, latency_cluster_kernel, a));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) { return launch_latency_cluster(m, x, y, nullptr, st); }
+// the same launch running the whole realtime step (keypoints -> normalised input -> lifter -> un-normalised pose)
+int forward_latency_cluster_rt(p3d_model* m, const rt::Fused& f, float* y, cudaStream_t st) {
+  if (m->L != 1024 || m->cfg.mode != P3D_MODE_BF16) return 1;
+  return launch_latency_cluster(m, nullptr, y, &f, st);
 }
 
 int forward_small(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {

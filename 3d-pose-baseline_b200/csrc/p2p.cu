@@ -40,7 +40,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int rank, int world, double* __restrict__ buf, int n) {
+// Optional tail of a forward SyncBN reduction: the BatchNorm finalisation (mean / biased variance over the global
+// batch, moving averages with momentum .99 - train.cu's bn_finalize_kernel) runs on the freshly summed columns.
+__global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int rank, int world, double* __restrict__ buf, int n,
+                                                        const BnFinalize fin) {
   Layout* me = peers.p[rank];
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) s_seq = me->seq + 1;           // sequence numbers start at 1 (flags are zero-initialised)
@@ -54,7 +57,8 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int r
     for (int i = threadIdx.x; i < n2; i += blockDim.x) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(buf)[i];
     if ((n & 1) && threadIdx.x == 0) dst[n - 1] = buf[n - 1];
   }
-  __threadfence_system();
+  // The block barrier orders every thread's peer stores before the flag threads; their st.release.sys is cumulative,
+  // so one system-scope fence per flag thread publishes the whole vector (instead of 512 membar.sys).
   __syncthreads();
   // 2. raise my flag on every rank   3. wait for everybody's flag here
   if (threadIdx.x < world) {
@@ -66,10 +70,29 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int r
   }
   __syncthreads();
   // 4. sum in rank order
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < world; ++r) s += *reinterpret_cast<volatile double*>(&me->data[slot][r][i]);
-    buf[i] = s;
+  if (fin.mean == nullptr) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      double s = 0.0;
+      for (int r = 0; r < world; ++r) s += *reinterpret_cast<volatile double*>(&me->data[slot][r][i]);
+      buf[i] = s;
+    }
+  } else {
+    const int L = n >> 1;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int r = 0; r < world; ++r) {
+        s0 += *reinterpret_cast<volatile double*>(&me->data[slot][r][c]);
+        s1 += *reinterpret_cast<volatile double*>(&me->data[slot][r][L + c]);
+      }
+      buf[c] = s0; buf[L + c] = s1;
+      const double mu = s0 * fin.invB;
+      double var = s1 * fin.invB - mu * mu;
+      if (var < 0) var = 0;
+      fin.mean[c] = static_cast<float>(mu);
+      fin.rstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+      fin.mm[c] = fin.mm[c] * kBnMomentum + static_cast<float>(mu) * (1.f - kBnMomentum);
+      fin.mv[c] = fin.mv[c] * kBnMomentum + static_cast<float>(var) * (1.f - kBnMomentum);
+    }
   }
   if (threadIdx.x == 0) me->seq = seq;
 }
@@ -121,10 +144,11 @@ int attach(p3d_model* m, const uint8_t* handles, int rank, int world) {
 
 bool ready(const p3d_model* m) { return m->p2p_state && static_cast<const State*>(m->p2p_state)->ready; }
 
-int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st) {
+int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st, const BnFinalize* fin) {
   State* s = state_of(m);
   P3D_REQUIRE(s && s->ready && n >= 1 && n <= MAXN, "peer all-reduce: not attached or vector too long");
-  allreduce_kernel<<<1, 512, 0, st>>>(s->peers, s->rank, s->world, buf, static_cast<int>(n));
+  P3D_REQUIRE(!fin || (n % 2) == 0, "peer all-reduce: the BatchNorm tail needs [sum | sumsq]");
+  allreduce_kernel<<<1, 512, 0, st>>>(s->peers, s->rank, s->world, buf, static_cast<int>(n), fin ? *fin : BnFinalize());
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -544,6 +544,13 @@ static bool fused_enabled() {
   static const bool on = [] { const char* e = getenv("P3D_TRAIN_FUSED"); return !(e && e[0] == '0'); }();
   return on;
 }
+// Bucketed gradient all-reduce overlapped with the backward pass (P3D_DP_OVERLAP=1/0 forces it on/off).  Measured on
+// 2 GPUs the four bucket calls cost more than they hide (610 -> 647 us at 4096 poses: the all-reduce of 17 MB between
+// two GPUs is short, and the NCCL CTAs compete with the GEMMs), so the default is one flat call there.
+static bool overlap_enabled(int world) {
+  static const int force = [] { const char* e = getenv("P3D_DP_OVERLAP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  return force >= 0 ? force == 1 : world >= 4;
+}
 static inline dim3 colgrid(int cols, int64_t B) { return dim3((cols + 31) / 32, static_cast<unsigned>((B + RCH - 1) / RCH)); }
 static inline int egrid(long long n) { long long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; return static_cast<int>(g < 1 ? 1 : g); }
 
@@ -719,6 +726,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     P3D_LAUNCH_CHECK();
   }
   const bool fused = tc && m->world == 1 && B <= 128 && (L % 32) == 0 && fused_enabled();
+  bool overlap = false;
   if (fused) {
     P3D_TRY(fwd_bwd_fused(m, t, B, dropout, mask_in, y, st));
   } else {
@@ -748,9 +756,16 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
         colstats_kernel<<<colgrid(L, B), dim3(32, 8), 0, st>>>(z, B, L, stats);
         P3D_LAUNCH_CHECK();
       }
-      P3D_TRY(allreduce(m, stats, 2ull * L, ncclDouble, st));
-      bn_finalize_kernel<<<(L + 255) / 256, 256, 0, st>>>(stats, invBg, L, mean, rstd, m->moving + ly.off_mm, m->moving + ly.off_mv);
-      P3D_LAUNCH_CHECK();
+      if (m->world > 1 && 2ull * L <= 8192 && p2p::ready(m)) {
+        // peer-memory reduction with the BatchNorm finalisation as its tail: one launch
+        p2p::BnFinalize fin;
+        fin.invB = invBg; fin.mean = mean; fin.rstd = rstd; fin.mm = m->moving + ly.off_mm; fin.mv = m->moving + ly.off_mv;
+        P3D_TRY(p2p::allreduce_small(m, stats, 2ull * L, st, &fin));
+      } else {
+        P3D_TRY(allreduce(m, stats, 2ull * L, ncclDouble, st));
+        bn_finalize_kernel<<<(L + 255) / 256, 256, 0, st>>>(stats, invBg, L, mean, rstd, m->moving + ly.off_mm, m->moving + ly.off_mv);
+        P3D_LAUNCH_CHECK();
+      }
     }
     ActArgs a;
     a.z = z; a.mean = mean; a.rstd = rstd;
@@ -786,6 +801,25 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   // ---------------------------------------------------------------- backward
   float* G[3] = {w.dh, w.dres, w.dres + bl};
   int cur = 0, keepi = -1;
+  // Data parallel: a layer's weight gradient (the flat buffer is [all W | b, gamma, beta per layer]) is complete as
+  // soon as its GEMM has run, so its all-reduce starts right there on the side stream (a parallel branch of the
+  // captured graph) and travels over NVLink while the remaining layers are still being differentiated.
+  // Buckets: [W of the last hidden + output layer] | one per middle layer | [W of the first two layers], then the
+  // short vector tail (b, gamma, beta of every layer).  Only when the small reductions go over peer memory: then
+  // these buckets are the communicator's only operations and they all sit on one stream.
+  overlap = overlap_enabled(m->world) && m->world > 1 && p2p::ready(m) && nh >= 3;
+  int nev = 0;
+  auto bucket = [&](int lo, int hi) -> int {   // all-reduce the segments of layers lo..hi (inclusive)
+    if (!overlap) return P3D_OK;
+    const size_t n_w = m->layers[nh].off_w + static_cast<size_t>(m->layers[nh].K) * m->layers[nh].N;
+    const size_t beg = lo < 0 ? n_w : m->layers[lo].off_w;                       // lo < 0: the vector tail
+    const size_t end = lo < 0 ? m->n_train : (hi + 1 < nlay ? m->layers[hi + 1].off_w : n_w);
+    cudaEvent_t ready = w.ev[nev++ % 16];
+    P3D_CUDA(cudaEventRecord(ready, st));
+    P3D_CUDA(cudaStreamWaitEvent(w.side_stream, ready, 0));
+    P3D_NCCL(nccl()->AllReduce(m->grad + beg, m->grad + beg, end - beg, ncclFloat, ncclSum, static_cast<ncclComm_t>(m->nccl_comm), w.side_stream));
+    return P3D_OK;
+  };
   {
     const Layer& ly = m->layers[nh];
     if (tc) {
@@ -852,6 +886,9 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       Epilogue e0;
       P3D_TRY(sgemm(true, false, ly.K, L, static_cast<int>(B), in, lda, w.dz, L, m->grad + ly.off_w, L, e0, st));
     }
+    if (li == nh - 1) P3D_TRY(bucket(nh - 1, nh));
+    else if (li >= 2) P3D_TRY(bucket(li, li));
+    else if (li == 0) { P3D_TRY(bucket(0, 1)); P3D_TRY(bucket(-1, -1)); }
     if (li > 0) {
       int nxt = 0;
       while (nxt == cur || nxt == keepi) ++nxt;
@@ -873,9 +910,14 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       cur = nxt;
     }
   }
+  if (overlap) {   // join: the optimizer needs every bucket
+    cudaEvent_t joined = w.ev[nev++ % 16];
+    P3D_CUDA(cudaEventRecord(joined, w.side_stream));
+    P3D_CUDA(cudaStreamWaitEvent(st, joined, 0));
+  }
   }   // unfused path
   // ---------------------------------------------------------------- gradient exchange + update
-  P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
+  if (!overlap) P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
   if (clip) {
     clipdot_kernel<<<dim3(148, nlay), 256, 0, st>>>(m->theta, m->grad, tab, dots);
     P3D_LAUNCH_CHECK();

@@ -123,6 +123,33 @@ int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle64_host);
 int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, int world);
 int64_t p3d_model_global_step(p3d_model* m);
 
+/* CRC-32C of a HOST buffer (host code, slice-by-8): the checksum TensorFlow's checkpoint format uses for table blocks
+ * and tensors (tf.train.Saver, src/linear_model.py:151) - see p3d/checkpoint.py.  init = CRC of the preceding bytes. */
+uint32_t p3d_crc32c(const void* data_host, size_t n, uint32_t init);
+
+/* ---------------------------------------------------------------- realtime front-end ----------
+ * The per-frame arithmetic of src/openpose_3dpose_sandbox_realtime.py:137-171 around model.step():
+ *   xy36 = the first 18 OpenPose/COCO keypoints as (x,y) pairs (:137-142, fp64 like the JSON floats)
+ *   -> scatter into H3.6M joint order (order = [15,12,25,26,27,17,18,19,1,2,3,6,7,8], :20,:144-147),
+ *      Hip = (RHip+LHip)/2, Neck/Nose = (Head+Spine)/2, Thorax = 2*Spine - Neck/Nose (:148-154)
+ *   -> enc_in = (enc_in[dim_to_use_2d] - mean) / std in fp64 (:160-163), cast to fp32 by the feed
+ *   -> y = model.step(enc_in, isTraining=False) (:168)
+ *   -> pose3d[96] = data_utils.unNormalizeData(y, mean3d, std3d, ignore) (:171; src/data_utils.py:283-311).
+ * create() copies the statistics: mean2d/std2d[64], use2d[32] = dim_to_use_2d, mean3d/std3d[96],
+ * use3d[out] = dim_to_use_3d (all HOST pointers, as returned by normalization_stats). */
+typedef struct p3d_realtime p3d_realtime;
+int p3d_realtime_create(p3d_model* m, const double* mean2d_host, const double* std2d_host, const int32_t* use2d_host,
+                        const double* mean3d_host, const double* std3d_host, const int32_t* use3d_host, p3d_realtime** out);
+void p3d_realtime_destroy(p3d_realtime* r);
+/* One frame, HOST buffers, synchronous.  With linear_size 1024 in bf16 mode this is a single kernel launch that reads
+ * the keypoints from and writes the results to mapped pinned memory (no cudaMemcpy, no stream synchronise).
+ * enc_in_host[32] and y_host[out] (the normalised input / prediction) are optional. */
+int p3d_realtime_step_host(p3d_realtime* r, const double* xy36_host, float* enc_in_host_or_null, float* y_host_or_null,
+                           double* pose3d_host /*[96]*/);
+/* B frames, DEVICE buffers, asynchronous on `stream`: xy36[B,36] fp64 -> enc_in[B,32], y[B,out], pose3d[B,96] (optional). */
+int p3d_realtime_step(p3d_realtime* r, const double* xy36, float* enc_in, float* y, double* pose3d_or_null, int64_t B,
+                      void* stream);
+
 /* ---------------------------------------------------------------- cameras ---------------------
  * One H36M camera as loaded by cameras.load_camera_params (src/cameras.py:92-120). */
 typedef struct {

@@ -49,4 +49,15 @@ void hc_pose_errors_f32(const float* gt, const float* pred, const float* sd, con
     }
   }
 }
+
+// realtime front-end: enc[n][32] = (h36m(kp[n][36])[use2[i]] - mu2[use2[i]]) / sd2[use2[i]] (fp64)
+void hc_openpose_frontend(const double* kp, const int* use2, const double* mu2, const double* sd2, double* enc, int n) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < 32; ++i)
+      enc[b * 32 + i] = (p3d::openpose_h36m_coord(kp + 36 * b, use2[i]) - mu2[use2[i]]) / sd2[use2[i]];
+}
+void hc_openpose_h36m64(const double* kp, double* enc64) {
+  for (int d = 0; d < 64; ++d) enc64[d] = p3d::openpose_h36m_coord(kp, d);
+}
+
 }

@@ -63,17 +63,24 @@ mk = (rng.uniform(size=(nh, B, 256)) < keep).astype(np.uint8)
 lb, _, _, yb = mb.step(None, xb_, tb_, keep, isTraining=True, dropout_mask=mk)
 yq, cq_ = M.forward(pb64, xb_.astype(np.float64), cfg, training=True, keep_prob=keep, masks=list(mk), want_cache=True, quant=qf)
 gq = M.backward(pb64, xb_.astype(np.float64), tb_.astype(np.float64), cfg, cq_, yq, quant=qf)
-ok_b = abs(float(lb) - M.loss_fn(yq, tb_.astype(np.float64))) <= 1e-4 * max(1.0, float(lb))
-ok_b &= np.abs(yb - yq).max() <= 3e-3 * max(np.abs(yq).max(), 1.0)
+why = []
+if not abs(float(lb) - M.loss_fn(yq, tb_.astype(np.float64))) <= 1e-4 * max(1.0, float(lb)):
+    why.append("loss %r vs %r" % (float(lb), M.loss_fn(yq, tb_.astype(np.float64))))
+if not np.abs(yb - yq).max() <= 3e-3 * max(np.abs(yq).max(), 1.0):
+    why.append("outputs: max abs diff %.3e" % np.abs(yb - yq).max())
 gb = mb.get_gradients()
 for name, gref in gq.items():
     if np.abs(gref).max() > 1e-12:
-        ok_b &= np.linalg.norm(gb[name] - gref) <= 5e-2 * np.linalg.norm(gref)
+        rel = np.linalg.norm(gb[name] - gref) / np.linalg.norm(gref)
+        if not rel <= 5e-2:
+            why.append("grad %s rel L2 %.3e" % (name, rel))
 wb_ = torch.from_numpy(mb.get_variables()["linear_model/w1"]).cuda()
 wb0 = wb_.clone(); dist.broadcast(wb0, 0)
-ok_b &= bool(torch.equal(wb_, wb0))
-if not ok_b and rank == 0:
-    print("bf16 data-parallel step FAILED", float(lb), M.loss_fn(yq, tb_.astype(np.float64)))
+if not bool(torch.equal(wb_, wb0)):
+    why.append("w1 differs between ranks after the update")
+ok_b = not why
+if why:
+    print("bf16 data-parallel step FAILED on rank %d: %s" % (rank, "; ".join(why)), flush=True)
 ok &= bool(ok_b)
 mb.close()
 
