@@ -289,6 +289,11 @@ int p3d_model_set_param_host(p3d_model* m, const char* name, const float* host, 
     m->global_step = static_cast<int64_t>(host[0]);
     return P3D_OK;
   }
+  if (strcmp(name, "learning_rate") == 0) {   // the base rate variable (src/linear_model.py:86); not enumerated
+    P3D_REQUIRE(n == 1, "learning_rate is a scalar");
+    m->cfg.learning_rate = host[0];
+    return P3D_OK;
+  }
   NamedParam* p = find_param(m, name);
   P3D_REQUIRE(p, "unknown variable '%s'", name);
   P3D_REQUIRE(p->numel == n, "variable '%s' has %zu elements, got %zu", name, p->numel, n);
@@ -303,6 +308,11 @@ int p3d_model_get_param_host(p3d_model* m, const char* name, float* host, size_t
   if (strcmp(name, "global_step") == 0) {
     P3D_REQUIRE(n == 1, "global_step is a scalar");
     host[0] = static_cast<float>(m->global_step);
+    return P3D_OK;
+  }
+  if (strcmp(name, "learning_rate") == 0) {
+    P3D_REQUIRE(n == 1, "learning_rate is a scalar");
+    host[0] = m->cfg.learning_rate;
     return P3D_OK;
   }
   NamedParam* p = find_param(m, name);

@@ -350,9 +350,10 @@ def write_bundle(prefix, tensors):
             a = np.asarray(tensors[n])
             if a.dtype not in _DT_OF:
                 raise ValueError("variable %s: dtype %s cannot be stored" % (n, a.dtype))
+            shape = a.shape                                   # ascontiguousarray would turn a scalar into [1]
             a = np.ascontiguousarray(a.astype(a.dtype.newbyteorder("<"), copy=False))
             f.write(a.tobytes())
-            items.append((n.encode(), _encode_entry(_DT_OF[np.dtype(a.dtype.name)], a.shape, offset, a.nbytes, mask_crc(crc32c(a)))))
+            items.append((n.encode(), _encode_entry(_DT_OF[np.dtype(a.dtype.name)], shape, offset, a.nbytes, mask_crc(crc32c(a)))))
             offset += a.nbytes
     write_table(prefix + ".index", items)
     return prefix

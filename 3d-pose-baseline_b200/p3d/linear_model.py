@@ -71,6 +71,52 @@ def shard_rows(n_rows: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
+class _Saver(object):
+    """tf.train.Saver(tf.global_variables(), max_to_keep=10) of the reference (linear_model.py:151) writing and
+    reading TensorFlow's checkpoint format without TensorFlow (p3d/checkpoint.py):
+        model.saver.save(sess, os.path.join(train_dir, 'checkpoint'), global_step=step)   # predict_3dpose.py:328
+        model.saver.restore(sess, ckpt.model_checkpoint_path)                             # predict_3dpose.py:180
+    Variables carry the TF1 graph's names; `global_step` is an int32 scalar, `learning_rate` the base rate,
+    `beta1_power` / `beta2_power` the optimizer's non-slot variables (beta^(global_step + 1))."""
+
+    def __init__(self, model, max_to_keep=10):
+        self._model, self.max_to_keep = model, max_to_keep
+
+    def save(self, sess, save_path, global_step=None):
+        from . import checkpoint
+        m = self._model
+        prefix = save_path if global_step is None else "{0}-{1}".format(save_path, int(global_step))
+        t = {}
+        for name, v in m.get_variables(include_optimizer=True).items():
+            t[name] = np.int32(int(v)) if name == "global_step" else np.asarray(v, dtype=np.float32)
+        g = int(m.global_step.eval())
+        t["learning_rate"] = np.float32(m._lr0)
+        t["beta1_power"] = np.float32(0.9 ** (g + 1))
+        t["beta2_power"] = np.float32(0.999 ** (g + 1))
+        checkpoint.write_bundle(prefix, t)
+        checkpoint.update_checkpoint_state(os.path.dirname(os.path.abspath(prefix)), prefix, self.max_to_keep)
+        return prefix
+
+    def restore(self, sess, save_path):
+        from . import checkpoint
+        m = self._model
+        t = checkpoint.read_bundle(save_path)          # ValueError if <save_path>.index is missing (predict_3dpose.py:175)
+        shapes = m.variable_shapes()
+        wanted = [n for n in m.get_variable_names(include_optimizer=True)]
+        missing = [n for n in wanted if n not in t and "Adam" not in n]
+        if missing:
+            raise ValueError("checkpoint {0} lacks variables: {1}".format(save_path, ", ".join(missing[:4])))
+        for n in wanted:
+            if n not in t:
+                continue                                 # a checkpoint saved without optimizer slots keeps the fresh ones
+            a = np.asarray(t[n])
+            if n != "global_step" and tuple(a.shape) != tuple(shapes[n]):
+                raise ValueError("variable {0}: checkpoint shape {1} != model shape {2}".format(n, a.shape, shapes[n]))
+            m.set_variable(n, a.astype(np.float32))      # fp16 checkpoints (--use_fp16) widen here
+        if "learning_rate" in t:
+            m._set_base_learning_rate(float(np.asarray(t["learning_rate"])))
+
+
 class LinearModel(object):
     """A simple Linear+RELU model (linear_model.py:31)."""
 
@@ -107,6 +153,7 @@ class LinearModel(object):
         self.learning_rate = _Evaluable(self._decayed_lr)
         self._names = self._query_names()
         self._init_variables(np.random.RandomState(self._seed))
+        self.saver = _Saver(self, max_to_keep=10)                     # linear_model.py:151
         # data parallel (one process per GPU, torch.distributed for the rendezvous only)
         self.rank, self.world = 0, 1
         if dist is not None:
@@ -164,6 +211,10 @@ class LinearModel(object):
         return {n: self.get_variable(n) for n in self._names
                 if not n.endswith("/gradient") and (include_optimizer or ("Adam" not in n and n != "global_step"))}
 
+    def get_variable_names(self, include_optimizer=False):
+        return [n for n in self._names
+                if not n.endswith("/gradient") and (include_optimizer or ("Adam" not in n and n != "global_step"))]
+
     def get_gradients(self):
         """Gradients of the last training step by variable name (model.gradients, linear_model.py:143-144)."""
         return {n[:-len("/gradient")]: self.get_variable(n) for n in self._names if n.endswith("/gradient")}
@@ -182,6 +233,12 @@ class LinearModel(object):
         with np.load(path) as z:
             for k in z.files:
                 self.set_variable(k.replace("|", "/"), z[k])
+
+    def _set_base_learning_rate(self, lr):
+        """The `learning_rate` variable of a restored checkpoint replaces the constructor's value (linear_model.py:86)."""
+        a = np.array([lr], dtype=np.float32)
+        check(lib.p3d_model_set_param_host(self._handle, b"learning_rate", _lib.np_ptr(a), 1))
+        self._lr0 = float(a[0])
 
     def _decayed_lr(self):
         """tf.train.exponential_decay(lr, global_step, 100000, 0.96) (linear_model.py:86-90)."""

@@ -71,7 +71,8 @@ void p3d_model_destroy(p3d_model* m);
  * "linear_model/w1", "linear_model/b1", "linear_model/batch_normalization/{gamma,beta,moving_mean,
  * moving_variance}", "linear_model/two_linear_<i>/{w2_<i>,b2_<i>,batch_normalization1<i>/...,w3_<i>,
  * b3_<i>,batch_normalization2<i>/...}", "linear_model/w4", "linear_model/b4"; optimizer state as
- * "<var>/Adam" (m) and "<var>/Adam_1" (v); "global_step" (as float).  Weights are [in,out] row-major. */
+ * "<var>/Adam" (m) and "<var>/Adam_1" (v); "global_step" (as float); "learning_rate" (the base
+ * rate variable, src/linear_model.py:86) is settable/gettable by name but not enumerated.  Weights are [in,out] row-major. */
 int p3d_model_set_param_host(p3d_model* m, const char* tf_name, const float* host, size_t n);
 int p3d_model_get_param_host(p3d_model* m, const char* tf_name, float* host, size_t n);
 int p3d_model_param_count(p3d_model* m);
