@@ -8,7 +8,7 @@ A checkpoint `<prefix>` is
     <prefix>.data-00000-of-00001   the raw little-endian tensor bytes, back to back in key order
 plus the text file `checkpoint` in the directory naming the latest prefix (CheckpointState).
 
-TensorFlow is not part of /root/reference (third-party, un-vendored, version unpinned - README.md:23) and is not
+TensorFlow is not part of the reference tree (third-party, un-vendored, version unpinned - README.md:23) and is not
 installable here, and the reference ships no checkpoint: this module follows the published formats (LevelDB table
 format; tensorflow/core/protobuf/tensor_bundle.proto; tensorflow/core/util/tensor_bundle) and is tested by round trips,
 CRC known answers and hand-assembled tables (tests/test_checkpoint_cpu.py) - PARITY UNPINNED against real TF files.
