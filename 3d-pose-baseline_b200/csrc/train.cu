@@ -544,12 +544,14 @@ static bool fused_enabled() {
   static const bool on = [] { const char* e = getenv("P3D_TRAIN_FUSED"); return !(e && e[0] == '0'); }();
   return on;
 }
-// Bucketed gradient all-reduce overlapped with the backward pass (P3D_DP_OVERLAP=1/0 forces it on/off).  Measured on
-// 2 GPUs the four bucket calls cost more than they hide (610 -> 647 us at 4096 poses: the all-reduce of 17 MB between
-// two GPUs is short, and the NCCL CTAs compete with the GEMMs), so the default is one flat call there.
+// Bucketed gradient all-reduce overlapped with the backward pass: opt-in (P3D_DP_OVERLAP=1).  Measured, it costs more
+// than it hides on this node: 2 GPUs 610 -> 647 us and 8 GPUs 622 -> 657 us at 4096 poses, 869 -> 906 us at 32768 -
+// five NCCL launches instead of one, and their CTAs compete with the remaining GEMMs while the 17 MB exchange itself
+// is short over NVSwitch.  The default is one flat call after the backward pass.
 static bool overlap_enabled(int world) {
   static const int force = [] { const char* e = getenv("P3D_DP_OVERLAP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
-  return force >= 0 ? force == 1 : world >= 4;
+  (void)world;
+  return force == 1;
 }
 static inline dim3 colgrid(int cols, int64_t B) { return dim3((cols + 31) / 32, static_cast<unsigned>((B + RCH - 1) / RCH)); }
 static inline int egrid(long long n) { long long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; return static_cast<int>(g < 1 ? 1 : g); }

@@ -431,3 +431,54 @@ class LinearModel(object):
             self.close()
         except Exception:
             pass
+
+
+class PoseBase(object):
+    """Facade with the call signature of the reference's TF2 twin `PoseBase` (src/top_vae_3d_pose/models.py:287-481):
+    `PoseBase(units=1024, input_size=32, output_size=48)`, `model(inputs, training=False)` -> [B, output_size].
+    It is LinearModel(units, 2, residual, batch_norm, max_norm) - the layer chain of `call` (:442-481) - so the VAE
+    scripts can use the B200 lifter as their frozen `pose3d` network.  Variables carry the same names
+    ("linear_model/w1", "linear_model/two_linear_0/w2_0", ...; :295-439) and are reachable as attributes w1, b1,
+    w2_0, ... (NumPy copies) or through `model.linear`.  Only inference (`training=False`, moving statistics) is
+    served: `training=True` in the reference is a forward with batch statistics inside a tf.GradientTape, which
+    belongs to LinearModel.step(isTraining=True) here."""
+
+    def __init__(self, units=1024, input_size=32, output_size=48, **kw):
+        if input_size != 32 or output_size not in (48, 42):
+            raise ValueError("PoseBase lifts 32-d 2D poses to 48-d (or 42-d) 3D poses")
+        self.linear_size, self.input_size, self.output_size = units, input_size, output_size
+        self.linear = LinearModel(units, 2, True, True, True, 64, 1e-3, predict_14=(output_size == 42), **kw)
+
+    def __call__(self, inputs, training=True):
+        return self.call(inputs, training=training)
+
+    def call(self, inputs, training=True):
+        if training:
+            raise NotImplementedError("PoseBase facade serves training=False; train through LinearModel.step")
+        is_torch = hasattr(inputs, "is_cuda")
+        if is_torch:
+            torch = _lib.require_cuda()
+            zeros = torch.zeros((inputs.shape[0], self.output_size), dtype=torch.float32, device=inputs.device)
+        else:
+            zeros = np.zeros((np.asarray(inputs).shape[0], self.output_size), dtype=np.float32)
+        return self.linear.step(None, inputs, zeros, 1.0, isTraining=False)[2]
+
+    def __getattr__(self, name):                      # w1, b1, w2_0, b3_1, w4, ... (models.py:296-439)
+        if name in ("linear", "linear_size", "input_size", "output_size"):
+            raise AttributeError(name)
+        full = None
+        if name in ("w1", "b1", "w4", "b4"):
+            full = "linear_model/" + name
+        elif len(name) == 4 and name[0] in "wb" and name[1] in "23" and name[2] == "_" and name[3] in "01":
+            full = "linear_model/two_linear_{0}/{1}".format(name[3], name)
+        if full is None:
+            raise AttributeError(name)
+        return self.linear.get_variable(full)
+
+    def load_weights(self, values):
+        """{TF variable name: array} (e.g. checkpoint.read_bundle(prefix)) -> the model's variables."""
+        have = set(self.linear.get_variable_names(include_optimizer=True))
+        self.linear.set_variables({k: v for k, v in values.items() if k in have})
+
+    def close(self):
+        self.linear.close()

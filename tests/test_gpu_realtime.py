@@ -112,3 +112,22 @@ def test_predict_14_and_bad_tables(gold, golden_dir):
     with pytest.raises(_lib.P3DError):
         _lifter(model, gold, use3=bad)                   # repeated dimension
     model.close()
+
+
+def test_posebase_facade_matches_linear_model():
+    """src/top_vae_3d_pose/models.py:287-481 - the TF2 twin's call signature over the same kernels."""
+    from p3d.linear_model import PoseBase
+    cfg = M.Config(1024, 2, True, True, True)
+    p = {k: v.astype(np.float32) for k, v in M.init_params(1024, 2, seed=8, bn="trained").items()}
+    pb = PoseBase(units=1024, input_size=32, output_size=48, seed=1)
+    pb.load_weights(p)
+    x = np.random.RandomState(0).normal(size=(33, 32))
+    y = pb(x, training=False)
+    ref = M.forward({k: v.astype(np.float64) for k, v in p.items()}, x.astype(np.float32).astype(np.float64), cfg, training=False)
+    assert y.shape == (33, 48) and rowwise_rel(y, ref).max() <= 1e-2
+    assert np.array_equal(pb.w2_1, p["linear_model/two_linear_1/w2_1"]) and pb.b4.shape == (48,)
+    with pytest.raises(NotImplementedError):
+        pb(x, training=True)
+    with pytest.raises(AttributeError):
+        pb.w5
+    pb.close()
