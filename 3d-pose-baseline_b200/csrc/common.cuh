@@ -203,7 +203,9 @@ struct GemmArgs {
   // must not depend on that predecessor - its first tiles are fetched ahead of the dependency wait
   int pdl = 0;
   void* dbg = nullptr;                // diagnostics: [ctas][8] globaltimer stamps
-  int fused_mode = 0;                 // 0, or 3 / 4: small-batch fused training epilogue (needs M <= 128, unsplit K)
+  int fused_mode = 0;                 // 0, or 3 / 4: small-batch fused training epilogue (needs M <= 128, unsplit K);
+                                      // 5 (any M): C = dh of a hidden layer, colsum += BatchNorm backward sums
+                                      // [sum da | sum da*xhat] of that layer (fused.z/mask/mean/rstd/gamma/beta/sc/dropout)
   FusedTrain fused;
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)

@@ -94,8 +94,10 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 // OUT: 0 = fp32 store, 1 = fp32 reduction (split-K / accumulate), 2 = bf16 (relu, residual in bf16)
-// RES: a residual operand is added;  CS: column sums of the result and its square are accumulated
-template <int OUT, bool RES, bool CS>
+// RES: a residual operand is added;  CS: 1 = column sums of the result and its square are accumulated (BatchNorm
+// statistics of a forward layer); 2 = the result is dh of a hidden layer: column sums of da = dh * dropout * relu'
+// and of da * xhat (the BatchNorm backward sums, what train.cu's bwd_act_kernel computes in a pass of its own)
+template <int OUT, bool RES, int CS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -464,6 +466,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const bool first_split = (blockIdx.z == 0);
     grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
+    const float inv_keep2 = (CS == 2 && p.ft.dropout) ? static_cast<const train::StepScalars*>(p.ft.sc)->inv_keep : 1.f;
     const int et = (warp - 2) * 32 + lane;       // 0..255
     for (int j = et; j < p.bn; j += EPI_THREADS) {
       sbias[j] = (first_split && p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -500,6 +503,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const float4 b4 = lds128(sbias_s + (c0 + cq) * 4);
       float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
       if (fast) {
+        // CS == 2: this chunk's pre-activations / keep-mask and the per-column BatchNorm constants; none of them
+        // depends on the accumulator, so the loads are in flight while the tile is read back from shared memory
+        float4 z4[CS == 2 ? 8 : 1];
+        uchar4 mk[CS == 2 ? 8 : 1];
+        float4 bmu, brs, bga, bbe;
+        if (CS == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            z4[i] = make_float4(0.f, 0.f, 0.f, 0.f); mk[i] = make_uchar4(1, 1, 1, 1);
+            if (m < p.M) {
+              z4[i] = __ldg(reinterpret_cast<const float4*>(p.ft.z + static_cast<size_t>(m) * p.N + n));
+              if (p.ft.dropout) mk[i] = *reinterpret_cast<const uchar4*>(p.ft.mask + static_cast<size_t>(m) * p.N + n);
+            }
+          }
+          bmu = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)); brs = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
+          bga = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)); bbe = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+        }
         float4 t4[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t4[i] = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
@@ -521,7 +542,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int m = mrow0 + 4 * i;
           const bool live = m < p.M;
           float o[4] = {alpha * t4[i].x + b4.x, alpha * t4[i].y + b4.y, alpha * t4[i].z + b4.z, alpha * t4[i].w + b4.w};
-          if (CS) {
+          if (CS == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { const float q = live ? o[j] : 0.f; cs1[j] += q; cs2[j] += q * q; }
           }
@@ -541,6 +562,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (live) *reinterpret_cast<uint2*>(p.out_b + static_cast<size_t>(m) * p.ldob + n) = q;
           } else {
             if (use_res) { o[0] += r4[i].x; o[1] += r4[i].y; o[2] += r4[i].z; o[3] += r4[i].w; }
+            if (CS == 2) {
+              // o = dh of this hidden layer (the gradient that bypassed the block included): pass A of the BatchNorm backward
+              const float zz[4] = {z4[i].x, z4[i].y, z4[i].z, z4[i].w};
+              const unsigned char kk[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+              const float mu[4] = {bmu.x, bmu.y, bmu.z, bmu.w}, rs[4] = {brs.x, brs.y, brs.z, brs.w};
+              const float ga[4] = {bga.x, bga.y, bga.z, bga.w}, be[4] = {bbe.x, bbe.y, bbe.z, bbe.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float xh = (zz[j] - mu[j]) * rs[j];
+                const float act = ga[j] * xh + be[j];
+                float gr = o[j];
+                if (p.ft.dropout) gr = kk[j] ? gr * inv_keep2 : 0.f;
+                const float da = (live && act > 0.f) ? gr : 0.f;
+                cs1[j] += da; cs2[j] += da * xh;
+              }
+            }
             float* crow = p.C + static_cast<size_t>(m) * p.ldc + n;
             if (live) {
               if (OUT == 1) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
@@ -561,7 +598,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int j = 0; j < 4; ++j) {
             if (n + j >= p.N) break;
             float o = alpha * tv[j] + bias[j];
-            if (CS) { cs1[j] += o; cs2[j] += o * o; }
+            if (CS == 1) { cs1[j] += o; cs2[j] += o * o; }     // CS == 2 never takes the ragged path (checked by plan())
             if (OUT == 2) {
               __nv_bfloat16 ob = __float2bfloat16_rn(p.relu ? fmaxf(o, 0.f) : o);
               if (use_res) ob = __float2bfloat16_rn(__bfloat162float(ob) + __bfloat162float(p.res_b[static_cast<size_t>(m) * p.ldrb + n + j]));
@@ -743,7 +780,14 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   d->pdl = g.pdl;
   p.ft = g.fused;
   d->fused_mode = g.fused_mode;
-  if (g.fused_mode) {
+  if (g.fused_mode == 5) {
+    // any batch: the dh-producing GEMM also accumulates the BatchNorm backward sums of the layer it feeds
+    P3D_REQUIRE(g.colsum && g.C && !g.out_bf16 && splits == 1 && !g.accumulate, "tc_gemm: backward-sum epilogue needs colsum, fp32 C, unsplit K");
+    P3D_REQUIRE((g.N % 256) == 0 && g.ldc == g.N && (!g.res || g.ldres == g.N) && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0,
+                "tc_gemm: backward-sum epilogue needs N %% 256 == 0 and dense, aligned C / residual");
+    P3D_REQUIRE(g.fused.z && g.fused.mean && g.fused.rstd && g.fused.gamma && g.fused.beta && g.fused.sc && (!g.fused.dropout || g.fused.mask),
+                "tc_gemm: backward-sum epilogue operands missing");
+  } else if (g.fused_mode) {
     P3D_REQUIRE(g.fused_mode == 3 || g.fused_mode == 4, "tc_gemm: unknown fused mode %d", g.fused_mode);
     P3D_REQUIRE(mt == 1 && splits == 1 && (g.N % 32) == 0 && g.ldc == g.N && !g.out_bf16 && !g.colsum,
                 "tc_gemm: fused training epilogues need M <= 128, N %% 32 == 0, unsplit K, dense C");
@@ -762,22 +806,25 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Params);
   const Params& q = d->p;
   const int out = q.out_b ? 2 : (q.atomic ? 1 : 0);
-  const bool res = q.out_b ? (q.res_b != nullptr) : (q.res != nullptr), cs = q.colsum != nullptr;
+  const bool res = q.out_b ? (q.res_b != nullptr) : (q.res != nullptr);
+  const int cs = q.colsum ? (d->fused_mode == 5 ? 2 : 1) : 0;
   KernelFn fn = nullptr;
 #define P3D_TCG_PICK(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S>;
-  P3D_TCG_PICK(0, false, false) P3D_TCG_PICK(0, false, true) P3D_TCG_PICK(0, true, false) P3D_TCG_PICK(0, true, true)
-  P3D_TCG_PICK(1, false, false) P3D_TCG_PICK(1, true, false)
-  P3D_TCG_PICK(2, false, false) P3D_TCG_PICK(2, true, false)
+  P3D_TCG_PICK(0, false, 0) P3D_TCG_PICK(0, false, 1) P3D_TCG_PICK(0, true, 0) P3D_TCG_PICK(0, true, 1)
+  P3D_TCG_PICK(0, false, 2) P3D_TCG_PICK(0, true, 2)
+  P3D_TCG_PICK(1, false, 0) P3D_TCG_PICK(1, true, 0)
+  P3D_TCG_PICK(2, false, 0) P3D_TCG_PICK(2, true, 0)
 #undef P3D_TCG_PICK
-  if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, false>;
-  if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, false>;
+  if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
+  if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
   static bool attr = false;
   if (!attr) {
-    KernelFn all[] = {tc_gemm_kernel<0, false, false>, tc_gemm_kernel<0, false, true>, tc_gemm_kernel<0, true, false>,
-                      tc_gemm_kernel<0, true, true>, tc_gemm_kernel<1, false, false>, tc_gemm_kernel<1, true, false>,
-                      tc_gemm_kernel<2, false, false>, tc_gemm_kernel<2, true, false>,
-                      tc_gemm_kernel<3, false, false>, tc_gemm_kernel<4, false, false>};
+    KernelFn all[] = {tc_gemm_kernel<0, false, 0>, tc_gemm_kernel<0, false, 1>, tc_gemm_kernel<0, true, 0>,
+                      tc_gemm_kernel<0, true, 1>, tc_gemm_kernel<0, false, 2>, tc_gemm_kernel<0, true, 2>,
+                      tc_gemm_kernel<1, false, 0>, tc_gemm_kernel<1, true, 0>,
+                      tc_gemm_kernel<2, false, 0>, tc_gemm_kernel<2, true, 0>,
+                      tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }

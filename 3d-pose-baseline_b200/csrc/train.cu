@@ -553,6 +553,14 @@ static bool overlap_enabled(int world) {
   (void)world;
   return force == 1;
 }
+// Pass A of the BatchNorm backward inside the dh-producing GEMM's epilogue (tc_gemm fused_mode 5): opt-in
+// (P3D_TRAIN_ACTFUSE=1).  Parity-green, but measured SLOWER on B200: 508 -> 561 us per step at 4096 poses, 2645 -> 3069 us
+// at 32768.  A tc_gemm CTA owns one tile, so nothing overlaps its epilogue; reading z and the keep-mask there (160 KB per
+// tile, a chunk at a time) runs at ~13 GB/s per SM, while bwd_act_kernel streams the same bytes at HBM speed.
+static bool act_fuse_enabled() {
+  static const bool on = [] { const char* e = getenv("P3D_TRAIN_ACTFUSE"); return e && e[0] == '1'; }();
+  return on;
+}
 static inline dim3 colgrid(int cols, int64_t B) { return dim3((cols + 31) / 32, static_cast<unsigned>((B + RCH - 1) / RCH)); }
 static inline int egrid(long long n) { long long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; return static_cast<int>(g < 1 ? 1 : g); }
 
@@ -803,6 +811,21 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   // ---------------------------------------------------------------- backward
   float* G[3] = {w.dh, w.dres, w.dres + bl};
   int cur = 0, keepi = -1;
+  // Pass A of a BatchNorm layer's backward (da = dh * dropout * relu', column sums of da and da * xhat) rides in the
+  // epilogue of the GEMM that produces dh (tc_gemm fused_mode 5): one elementwise pass over [B, L] less per layer.
+  bool act_sums_fused = false;
+  auto fuse_act_sums = [&](GemmArgs& gd, int tl) -> bool {     // gd writes dh of hidden layer tl
+    const Layer& lt = m->layers[tl];
+    if (!tc || !lt.has_bn || (L % 256) != 0 || !act_fuse_enabled()) return false;
+    gd.fused_mode = 5;
+    gd.colsum = w.red + 2ull * tl * L;
+    tcg::FusedTrain& f = gd.fused;
+    f.sc = sc; f.has_bn = 1; f.dropout = dropout ? 1 : 0; f.layer = tl;
+    f.z = w.z + tl * bl; f.mask = maskbuf + tl * bl;
+    f.mean = w.mean + static_cast<size_t>(tl) * L; f.rstd = w.rstd + static_cast<size_t>(tl) * L;
+    f.gamma = m->theta + lt.off_gamma; f.beta = m->theta + lt.off_beta;
+    return true;
+  };
   // Data parallel: a layer's weight gradient (the flat buffer is [all W | b, gamma, beta per layer]) is complete as
   // soon as its GEMM has run, so its all-reduce starts right there on the side stream (a parallel branch of the
   // captured graph) and travels over NVLink while the remaining layers are still being differentiated.
@@ -843,6 +866,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       gd.A = w.dyb; gd.lda = kOutPad;
       gd.B = w.wb + ly.off_w; gd.ldb = kOutPad;
       gd.C = G[cur]; gd.ldc = L; gd.alpha_dev = clip ? scale + nh : nullptr;
+      act_sums_fused = fuse_act_sums(gd, nh - 1);
       P3D_TRY(tcg::gemm(gd, st));
     } else {
       Epilogue e1; e1.alpha_dev = clip ? scale + nh : nullptr;
@@ -858,8 +882,11 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     a.mask = maskbuf + li * bl; a.dz = (tc && ly.has_bn) ? nullptr : w.dz;   // tensor-core + BN: pass B recomputes da
     a.dzb = (tc && !ly.has_bn) ? w.dzb : nullptr; a.sums = w.red + 2ull * li * L; a.sc = sc;
     a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
-    bwd_act_kernel<<<dim3((L / 4 + 31) / 32, static_cast<unsigned>((B + RCH4 - 1) / RCH4)), dim3(32, 8), 0, st>>>(a);
-    P3D_LAUNCH_CHECK();
+    if (!act_sums_fused) {
+      bwd_act_kernel<<<dim3((L / 4 + 31) / 32, static_cast<unsigned>((B + RCH4 - 1) / RCH4)), dim3(32, 8), 0, st>>>(a);
+      P3D_LAUNCH_CHECK();
+    }
+    act_sums_fused = false;
     if (ly.has_bn) {
       P3D_TRY(allreduce(m, a.sums, 2ull * L, ncclDouble, st));
       // dz (bf16 only on the tensor-core path) + dgamma / dbeta.  The sums are already global after the all-reduce,
@@ -902,6 +929,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
         gd.B = w.wb + ly.off_w; gd.ldb = L;
         gd.C = G[nxt]; gd.ldc = L; gd.alpha_dev = clip ? scale + li : nullptr;
         if (add) { gd.res = G[keepi]; gd.ldres = L; }
+        act_sums_fused = fuse_act_sums(gd, li - 1);
         P3D_TRY(tcg::gemm(gd, st));
       } else {
         Epilogue e1; e1.alpha_dev = clip ? scale + li : nullptr;
