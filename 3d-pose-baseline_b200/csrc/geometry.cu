@@ -3,6 +3,8 @@
 //   data_utils.project_to_cameras + transform_world_to_camera + postprocess_3d + normalize_data
 //                                                   (src/data_utils.py:233-280,339-364,474-494)
 //   data_utils.normalize_data / unNormalizeData     (src/data_utils.py:260-311)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "math_hd.h"
 
@@ -63,7 +65,11 @@ static inline int grid_for(long long n, int block = 256) {
 
 // ------------------------------------------------------------------ fused project + normalise
 constexpr int MAXCAMS = 8;
+// Two cameras side by side (.x = camera 2i, .y = camera 2i + 1): every parameter is one 64-bit constant-bank operand of a
+// packed fp32x2 instruction (FFMA2 / FMUL2 / FADD2 on sm_100a).  nT = -T.
+struct CamPair { float2 R[9], nT[3], k[3], p[2], f[2], c[2]; };
 struct FusedArgs {
+  CamPair pair[MAXCAMS / 2];
   CamT<float> cam[MAXCAMS];
   float mean2[32], istd2[32];   // gathered to the used dims
   float mean3[48], istd3[48];
@@ -191,8 +197,151 @@ __global__ void __launch_bounds__(PN_WARPS * 32, PN_BLOCKS) project_normalize_ke
   }
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a): one instruction works on two cameras
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 pk(const float2& c) { return pk(c.x, c.y); }
+__device__ __forceinline__ void unpk(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+
+// The same kernel with the cameras taken two at a time through packed fp32x2 instructions.  The scalar kernel above is
+// issue bound (~400 warp instructions per pose pair at 4 cameras, 187 of them FFMA/FMUL/FADD); pairing the cameras halves
+// the arithmetic instructions and the warp barriers of the 3D repack.  NP = number of camera PAIRS (ncams = 2 NP).
+// Rounding: every operation is the same IEEE fp32 operation as in the scalar kernel, on the same operands.
+template <int NP, bool H2, bool H3>
+__global__ void __launch_bounds__(PN_WARPS * 32, PN_BLOCKS) project_normalize_pair_kernel(const float* __restrict__ world, const __grid_constant__ FusedArgs a,
+                                                                                 float* __restrict__ x2d, float* __restrict__ y3d, long long N) {
+  __shared__ __align__(16) float s_in[PN_WARPS][2 * PN_POSE_PITCH];
+  __shared__ __align__(16) float s_out[PN_WARPS][4][2 * 48 + 4];      // two camera pairs in flight; +4: dump slot
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lp = lane >> 4, j = lane & 15;
+  float* sw = s_in[wib];
+  const int j2 = kJoints2D[j];
+  const bool has3 = j < a.nj3;
+  const int j3 = has3 ? (a.predict_14 ? kJoints3D14[j] : kJoints3D16[j]) : 0;
+  float i2x = a.istd2[2 * j], i2y = a.istd2[2 * j + 1];
+  float n2x = -a.mean2[2 * j] * i2x, n2y = -a.mean2[2 * j + 1] * i2y;
+  float n3[3], i3[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { i3[d] = has3 ? a.istd3[3 * j + d] : 0.f; n3[d] = has3 ? -a.mean3[3 * j + d] * i3[d] : 0.f; }
+  PIN(n2x); PIN(n2y); PIN(i2x); PIN(i2y);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { PIN(n3[d]); PIN(i3[d]); }
+  const f2 I2x = pk(i2x, i2x), I2y = pk(i2y, i2y), N2x = pk(n2x, n2x), N2y = pk(n2y, n2y);
+  const f2 one2 = pk(1.f, 1.f);
+  const int out3 = a.out3;
+  const int o_off = has3 ? lp * out3 + 3 * j : 2 * 48;
+  const int pair_f4 = 2 * out3 / 4;
+  const bool y_vec = H3 && ((reinterpret_cast<uintptr_t>(y3d) & 15) == 0) && (((N * out3) & 3) == 0) && ((2 * out3) % 4 == 0);
+  const long long npairs = (N + 1) / 2;
+  const long long nwarps = static_cast<long long>(gridDim.x) * PN_WARPS;
+  const long long tot_f4 = N * 24;
+  const long long x_cam_stride = N * 32, y_cam_stride = N * out3;
+  const float4* src = reinterpret_cast<const float4*>(world);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int st0 = (lane < 24 ? lane : lane + 1);
+  const int st1 = 32 + lane + 1;
+  long long pair = static_cast<long long>(blockIdx.x) * PN_WARPS + wib;
+  float4 c0 = zero4, c1 = zero4;
+  if (pair < npairs) {
+    const long long b = pair * 48;
+    if (b + lane < tot_f4) c0 = __ldcs(src + b + lane);
+    if (lane < 16 && b + 32 + lane < tot_f4) c1 = __ldcs(src + b + 32 + lane);
+  }
+  int buf = 0;                                               // slabs (buf, buf + 1) belong to the current camera pair
+  for (; pair < npairs; pair += nwarps) {
+    float4 n0 = zero4, n1 = zero4;
+    {
+      const long long b = (pair + nwarps) * 48;
+      if (b + lane < tot_f4) n0 = __ldcs(src + b + lane);
+      if (lane < 16 && b + 32 + lane < tot_f4) n1 = __ldcs(src + b + 32 + lane);
+    }
+    reinterpret_cast<float4*>(sw)[st0] = c0;
+    if (lane < 16) reinterpret_cast<float4*>(sw)[st1] = c1;
+    __syncwarp();
+    const long long p = pair * 2 + lp;
+    const bool live = p < N;
+    const bool full = pair * 2 + 1 < N;
+    const float* w = sw + lp * PN_POSE_PITCH;
+    const float px = w[j2 * 3], py = w[j2 * 3 + 1], pz = w[j2 * 3 + 2];
+    const float qx = w[j3 * 3] - w[0], qy = w[j3 * 3 + 1] - w[1], qz = w[j3 * 3 + 2] - w[2];
+    __syncwarp();
+    const f2 PX = pk(px, px), PY = pk(py, py), PZ = pk(pz, pz);
+    const f2 QX = pk(qx, qx), QY = pk(qy, qy), QZ = pk(qz, qz);
+    float2* xo = reinterpret_cast<float2*>(x2d + p * 32) + j;
+    float* yo = y3d + pair * 2 * out3;
+#pragma unroll
+    for (int cp = 0; cp < NP; ++cp) {
+      const CamPair& C = a.pair[cp];
+      if (H2) {
+        // cameras.project_point_radial (src/cameras.py:39-51) in fp32, cameras 2cp and 2cp+1 in the two halves
+        const f2 dx = add2(PX, pk(C.nT[0])), dy = add2(PY, pk(C.nT[1])), dz = add2(PZ, pk(C.nT[2]));
+        const f2 X0 = fma2(pk(C.R[2]), dz, fma2(pk(C.R[1]), dy, mul2(pk(C.R[0]), dx)));
+        const f2 X1 = fma2(pk(C.R[5]), dz, fma2(pk(C.R[4]), dy, mul2(pk(C.R[3]), dx)));
+        const f2 X2 = fma2(pk(C.R[8]), dz, fma2(pk(C.R[7]), dy, mul2(pk(C.R[6]), dx)));
+        float za, zb;
+        unpk(X2, za, zb);
+        const f2 rz = pk(__fdividef(1.f, za), __fdividef(1.f, zb));          // MUFU.RCP per camera
+        const f2 x = mul2(X0, rz), y = mul2(X1, rz);
+        const f2 r2 = fma2(y, y, mul2(x, x));
+        const f2 radial = fma2(r2, fma2(r2, fma2(r2, pk(C.k[2]), pk(C.k[1])), pk(C.k[0])), one2);
+        const f2 s = add2(radial, fma2(pk(C.p[1]), x, mul2(pk(C.p[0]), y)));
+        const f2 u = fma2(pk(C.f[0]), fma2(pk(C.p[1]), r2, mul2(x, s)), pk(C.c[0]));
+        const f2 v = fma2(pk(C.f[1]), fma2(pk(C.p[0]), r2, mul2(y, s)), pk(C.c[1]));
+        const f2 un = fma2(u, I2x, N2x), vn = fma2(v, I2y, N2y);
+        float ua, ub, va, vb;
+        unpk(un, ua, ub); unpk(vn, va, vb);
+        if (live) {
+          __stcs(xo, make_float2(ua, va));
+          __stcs(xo + x_cam_stride / 2, make_float2(ub, vb));
+        }
+        xo += x_cam_stride;                                  // two camera planes (in float2 units: 2 * stride / 2)
+      }
+      if (H3) {
+        float* soa = s_out[wib][buf];
+        float* sob = s_out[wib][buf + 1];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const f2 r = fma2(pk(C.R[3 * d + 2]), QZ, fma2(pk(C.R[3 * d + 1]), QY, mul2(pk(C.R[3 * d]), QX)));
+          const f2 o = fma2(r, pk(i3[d], i3[d]), pk(n3[d], n3[d]));
+          float oa, ob;
+          unpk(o, oa, ob);
+          soa[o_off + d] = oa; sob[o_off + d] = ob;
+        }
+        __syncwarp();
+        if (y_vec && full) {
+          if (lane < pair_f4) {
+            __stcs(reinterpret_cast<float4*>(yo) + lane, reinterpret_cast<const float4*>(soa)[lane]);
+            __stcs(reinterpret_cast<float4*>(yo + y_cam_stride) + lane, reinterpret_cast<const float4*>(sob)[lane]);
+          }
+        } else {
+          const int tot = (full ? 2 : 1) * out3;
+          for (int i = lane; i < tot; i += 32) { __stcs(yo + i, soa[i]); __stcs(yo + y_cam_stride + i, sob[i]); }
+        }
+        yo += 2 * y_cam_stride;
+        buf ^= 2;              // the other two slabs are free: their readers passed the __syncwarp above
+      }
+    }
+    c0 = n0; c1 = n1;
+  }
+}
+
+static bool pn_packed_enabled() {   // P3D_PN_PACKED=0: scalar kernel for every camera count (A/B measurements)
+  static const bool on = [] { const char* e = getenv("P3D_PN_PACKED"); return !(e && e[0] == '0'); }();
+  return on;
+}
 template <int NC>
 static void launch_project_normalize(int grid, cudaStream_t st, const float* world, const FusedArgs& a, float* x2d, float* y3d, long long N) {
+  if constexpr ((NC % 2) == 0) {
+    if (pn_packed_enabled()) {       // an even number of cameras: two per packed fp32x2 instruction
+      if (x2d && y3d) project_normalize_pair_kernel<NC / 2, true, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
+      else if (x2d) project_normalize_pair_kernel<NC / 2, true, false><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
+      else project_normalize_pair_kernel<NC / 2, false, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
+      return;
+    }
+  }
   if (x2d && y3d) project_normalize_kernel<NC, true, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
   else if (x2d) project_normalize_kernel<NC, true, false><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
   else project_normalize_kernel<NC, false, true><<<grid, PN_WARPS * 32, 0, st>>>(world, a, x2d, y3d, N);
@@ -338,6 +487,13 @@ int p3d_project_normalize(const float* world, const p3d_camera* cams, int ncams,
   memset(&a, 0, sizeof(a));
   a.ncams = ncams;
   for (int c = 0; c < ncams; ++c) a.cam[c] = to_cam<float>(cams[c]);
+  for (int c = 0; c + 1 < ncams; c += 2) {
+    const CamT<float>& A = a.cam[c]; const CamT<float>& B = a.cam[c + 1];
+    CamPair& P = a.pair[c / 2];
+    for (int i = 0; i < 9; ++i) P.R[i] = make_float2(A.R[i], B.R[i]);
+    for (int i = 0; i < 3; ++i) { P.nT[i] = make_float2(-A.Tr[i], -B.Tr[i]); P.k[i] = make_float2(A.k[i], B.k[i]); }
+    for (int i = 0; i < 2; ++i) { P.p[i] = make_float2(A.p[i], B.p[i]); P.f[i] = make_float2(A.f[i], B.f[i]); P.c[i] = make_float2(A.c[i], B.c[i]); }
+  }
   int use[96], n;
   if (x2d) {
     P3D_TRY(use_table(2, 0, use, &n));

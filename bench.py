@@ -247,6 +247,28 @@ def secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr):
                          "frac": round(bts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4), "algorithmic_bytes": bts}}
     ev["workload"] = "un-normalise + (Procrustes) + MPJPE, 4 x 2^20 poses, fp32 kernel"
     out["evaluation"] = ev
+
+    # one realtime frame end to end (openpose_3dpose_sandbox_realtime.py:137-171): host keypoints -> host 3D pose, one
+    # cluster-kernel launch over mapped pinned memory; host wall clock through the public Python call
+    import time
+    from p3d.realtime import RealtimeLifter
+    rs = np.random.RandomState(5)
+    use2 = np.array([0, 1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15, 16, 17, 24, 25, 26, 27, 30, 31, 34, 35, 36, 37, 38, 39, 50, 51, 52, 53, 54, 55])
+    use3 = np.array([c for j in (1, 2, 3, 6, 7, 8, 12, 13, 14, 15, 17, 18, 19, 25, 26, 27) for c in (3 * j, 3 * j + 1, 3 * j + 2)])
+    lifter = RealtimeLifter(model, np.full(64, 500.0), np.full(64, 150.0), use2, m3, s3, use3)
+    frames = rs.uniform(100, 900, size=(64, 36)).tolist()
+    for i in range(200):
+        lifter.step(frames[i % 64])
+    lat = []
+    for i in range(2000):
+        t0 = time.perf_counter()
+        lifter.step(frames[i % 64])
+        lat.append((time.perf_counter() - t0) * 1e6)
+    lat.sort()
+    out["realtime_frame"] = {"workload": "OpenPose keypoints (host) -> normalise -> lifter -> un-normalised 3D pose (host), batch 1",
+                             "launches_per_frame": 1, "p50_us_wall": round(lat[len(lat) // 2], 2), "p99_us_wall": round(lat[int(0.99 * len(lat))], 2),
+                             "frames": len(lat)}
+    lifter.close()
     return out
 
 
