@@ -83,6 +83,7 @@ PROTOTYPES = {
                                      c_void_p, c_void_p]),
     "p3d_similarity_transform_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
+    "p3d_debug_stream_mix": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "p3d_debug_latency_stamps": (c_int, [c_void_p, c_void_p, c_int]),
     "p3d_crc32c": (C.c_uint32, [c_void_p, c_size_t, C.c_uint32]),
     "p3d_realtime_create": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_void_p)]),

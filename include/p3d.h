@@ -217,6 +217,10 @@ int p3d_procrustes_mpjpe_f64(const float* pred_n, const float* gt_n, const doubl
 int p3d_similarity_transform_f64(const double* X, const double* Y, int J, int compute_optimal_scale, int64_t N,
                                  double* d, double* Z, double* T, double* b, double* c, void* stream);
 
+/* Streaming probe (diagnostics): reads n_read_f4 and writes n_write_f4 16-byte words with coalesced streaming accesses;
+ * timed by tools/bench_aux.py to give the HBM ceiling at the read:write mix of the preprocessing / evaluation kernels. */
+int p3d_debug_stream_mix(const void* src, void* dst, int64_t n_read_f4, int64_t n_write_f4, void* stream);
+
 /* ---------------------------------------------------------------- debug / self-test -----------
  * One-CTA tcgen05 GEMM: C[128,N] = A[128,K] * W[N,K]^T, A/W bf16 row-major (K contiguous),
  * K % 64 == 0, N % 16 == 0, N <= 256.  Exercises TMA + UMMA descriptors + TMEM load in isolation. */

@@ -84,6 +84,17 @@ for prec, fn in (("fp32", _lib.lib.p3d_procrustes_mpjpe), ("fp64", _lib.lib.p3d_
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": HBM, "unit": "GB/s", "frac": gbs / HBM,
                                        "algorithmic_bytes": b}}))
 
+# ---- streaming probes: what a plain coalesced stream reaches at each kernel's read:write mix (the measured HBM peak is a 1:1 copy)
+src = torch.empty(N * 1664 // 4, dtype=torch.float32, device="cuda").normal_()
+dst = torch.empty(N * 1664 // 4, dtype=torch.float32, device="cuda")
+for name, rb, wb in (("stream probe 384 B read : 1280 B write per pose (preprocessing 2D+3D mix)", 384, 1280),
+                     ("stream probe 384 B read : 512 B write per pose (preprocessing 2D mix)", 384, 512),
+                     ("stream probe read only (evaluation mix), 4 x 2^20 x 384 B", 1536, 0),
+                     ("stream probe 1:1 copy", 832, 832)):
+    ms = timeit(lambda: _lib.check(_lib.lib.p3d_debug_stream_mix(src.data_ptr(), dst.data_ptr(), N * rb // 16, N * wb // 16, _lib.current_stream())))
+    gbs = N * (rb + wb) / (ms * 1e-3) / 1e9
+    print(json.dumps({"workload": name, "ms": ms, "achieved_gbs": gbs, "frac_of_copy_peak": gbs / HBM}))
+
 # ---- training step (dropout keep 0.5, max_norm, Adam): batch 64 and 4096
 for B, mode in (() if args.no_train else ((64, "bf16"), (4096, "bf16"), (64, "fp32"), (4096, "fp32"))):
     model = LinearModel(1024, 2, True, True, True, B, 1e-3, seed=1, mode=mode)
