@@ -206,6 +206,13 @@ P3D_HD float p3d_rsqrt(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
+P3D_HD float p3d_rsqrt_fast(float x) {          // MUFU.RSQ (~2 ulp), x > 0
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
 P3D_HD float p3d_rcp(float x) {
 #if defined(__CUDA_ARCH__)
   return __frcp_rn(x);
@@ -250,12 +257,20 @@ P3D_HD void kabsch_rotation_f32(const float A[9], float T[9], float& tr) {
       const float ga = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
       float c = 1.f, s = 0.f;
       if (ga * ga > 1e-16f * al * be) {          // already orthogonal to fp32 accuracy otherwise
-        // the angle may be approximate (it only affects the convergence rate); (c,s) must be an exact rotation
-        const float zeta = (be - al) * p3d_rcp_fast(2.f * ga);
-        const float t = (zeta >= 0.f ? 1.f : -1.f) * p3d_rcp_fast(fabsf(zeta) + p3d_sqrt_fast(zeta * zeta + 1.f));
-        c = p3d_rsqrt(t * t + 1.f);
-        s = t * c;
-        tmax = fmaxf(tmax, fabsf(t));
+        // Rotation by theta with tan 2 theta = 2 ga / (be - al), |theta| <= pi/4, from the double-angle form:
+        //   cos 2theta = |a| / r, sin 2theta = sign(a) b / r  (a = be - al, b = 2 ga, r = hypot(a, b)),
+        //   c = sqrt((1 + cos 2theta) / 2), s = sin 2theta / (2 c).
+        // Two dependent MUFU.RSQ instead of the four special-function steps of the tangent form (rcp, sqrt, rcp,
+        // rsqrt): the kernel is bound by the latency of this serial chain (12 rotations per pose), not by issue slots.
+        // (c, s) is a rotation times (1 + O(1e-7)): a uniform scaling of the (p, q) plane, applied to B and V alike,
+        // which the normalisations after the sweeps remove.
+        const float a_ = be - al, b_ = ga + ga;
+        const float rinv = p3d_rsqrt_fast(a_ * a_ + b_ * b_);
+        const float c2 = 0.5f * fabsf(a_) * rinv + 0.5f;
+        const float rs = p3d_rsqrt_fast(c2);
+        c = c2 * rs;
+        s = (a_ >= 0.f ? b_ : -b_) * (0.5f * rinv) * rs;
+        tmax = fmaxf(tmax, fabsf(s));
       }
       P3D_UNROLL
       for (int k = 0; k < 3; ++k) {
@@ -373,19 +388,20 @@ P3D_HD void pose_errors_f32(float (&g)[W], float (&p)[W], const float* sd, const
   const float b = tr * p3d_sqrt_fast(ssx * p3d_rcp(ssy));          // compute_optimal_scale=True (procrustes.py:52-55)
   P3D_UNROLL
   for (int i = 0; i < 9; ++i) T[i] *= b;
+  // e = y_c (bT) - x_c with the subtraction folded into the first multiply-add: three FFMA per coordinate
   if (J0) {
-    const float e0 = (hy[0] * T[0] + hy[1] * T[3] + hy[2] * T[6]) - hx[0];
-    const float e1 = (hy[0] * T[1] + hy[1] * T[4] + hy[2] * T[7]) - hx[1];
-    const float e2 = (hy[0] * T[2] + hy[1] * T[5] + hy[2] * T[8]) - hx[2];
-    dj[0] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
+    const float e0 = fmaf(hy[2], T[6], fmaf(hy[1], T[3], fmaf(hy[0], T[0], -hx[0])));
+    const float e1 = fmaf(hy[2], T[7], fmaf(hy[1], T[4], fmaf(hy[0], T[1], -hx[1])));
+    const float e2 = fmaf(hy[2], T[8], fmaf(hy[1], T[5], fmaf(hy[0], T[2], -hx[2])));
+    dj[0] = p3d_sqrt_fast(fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
   }
   P3D_UNROLL
   for (int j = J0; j < J; ++j) {
     const int k = (j - J0) * 3;
-    const float e0 = (p[k] * T[0] + p[k + 1] * T[3] + p[k + 2] * T[6]) - g[k];
-    const float e1 = (p[k] * T[1] + p[k + 1] * T[4] + p[k + 2] * T[7]) - g[k + 1];
-    const float e2 = (p[k] * T[2] + p[k + 1] * T[5] + p[k + 2] * T[8]) - g[k + 2];
-    dj[j] = p3d_sqrt_fast(e0 * e0 + e1 * e1 + e2 * e2);
+    const float e0 = fmaf(p[k + 2], T[6], fmaf(p[k + 1], T[3], fmaf(p[k], T[0], -g[k])));
+    const float e1 = fmaf(p[k + 2], T[7], fmaf(p[k + 1], T[4], fmaf(p[k], T[1], -g[k + 1])));
+    const float e2 = fmaf(p[k + 2], T[8], fmaf(p[k + 1], T[5], fmaf(p[k], T[2], -g[k + 2])));
+    dj[j] = p3d_sqrt_fast(fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
   }
 }
 

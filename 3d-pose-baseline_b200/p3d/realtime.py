@@ -88,7 +88,14 @@ class RealtimeLifter(object):
         check(lib.p3d_realtime_create(model._handle, _lib.np_ptr(mu2), _lib.np_ptr(sd2), _lib.np_ptr(u2),
                                       _lib.np_ptr(mu3), _lib.np_ptr(sd3), _lib.np_ptr(u3), C.byref(h)))
         self._handle = h
+        # per-frame buffers and their addresses are made once: the frame call itself is ~50 us, ctypes argument
+        # conversion of four fresh arrays was a fifth of that
         self._kp = np.zeros(36, dtype=np.float64)
+        self._enc = np.empty((1, 32), dtype=np.float32)
+        self._y = np.empty((1, self.output_size), dtype=np.float32)
+        self._pose = np.empty((1, 96), dtype=np.float64)
+        self._args = (self._handle, C.c_void_p(self._kp.ctypes.data), C.c_void_p(self._enc.ctypes.data),
+                      C.c_void_p(self._y.ctypes.data), C.c_void_p(self._pose.ctypes.data))
 
     def step(self, xy):
         """One frame: xy = at least 36 coordinates (x0,y0,x1,y1,...; :137-142 use the first 36).
@@ -96,12 +103,11 @@ class RealtimeLifter(object):
         enc_in after :163, the model output of :168 and its unNormalizeData of :171."""
         if len(xy) < 36:
             raise IndexError("need at least 36 keypoint coordinates, got %d" % len(xy))   # the reference's xy[o] raises too
-        self._kp[:] = np.asarray(xy[:36], dtype=np.float64)
-        enc = np.empty((1, 32), dtype=np.float32)
-        y = np.empty((1, self.output_size), dtype=np.float32)
-        pose = np.empty((1, 96), dtype=np.float64)
-        check(lib.p3d_realtime_step_host(self._handle, _lib.np_ptr(self._kp), _lib.np_ptr(enc), _lib.np_ptr(y), _lib.np_ptr(pose)))
-        return enc, y, pose
+        if self._handle is None:
+            raise RuntimeError("RealtimeLifter is closed")
+        self._kp[:] = xy[:36]
+        check(lib.p3d_realtime_step_host(*self._args))
+        return self._enc.copy(), self._y.copy(), self._pose.copy()      # fresh arrays, like the reference returns
 
     def step_batch(self, xy):
         """Many frames at once: xy [B,36] (NumPy or torch CUDA fp64) -> (enc_in [B,32], y [B,out], poses3d [B,96])."""
