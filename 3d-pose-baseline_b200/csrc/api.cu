@@ -396,7 +396,12 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
   if (B == 0) return P3D_OK;
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   const int out = m->out_size;
-  const int64_t chunk = B < 65536 ? B : 65536;
+  // Chunk size of the H2D -> forward -> D2H pipeline (P3D_PIPE_CHUNK overrides).  Measured on 2^20 poses: 65536 and 32768
+  // give 130 M poses/s end to end, 16384 gives 123, 8192 gives 77 (below ~16 K poses the fused kernel no longer fills
+  // the machine).  The steady state is bound by the host->device copy: 320 B per pose at the ~45 GB/s this box's PCIe
+  // link sustains with the device->host copy running the other way (tools/probe_pcie.py: 47.5 GB/s per direction).
+  static const int64_t chunk_max = [] { const char* e = getenv("P3D_PIPE_CHUNK"); const long long v = e ? atoll(e) : 0; return v >= 1024 ? v : 65536LL; }();
+  const int64_t chunk = B < chunk_max ? B : chunk_max;
   if (!m->pipe_streams[0])
     for (int i = 0; i < 3; ++i) P3D_CUDA(cudaStreamCreateWithFlags(&m->pipe_streams[i], cudaStreamNonBlocking));
   if (m->pipe_chunk < chunk) {
