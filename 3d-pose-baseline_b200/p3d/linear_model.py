@@ -294,17 +294,24 @@ class LinearModel(object):
         memory from p3d_host_alloc, which lets the device->host copy overlap the compute)."""
         torch = _lib.require_cuda()
         is_torch = hasattr(encoder_inputs, "is_cuda")
+        # Extension of the reference contract: decoder_outputs=None for isTraining=False (the reference's callers pass
+        # zeros when they only want predictions, openpose_3dpose_sandbox_realtime.py:166-168): nothing is uploaded for
+        # it and the returned loss is 0.
+        no_target = decoder_outputs is None
+        if no_target and isTraining:
+            raise ValueError("decoder_outputs is required for a training step")
         if is_torch:
             x, t = encoder_inputs, decoder_outputs
-            if not (x.is_cuda and t.is_cuda and x.dtype == torch.float32 and t.dtype == torch.float32):
+            if not (x.is_cuda and x.dtype == torch.float32) or not (no_target or (t.is_cuda and t.dtype == torch.float32)):
                 raise ValueError("torch inputs must be float32 CUDA tensors")
-            x, t = x.contiguous(), t.contiguous()
+            x = x.contiguous()
+            t = None if no_target else t.contiguous()
         else:
             x = np.ascontiguousarray(np.asarray(encoder_inputs, dtype=np.float32))   # the TF feed casts fp64 -> fp32
-            t = np.ascontiguousarray(np.asarray(decoder_outputs, dtype=np.float32))
+            t = None if no_target else np.ascontiguousarray(np.asarray(decoder_outputs, dtype=np.float32))
         if x.ndim != 2 or x.shape[1] != self.input_size:
             raise ValueError("encoder_inputs must be [B,%d]" % self.input_size)
-        if t.ndim != 2 or t.shape[1] != self.output_size or t.shape[0] != x.shape[0]:
+        if not no_target and (t.ndim != 2 or t.shape[1] != self.output_size or t.shape[0] != x.shape[0]):
             raise ValueError("decoder_outputs must be [B,%d]" % self.output_size)
         B = int(x.shape[0])
 
@@ -315,7 +322,7 @@ class LinearModel(object):
                     loss = torch.zeros((), dtype=torch.float32, device=x.device)
                     st = _lib.current_stream()
                     check(lib.p3d_model_forward(self._handle, x.data_ptr(), y.data_ptr(), B, st))
-                    if B:
+                    if B and not no_target:
                         check(lib.p3d_model_mse(self._handle, y.data_ptr(), t.data_ptr(), B, loss.data_ptr(), st))
                 return loss, Summary("loss/loss", loss), y
             if out is not None:
@@ -325,8 +332,8 @@ class LinearModel(object):
             else:
                 y = np.empty((B, self.output_size), dtype=np.float32)
             loss = C.c_float(0.0)
-            check(lib.p3d_model_step_eval_host(self._handle, _lib.np_ptr(x), _lib.np_ptr(t), _lib.np_ptr(y),
-                                               C.byref(loss), B))
+            check(lib.p3d_model_step_eval_host(self._handle, _lib.np_ptr(x), None if no_target else _lib.np_ptr(t),
+                                               _lib.np_ptr(y), C.byref(loss), B))
             return np.float32(loss.value), Summary("loss/loss", np.float32(loss.value)), y
 
         # ---- training

@@ -224,3 +224,20 @@ def test_width_4096_stress_config():
     assert_matches_emulation(y, emu, np.sqrt(np.mean(ref ** 2)), ref)
     assert rowwise_rel(y, ref).max() <= 1e-2
     m.close()
+
+
+def test_step_without_target_is_an_extension_of_the_contract():
+    """decoder_outputs=None (isTraining=False only): same predictions, loss 0, nothing uploaded for the target."""
+    cfg = M.Config(1024, 2, True, True, True)
+    m, p = make_model(cfg, seed=2)
+    x, t = synth.mlp_inputs(700, seed=3)
+    l0, _, y0 = m.step(None, x, t, 1.0, isTraining=False)
+    l1, _, y1 = m.step(None, x, None, 1.0, isTraining=False)
+    assert np.array_equal(y0, y1) and float(l1) == 0.0 and float(l0) > 0.0
+    import torch
+    xd = torch.from_numpy(x.astype(np.float32)).cuda()
+    l2, _, y2 = m.step(None, xd, None, 1.0, isTraining=False)
+    assert np.array_equal(y2.cpu().numpy(), y0) and float(l2) == 0.0
+    with pytest.raises(ValueError):
+        m.step(None, x, None, 0.5, isTraining=True)
+    m.close()
