@@ -117,11 +117,24 @@ def cpu_port_rate(sample, threads, repeats=1):
     return sample / best, best
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently run the CPU arm's BLAS on one core:
+    raise the BLAS / OpenMP pools back to every core this process may use.  Returns the thread count in effect."""
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        got = [int(i.get("num_threads", 1)) for i in threadpool_info()]
+        return max(got) if got else want
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", want))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = use_all_host_threads()
     rate0, _ = cpu_port_rate(4096, threads)
     # size the per-step sample so that the whole run stays within ~2 minutes
     budget = 120.0 / max(1, args.steps + args.warmup)
@@ -407,7 +420,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = use_all_host_threads()
         r0, _ = cpu_port_rate(4096, threads)
         sample = int(min(B, max(4096, (r0 * 15.0) // 4096 * 4096)))          # ~15 s of CPU work
         rate, secs = cpu_port_rate(sample, threads)
