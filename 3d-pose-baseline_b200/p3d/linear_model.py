@@ -7,7 +7,9 @@ Differences that are visible to a caller, all additive:
   * `session` is accepted and ignored (there is no tf.Session).
   * keyword-only extras: `mode` ('bf16' tensor-core path, or 'fp32'), `device`, `seed`, `dist`.
   * `step()` also accepts torch CUDA tensors (fp32) and then returns torch tensors without any host copy.
-  * summaries are small `Summary(tag, value)` tuples instead of serialized protobufs.
+  * summaries are `Summary(tag, value)` tuples that serialize to the TF `Summary` protobuf on demand; with a
+    `summaries_dir` the train/test writers append real TensorBoard event files (p3d/summary.py), without one they
+    only collect what they are given.
 """
 from __future__ import annotations
 
@@ -20,8 +22,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import lib, check
-
-Summary = collections.namedtuple("Summary", ["tag", "value"])
+from .summary import FileWriter, Summary
 
 
 class _Evaluable:
@@ -41,7 +42,7 @@ class _Evaluable:
 
 
 class _NullWriter:
-    """train_writer/test_writer placeholders (linear_model.py:81-82): summaries are returned, not logged."""
+    """train_writer/test_writer when no summaries_dir was given: summaries are collected, nothing is written."""
 
     def __init__(self, path):
         self.path = path
@@ -50,7 +51,13 @@ class _NullWriter:
     def add_summary(self, summary, step=None):
         self.events.append((step, summary))
 
-    def add_graph(self, graph):
+    def add_graph(self, graph, global_step=None):
+        pass
+
+    def flush(self):
+        pass
+
+    def close(self):
         pass
 
 
@@ -139,9 +146,12 @@ class LinearModel(object):
         self._handle = None
         if mode not in ("bf16", "fp32"):
             raise ValueError("mode must be 'bf16' or 'fp32'")
-        sd = summaries_dir or ""
-        self.train_writer = _NullWriter(os.path.join(sd, "train"))
-        self.test_writer = _NullWriter(os.path.join(sd, "test"))
+        # Summary writers for train and test runs (linear_model.py:80-82)
+        if summaries_dir:
+            self.train_writer = FileWriter(os.path.join(summaries_dir, "train"))
+            self.test_writer = FileWriter(os.path.join(summaries_dir, "test"))
+        else:
+            self.train_writer, self.test_writer = _NullWriter("train"), _NullWriter("test")
 
         cfg = _lib.Cfg(self.linear_size, self.num_layers, int(self.residual), int(self.batch_norm),
                        int(self.max_norm), int(self.predict_14),
@@ -428,10 +438,19 @@ class LinearModel(object):
         n_batches = n // self.batch_size
         return np.split(encoder_inputs, n_batches), np.split(decoder_outputs, n_batches)
 
+    def err_mm_summary(self, err_mm):
+        """The 'loss/error_mm' summary of linear_model.py:133-134.  The reference evaluates it with
+        `sess.run(model.err_mm_summary, {model.err_mm: total_err})` (predict_3dpose.py:295,322); without a session
+        it is a call: `model.test_writer.add_summary(model.err_mm_summary(total_err), current_step)`."""
+        return Summary("loss/error_mm", np.float32(err_mm))
+
     def close(self):
         if self._handle is not None:
             lib.p3d_model_destroy(self._handle)
             self._handle = None
+        for w in (getattr(self, "train_writer", None), getattr(self, "test_writer", None)):
+            if w is not None:
+                w.close()
 
     def __del__(self):
         try:

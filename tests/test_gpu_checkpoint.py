@@ -51,3 +51,29 @@ def test_saver_roundtrip_continues_training(tmp_path):
         c.saver.restore(None, prefix)
     for m in (a, b, c):
         m.close()
+
+
+def test_summaries_dir_gets_tensorboard_event_files(tmp_path):
+    """The logging calls of the reference's train() (predict_3dpose.py:248-253, :322-323) against a model built with a
+    summaries_dir (linear_model.py:80-82): the event files hold the step() summaries, step by step."""
+    from p3d import LinearModel, summary
+    m = LinearModel(256, 2, True, True, True, 64, 1e-3, str(tmp_path / "log"), mode="fp32", seed=3)
+    x, t = synth.mlp_inputs(64, seed=5)
+    losses, lrs = [], []
+    for _ in range(3):
+        step_loss, loss_summary, lr_summary, _ = m.step(None, x, t, 0.5, isTraining=True)
+        current_step = m.global_step.eval()
+        m.train_writer.add_summary(loss_summary, current_step)
+        m.train_writer.add_summary(lr_summary, current_step)
+        losses.append(np.float32(step_loss)); lrs.append(np.float32(m.learning_rate.eval()))
+    m.test_writer.add_summary(m.err_mm_summary(47.25), current_step)
+    train_path, test_path = m.train_writer.path, m.test_writer.path
+    m.close()
+    assert os.path.dirname(train_path) == str(tmp_path / "log" / "train")
+    ev = summary.read_events(train_path)[1:]
+    assert [e["step"] for e in ev] == [1, 1, 2, 2, 3, 3]
+    assert [e["scalars"]["loss/loss"] for e in ev[0::2]] == losses
+    got_lr = np.array([e["scalars"]["learning_rate/learning_rate"] for e in ev[1::2]], dtype=np.float32)
+    assert np.allclose(got_lr, 1e-3, rtol=1e-4)
+    evt = summary.read_events(test_path)
+    assert evt[1]["step"] == 3 and evt[1]["scalars"] == {"loss/error_mm": 47.25}
