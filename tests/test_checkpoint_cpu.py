@@ -139,3 +139,72 @@ def test_checkpoint_state_file(tmp_path):
     assert not os.path.exists(os.path.join(d, "checkpoint-3.index")) and os.path.exists(os.path.join(d, "checkpoint-4.index"))
     txt = open(os.path.join(d, "checkpoint")).read().splitlines()
     assert txt[0] == 'model_checkpoint_path: "checkpoint-13"' and txt[1] == 'all_model_checkpoint_paths: "checkpoint-4"'
+
+
+def test_bundle_protos_against_the_protobuf_runtime_and_tf_descriptors():
+    """The index entries as Google's protobuf runtime sees them.  TensorShapeProto, VersionDef and the DataType enum are
+    TensorFlow's own generated descriptors (vendored by the `tensorboard` package); BundleHeaderProto / BundleEntryProto
+    are declared here from tensorflow/core/protobuf/tensor_bundle.proto (tensorboard does not ship that one)."""
+    pytest.importorskip("google.protobuf")
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    versions_pb2 = pytest.importorskip("tensorboard.compat.proto.versions_pb2")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="p3d_test/tensor_bundle.proto", package="p3d_test", syntax="proto3")
+    fd.dependency.extend([shape_pb2.DESCRIPTOR.name, types_pb2.DESCRIPTOR.name, versions_pb2.DESCRIPTOR.name])
+    hdr = fd.message_type.add(name="BundleHeaderProto")
+    en = hdr.enum_type.add(name="Endianness")
+    en.value.add(name="LITTLE", number=0); en.value.add(name="BIG", number=1)
+    hdr.field.add(name="num_shards", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    hdr.field.add(name="endianness", number=2, type=F.TYPE_ENUM, label=F.LABEL_OPTIONAL, type_name=".p3d_test.BundleHeaderProto.Endianness")
+    hdr.field.add(name="version", number=3, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name="." + versions_pb2.VersionDef.DESCRIPTOR.full_name)
+    ent = fd.message_type.add(name="BundleEntryProto")
+    ent.field.add(name="dtype", number=1, type=F.TYPE_ENUM, label=F.LABEL_OPTIONAL, type_name="." + types_pb2.DESCRIPTOR.enum_types_by_name["DataType"].full_name)
+    ent.field.add(name="shape", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name="." + shape_pb2.TensorShapeProto.DESCRIPTOR.full_name)
+    ent.field.add(name="shard_id", number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="offset", number=4, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="size", number=5, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    ent.field.add(name="crc32c", number=6, type=F.TYPE_FIXED32, label=F.LABEL_OPTIONAL)
+    pool = descriptor_pool.Default()
+    fdesc = pool.Add(fd) if hasattr(pool, "Add") else pool.AddSerializedFile(fd.SerializeToString())
+    if fdesc is None:
+        fdesc = pool.FindFileByName(fd.name)
+    get = getattr(message_factory, "GetMessageClass", None)
+    Header = get(fdesc.message_types_by_name["BundleHeaderProto"])
+    Entry = get(fdesc.message_types_by_name["BundleEntryProto"])
+
+    # dtype enum numbers of the reader/writer tables are TensorFlow's
+    for np_dt, name in ((np.float32, "DT_FLOAT"), (np.float64, "DT_DOUBLE"), (np.int32, "DT_INT32"), (np.int64, "DT_INT64"),
+                        (np.float16, "DT_HALF")):
+        assert ck._DT_OF[np.dtype(np_dt)] == types_pb2.DataType.Value(name)
+        assert ck._DT[types_pb2.DataType.Value(name)] == np.dtype(np_dt).newbyteorder("<")
+
+    # our bytes -> protobuf runtime
+    for shape, off in (((1024, 48), 0), ((32, 1024), 123456789012), ((), 8), ((7,), 0)):
+        raw = ck._encode_entry(1, shape, off, 4 * int(np.prod(shape)) if shape else 4, 0xDEADBEEF)
+        e = Entry.FromString(raw)
+        assert e.dtype == types_pb2.DT_FLOAT and [d.size for d in e.shape.dim] == list(shape)
+        assert (e.shard_id, e.offset, e.size, e.crc32c) == (0, off, 4 * int(np.prod(shape)) if shape else 4, 0xDEADBEEF)
+        assert not e.shape.unknown_rank
+    # protobuf runtime -> our decoder (the bytes TensorFlow itself would put into the index)
+    e = Entry(dtype=types_pb2.DT_INT32, shard_id=0, offset=77, size=4, crc32c=0x01020304)
+    d = ck._decode_entry(e.SerializeToString())
+    assert (d["dtype"], d["shape"], d["offset"], d["size"], d["crc32c"]) == (3, [], 77, 4, 0x01020304)
+    e = Entry(dtype=types_pb2.DT_HALF, shape=shape_pb2.TensorShapeProto(dim=[shape_pb2.TensorShapeProto.Dim(size=1024),
+                                                                            shape_pb2.TensorShapeProto.Dim(size=1024)]),
+              offset=1 << 33, size=2 << 20, crc32c=0xFFFFFFFF)
+    d = ck._decode_entry(e.SerializeToString())
+    assert (d["dtype"], d["shape"], d["offset"], d["size"], d["crc32c"]) == (19, [1024, 1024], 1 << 33, 2 << 20, 0xFFFFFFFF)
+
+
+def test_written_index_header_parses_as_bundle_header(tmp_path):
+    versions_pb2 = pytest.importorskip("tensorboard.compat.proto.versions_pb2")
+    prefix = ck.write_bundle(os.path.join(str(tmp_path), "c"), {"a": np.zeros(3, np.float32)})
+    items = dict(ck.read_table(prefix + ".index"))
+    hdr = items[b""]
+    # num_shards = 1 (field 1 varint), version (field 3) = VersionDef{producer: 1}
+    fields = list(ck._pb_fields(hdr))
+    assert fields[0] == (1, 0, 1)
+    v = versions_pb2.VersionDef.FromString(fields[1][2])
+    assert fields[1][0] == 3 and v.producer == 1 and v.min_consumer == 0 and list(v.bad_consumers) == []
