@@ -51,6 +51,16 @@ long long launch_count_now();
     if (rc__ != P3D_OK) return rc__; \
   } while (0)
 
+// Function attributes (dynamic shared memory limit, cluster size) belong to the device's context, not to the process:
+// a flag that remembers "already set" must be kept per device, or the second GPU used by one process launches with
+// the 48 KB default and fails.  `if (once.needed()) { ...cudaFuncSetAttribute...; once.mark(); }`
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static unsigned long long bit() { int d = 0; cudaGetDevice(&d); return 1ull << (d & 63); }
+  bool needed() const { return (mask.load(std::memory_order_acquire) & bit()) == 0; }
+  void mark() { mask.fetch_or(bit(), std::memory_order_release); }
+};
+
 constexpr float kBnEps = 1e-3f;       // tf.layers.batch_normalization default
 constexpr float kBnMomentum = 0.99f;  // idem
 constexpr int kIn = 32;               // HUMAN_2D_SIZE (linear_model.py:60)

@@ -565,7 +565,10 @@ __global__ void __launch_bounds__(LNT, 1) latency_cluster_kernel(const LatArgs a
 }
 
 static int launch_latency_cluster(p3d_model* m, const float* x, float* y, const rt::Fused* f, cudaStream_t st) {
-  static int ok = -1;
+  // per device: the attributes live in the device's context and the cluster may be schedulable on one GPU only
+  static int ok_dev[64] = {0};                      // 0 = not probed yet, 1 = usable, 2 = not usable
+  int& okd = ok_dev[m->cfg.device & 63];
+  int ok = okd == 1 ? 1 : (okd == 2 ? 0 : -1);
   if (ok < 0) {
     ok = 0;
     if (cudaFuncSetAttribute(latency_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
@@ -580,6 +583,7 @@ static int launch_latency_cluster(p3d_model* m, const float* x, float* y, const 
     }
     cudaGetLastError();
     if (const char* e = getenv("P3D_LAT_CLUSTER")) ok = ok && atoi(e);
+    okd = ok ? 1 : 2;
   }
   if (!ok || m->layers.size() < 3) return 1;       // caller falls back to the per-layer kernels
   LatArgs a;

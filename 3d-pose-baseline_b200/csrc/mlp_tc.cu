@@ -434,10 +434,10 @@ static int launch_forward(p3d_model* m, const __nv_bfloat16* xb, float* y, int64
   p.L = L; p.nlayers = nlayers; p.out_n = out_n; p.out_valid = m->out_size; p.residual = m->cfg.residual;
   p.ntiles = ntiles; p.B = B; p.act_half_rows = static_cast<long long>(grid) * BM;
   p.bias = m->bias_fold; p.y = y;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     P3D_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = T::SMEM_BYTES; cfg.stream = st;

@@ -352,10 +352,10 @@ int p3d_procrustes_mpjpe_f64(const float* pred_n, const float* gt_n, const doubl
   a.J = nj + a.with_hip;
   a.use_procrustes = use_procrustes ? 1 : 0;
   const size_t smem = sizeof(float) * 2 * PB * (a.width + 1);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
     P3D_CUDA(cudaFuncSetAttribute(procrustes_mpjpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
+    attr.mark();
   }
   const long long ntiles = (N + PB - 1) / PB;
   const int grid = ntiles < 148 * 4 ? (int)ntiles : 148 * 4;
@@ -397,13 +397,13 @@ int p3d_procrustes_mpjpe(const float* pred_n, const float* gt_n, const double* m
   cudaStream_t st = (cudaStream_t)stream;
   if (!predict_14) {
     constexpr int smem = EV_WARPS * 2 * 32 * EvalLayout<48>::PITCH * 4;
-    static bool attr = false;
-    if (!attr) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.needed()) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<48, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr.mark(); }
     mpjpe_f32_kernel<48, 1><<<grid, EV_WARPS * 32, smem, st>>>(pred_n, gt_n, a, dists, joint_sum, N);
   } else {
     constexpr int smem = EV_WARPS * 2 * 32 * EvalLayout<42>::PITCH * 4;
-    static bool attr = false;
-    if (!attr) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<42, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.needed()) { P3D_CUDA(cudaFuncSetAttribute(mpjpe_f32_kernel<42, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr.mark(); }
     mpjpe_f32_kernel<42, 0><<<grid, EV_WARPS * 32, smem, st>>>(pred_n, gt_n, a, dists, joint_sum, N);
   }
   P3D_LAUNCH_CHECK();

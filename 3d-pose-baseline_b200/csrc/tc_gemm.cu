@@ -818,15 +818,15 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
   if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
     KernelFn all[] = {tc_gemm_kernel<0, false, 0>, tc_gemm_kernel<0, false, 1>, tc_gemm_kernel<0, true, 0>,
                       tc_gemm_kernel<0, true, 1>, tc_gemm_kernel<0, false, 2>, tc_gemm_kernel<0, true, 2>,
                       tc_gemm_kernel<1, false, 0>, tc_gemm_kernel<1, true, 0>,
                       tc_gemm_kernel<2, false, 0>, tc_gemm_kernel<2, true, 0>,
                       tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
+    attr.mark();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
