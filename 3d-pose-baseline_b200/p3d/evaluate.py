@@ -4,6 +4,8 @@ as one fused CUDA pass: un-normalise ground truth and prediction, keep [0,1,2] U
 compute_optimal_scale=True, re-applied as b*out.dot(T)+c), per-joint Euclidean error."""
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import _dev, _lib
@@ -51,3 +53,38 @@ def mpjpe(poses3d_n, dec_out_n, data_mean_3d, data_std_3d, procrustes=False, pre
     if return_dists:
         return total_err, joint_err, dists
     return total_err, joint_err
+
+
+def evaluate_batches(sess, model,
+                     data_mean_3d, data_std_3d, dim_to_use_3d, dim_to_ignore_3d,
+                     data_mean_2d, data_std_2d, dim_to_use_2d, dim_to_ignore_2d,
+                     current_step, encoder_inputs, decoder_outputs, current_epoch=0, *, procrustes=False, dist=None):
+    """`predict_3dpose.evaluate_batches` (src/predict_3dpose.py:352-444) with its signature: evaluates a list of
+    batches (what `model.get_all_batches(..., training=False)` returns) and gives back
+    (total_err, joint_err, step_time, loss).  `--procrustes` is a keyword here (the reference reads the global FLAGS,
+    :413), `predict_14` is taken from the model.
+
+    The reference walks the batches one `session.run` at a time with a Python loop per pose inside; here the batches
+    are stacked once, uploaded once, lifted by one `model.step` and scored by one `mpjpe` pass - every pose is
+    independent at test time (moving BatchNorm statistics, keep probability 1), so the numbers are the same.  Like
+    the reference (:410-411,433) every batch must hold `model.batch_size` poses; `loss` is the mean of the per-batch
+    losses, which for equal batches is the mean over all elements."""
+    nbatches = len(encoder_inputs)
+    if nbatches == 0 or len(decoder_outputs) != nbatches:
+        raise ValueError("encoder_inputs / decoder_outputs must be equally long, non-empty lists of batches")
+    for e, d in zip(encoder_inputs, decoder_outputs):
+        assert e.shape[0] == model.batch_size and d.shape[0] == model.batch_size, "every batch must hold model.batch_size poses"
+    torch = _lib.require_cuda()
+    start_time = time.time()
+    dev = torch.device("cuda", model.device)
+    if hasattr(encoder_inputs[0], "is_cuda"):
+        enc, dec = torch.cat(list(encoder_inputs), 0), torch.cat(list(decoder_outputs), 0)
+    else:
+        enc = torch.from_numpy(np.concatenate([np.asarray(e, dtype=np.float32) for e in encoder_inputs], 0)).to(dev)
+        dec = torch.from_numpy(np.concatenate([np.asarray(d, dtype=np.float32) for d in decoder_outputs], 0)).to(dev)
+    loss, _, poses3d = model.step(sess, enc, dec, 1.0, isTraining=False)      # dropout keep probability is 1 at test time
+    total_err, joint_err = mpjpe(poses3d, dec, data_mean_3d, data_std_3d, procrustes=procrustes,
+                                 predict_14=model.predict_14, dist=dist)
+    loss = float(loss)
+    step_time = (time.time() - start_time) / nbatches
+    return total_err, joint_err, step_time, loss

@@ -126,3 +126,38 @@ def test_procrustes_properties_at_full_size():
     gt_t = (0.8 * gt.view(N, 16, 3) @ R).reshape(N, 48).contiguous()
     tot_0, _ = evaluate.mpjpe(gt_t, gt, mean, std, procrustes=True)
     assert tot_0 < 1e-3
+
+
+@pytest.mark.parametrize("p14", [False, True])
+def test_evaluate_batches_signature_and_numbers(p14):
+    """predict_3dpose.evaluate_batches (src/predict_3dpose.py:352-444) through its own signature: the one-pass CUDA form
+    against the reference's loop (one model.step per batch, oracle MPJPE on those predictions)."""
+    from helpers import make_model
+    from oracle import mlp_ref as M
+    from p3d import evaluate
+    cfg = M.Config(256, 2, True, True, True)
+    model, _ = make_model(cfg, seed=4, mode="bf16", batch_size=64, predict_14=p14)
+    use3, ign3 = G.dims_to_use(3, p14)
+    use2, ign2 = G.dims_to_use(2)
+    rng = np.random.RandomState(8)
+    mean3 = rng.normal(0, 50, 96); mean3[:3] = 0
+    std3 = rng.uniform(50, 200, 96)
+    mean2, std2 = rng.uniform(300, 700, 64), rng.uniform(50, 150, 64)
+    nb = 5
+    enc = [rng.normal(size=(64, 32)) for _ in range(nb)]                 # float64, like get_all_batches hands them over
+    dec = [0.3 * rng.normal(size=(64, len(use3))) for _ in range(nb)]
+    for use_proc in (False, True):
+        tot, joint, step_time, loss = evaluate.evaluate_batches(None, model, mean3, std3, use3, ign3, mean2, std2, use2, ign2,
+                                                                0, enc, dec, current_epoch=1, procrustes=use_proc)
+        ref_d, ref_loss = [], 0.0
+        for e, d in zip(enc, dec):
+            step_loss, _, poses3d = model.step(None, e, d, 1.0, isTraining=False)
+            ref_loss += float(step_loss)
+            ref_d.append(G.mpjpe(poses3d, d.astype(np.float32), mean3, std3, ign3, use3, procrustes=use_proc, predict_14=p14))
+        ref_d = np.vstack(ref_d)
+        assert joint.shape == (14 if p14 else 17,) and step_time > 0
+        assert abs(tot - ref_d.mean()) < 1e-3 and np.abs(joint - ref_d.mean(0)).max() < 1e-3
+        assert abs(loss - ref_loss / nb) < 1e-5 * max(1.0, ref_loss / nb)
+    with pytest.raises(AssertionError):
+        evaluate.evaluate_batches(None, model, mean3, std3, use3, ign3, mean2, std2, use2, ign2, 0, [enc[0][:10]], [dec[0][:10]])
+    model.close()
