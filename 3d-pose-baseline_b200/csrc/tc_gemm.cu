@@ -56,6 +56,8 @@ struct Params {
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
   int cn;                   // cluster size along N (1, 2, 4): the CTAs of one M tile share A - each fetches 1/cn of its rows and multicasts
+  int cg;                   // 2 = CTA pair along M (cta_group::2): one 256 x BN tile per pair, each CTA stages its own 128 rows of A
+                            // and HALF of the B tile - a third less L2 -> SM operand traffic per FLOP (1 = single-CTA tiles)
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
@@ -104,7 +106,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
   const int STAGES = p.stages;
-  const int B_BYTES = p.bn * BK * 2;
+  const int cg = p.cg;                           // 1, or 2 = cta_group::2 pair along M (cluster 1 x 2 x 1)
+  const int B_BYTES = (p.bn / cg) * BK * 2;      // this CTA's part of the B tile
   const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_SLOT;
@@ -116,7 +119,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   float* scol = sbias + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = p.cn > 1 ? cluster_ctarank() : 0u;
+  const uint32_t crank = (p.cn > 1 || cg == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cg == 1) || (crank == 0);   // of a pair: issues the MMAs, owns the "full" barriers
   if (warp == 0) P3D_STAMP(0);
   const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
   const int kbeg = blockIdx.z * p.k_per_split;
@@ -130,9 +134,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     mbar_init(accf, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
+  if (warp == 1) {
+    if (cg == 2) { tmem_alloc_2sm(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
+  }
   tc_fence_before();
-  if (p.cn > 1) cluster_sync(); else __syncthreads();     // peers must see initialised barriers before the first multicast
+  if (p.cn > 1 || cg == 2) cluster_sync(); else __syncthreads();     // peers must see initialised barriers before the first multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_launch_dependents();     // the next kernel of a programmatic-dependent chain may start its prologue now
@@ -146,13 +153,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // Every TMA operation of a stage belongs to its own lane and all of them leave in ONE instruction: issuing them
     // one after the other from a single thread costs ~0.12 us each, which is what bounded short-M GEMMs (16 serial
     // k-blocks x 2 operations = 4.3 us of a 7.6 us kernel).  Lanes [0, na) fetch A boxes, lanes [na, na + nb) B boxes.
-    const int na = p.a_mn ? 2 : 1, nb = p.b_mn ? p.bn / 64 : 1;
+    const int na = p.a_mn ? 2 : 1, nb = p.b_mn ? (p.bn / cg) / 64 : 1;
     const bool is_a = lane < na, is_b = lane >= na && lane < na + nb;
     const int bi = lane - na;                                         // B box index of this lane
     const CUtensorMap* my_map = is_a ? &tm_a : &tm_b;
     const bool my_mn = is_a ? (p.a_mn != 0) : (p.b_mn != 0);
     const int my_box = is_a ? lane : bi;
-    const int my_row0 = is_a ? m0 : n0;
+    const int my_row0 = is_a ? m0 : n0 + (cg == 2 ? static_cast<int>(crank) * (p.bn / 2) : 0);   // pair: this CTA's half of the N tile
     const uint32_t a_mask = static_cast<uint16_t>((1u << p.cn) - 1u);
     auto issue = [&](int stage, int k0, bool with_a, bool with_b) {
       if ((is_a && with_a) || (is_b && with_b)) {
@@ -161,16 +168,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (is_a && p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
           const int part = p.a_bytes / p.cn, rows = part / (BK * 2);
           tma_load_2d_mcast(dst + crank * part, my_map, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>(a_mask));
+        } else if (cg == 2) {       // into this CTA's smem, bytes signalled on the LEADER's barrier
+          tma_load_2d_2sm(dst, my_map, &full[stage], c0, c1);
         } else {
           tma_load_2d(dst, my_map, &full[stage], c0, c1);
         }
       }
     };
+    // pair: both CTAs' bytes are accounted on the leader's barrier (the peer's complete_tx may precede this arrive -
+    // the phase cannot complete before the one pending arrival has happened)
+    auto expect = [&](int stage) { if (lane == 0 && leader) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(cg) * bytes); };
     // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const int npre = p.b_independent ? (nk < STAGES ? nk : STAGES) : 0;
     for (int kb = 0; kb < npre; ++kb) {              // ring slots are free on the first pass
-      if (lane == 0) mbar_arrive_expect_tx(&full[kb], bytes);
+      expect(kb);
       __syncwarp();
       issue(kb, kbeg + kb * BK, false, true);
     }
@@ -180,7 +192,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int kb = 0; kb < nk; ++kb) {
       const int k0 = kbeg + kb * BK;
       mbar_wait(&empty[stage], phase ^ 1, 1);
-      if (kb >= npre && lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
+      if (kb >= npre) expect(stage);
       __syncwarp();
       issue(stage, k0, true, kb >= npre);
       if (kb == 3) P3D_STAMP(8);
@@ -190,8 +202,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     P3D_STAMP(2);
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+    // ------------------------------------------------------------ MMA issuer (of a pair: the leader CTA only)
+    if (leader) {
+    const uint32_t idesc = umma_idesc_bf16_f32(BM * cg, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K=16 slice
     int stage = 0; uint32_t phase = 0;
@@ -208,14 +221,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
           const uint64_t bd = p.b_mn ? desc_mn(bb + k * b_step) : desc_k(bb + k * b_step);
-          umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (cg == 2) umma_bf16_ss_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
+        if (cg == 2) umma_commit_2sm(&empty[stage], 0x3);      // frees the slot in both CTAs of the pair
+        else if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
         else umma_commit(&empty[stage]);
-        if (kb == nk - 1) umma_commit(accf);
+        if (kb == nk - 1) { if (cg == 2) umma_commit_2sm(accf, 0x3); else umma_commit(accf); }
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
     }
     P3D_STAMP(4);
   } else {
@@ -640,9 +656,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   if (warp == 2) P3D_STAMP(6);
   tc_fence_before();
-  if (p.cn > 1) cluster_sync(); else __syncthreads();     // no CTA may leave while a peer can still arrive on its barriers
+  if (p.cn > 1 || cg == 2) cluster_sync(); else __syncthreads();     // no CTA may leave while a peer can still arrive on its barriers
   if (warp == 0) P3D_STAMP(7);
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
+  if (warp == 1) {
+    tc_fence_after();
+    if (cg == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.bn)); else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn));
+  }
 }
 
 // ----------------------------------------------------------------------------- MMA issue-rate probe
@@ -758,11 +777,17 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   int cn = 1;
   static const bool mcast = [] { const char* e = getenv("P3D_GEMM_MCAST"); return e && e[0] == '1'; }();
   if (!g.a_mn && mcast) cn = (nt % 4 == 0) ? 4 : ((nt % 2 == 0) ? 2 : 1);
+  // CTA pairs along M (cta_group::2): a 256 x BN tile per pair, each CTA fetches its own A rows and half of the B tile,
+  // i.e. 32 KB instead of 48 KB per k-block at BN = 256.  The large-M GEMMs of the training step are bound by the
+  // L2 -> SM operand stream, which this cuts by a third.  Opt-in (P3D_GEMM_CG2=1) until measured.
+  static const bool pair_env = [] { const char* e = getenv("P3D_GEMM_CG2"); return e && e[0] == '1'; }();
+  int cg = 1;
+  if (pair_env && cn == 1 && !g.pdl && !g.fused_mode && g.M >= 2 * BM && bn >= 128) cg = 2;
   int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
   if (cn > 1) a_rows = (a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn);     // every share is whole 8-row swizzle groups
   if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows / cn));
   else P3D_TRY(make_map(&d->ta, g.A, g.M, g.K, g.lda, BK));
-  if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn));
+  if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn / cg));
   else P3D_TRY(make_map(&d->tb, g.B, g.N, g.K, g.ldb, BK));
   Params& p = d->p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.bn = bn; p.k_per_split = kps; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
@@ -772,8 +797,9 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
   p.cn = cn;
+  p.cg = cg;
   p.a_bytes = a_rows * BK * 2;
-  p.stages = RING_BYTES / (p.a_bytes + bn * BK * 2);
+  p.stages = RING_BYTES / (p.a_bytes + (bn / cg) * BK * 2);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
@@ -795,7 +821,7 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   }
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
-  d->grid = dim3(nt, mt, splits);
+  d->grid = dim3(nt, cg == 2 ? (mt + 1) / 2 * 2 : mt, splits);     // pairs: an odd last M tile gets an all-out-of-range partner
   out->valid = 1;
   return P3D_OK;
 }
@@ -831,9 +857,10 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
-  if (d->p.cn > 1) {
+  if (d->p.cn > 1 || d->p.cg == 2) {
     attrs[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cn; attrs[cfg.numAttrs].val.clusterDim.y = 1; attrs[cfg.numAttrs].val.clusterDim.z = 1;
+    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cn > 1 ? d->p.cn : 1; attrs[cfg.numAttrs].val.clusterDim.y = d->p.cg == 2 ? 2 : 1;
+    attrs[cfg.numAttrs].val.clusterDim.z = 1;
     cfg.attrs = attrs; ++cfg.numAttrs;
   }
   if (d->pdl) {

@@ -99,7 +99,15 @@ if __name__ == "__main__":
         dict(M=100, N=1024, K=64, a_mn=0, b_mn=0, bias=True),
         dict(M=1000, N=1024, K=1024, a_mn=0, b_mn=1, bias=True, colsum=True),              # ragged M
         dict(M=1024, N=1024, K=1000, a_mn=1, b_mn=1, split_k=1),                           # ragged K (batch)
+        # shapes that take the CTA-pair path (cta_group::2) under P3D_GEMM_CG2=1: M >= 256 with a tile >= 128 wide
+        dict(M=2176, N=1024, K=256, a_mn=0, b_mn=1, bias=True, colsum=True),               # BN=128, odd number of M tiles, MN-major B half = one box
+        dict(M=2100, N=1024, K=320, a_mn=0, b_mn=0, res=True),                             # BN=128, ragged M, K-major B half = 64 rows
+        dict(M=4224, N=1024, K=128, a_mn=0, b_mn=1),                                       # BN=256, 33 M tiles
+        dict(M=4096, N=1024, K=48, a_mn=0, b_mn=0),                                        # dh = dy W4^T at batch 4096
+        dict(M=384, N=1024, K=512, a_mn=1, b_mn=1, split_k=1),                             # split-K keeps BN=256; 3 M tiles, MN-major A
+        dict(M=32768, N=1024, K=1024, a_mn=0, b_mn=1, bias=True, colsum=True, time_it=True),
     ]
+    print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"))
     bad = 0
     for c in cases:
         try:
