@@ -427,10 +427,20 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
   int rc = P3D_OK;
   if (!m->pack_valid) rc = prep::prepare(m, s_cmp);
   if (rc == P3D_OK && cudaMemsetAsync(m->pipe_loss, 0, sizeof(double), s_cmp) != cudaSuccess) rc = P3D_ERR_CUDA;
+  // Tapered schedule (P3D_PIPE_TAPER=1, opt-in until measured): the first upload and the last forward + download are
+  // not overlapped by anything, so the pipeline starts and ends on quarter / half chunks (16 K poses still fill the
+  // fused kernel) and runs full chunks in between.
+  static const bool taper = [] { const char* e = getenv("P3D_PIPE_TAPER"); return e && e[0] == '1'; }();
+  int64_t head[2] = {0, 0}, tail[2] = {0, 0};
+  if (taper && B >= 4 * chunk && chunk >= 4096) { head[0] = chunk / 4; head[1] = chunk / 2; tail[0] = chunk / 2; tail[1] = chunk / 4; }
+  const int64_t body_end = B - tail[0] - tail[1];
   int64_t done = 0;
   for (int it = 0; rc == P3D_OK && done < B; ++it) {
     const int slot = it % 3;
-    const int64_t n = (B - done < chunk) ? (B - done) : chunk;
+    int64_t n;
+    if (it < 2 && head[it]) n = head[it];
+    else if (done < body_end) n = (body_end - done < chunk) ? (body_end - done) : chunk;
+    else n = (done == body_end && tail[0]) ? tail[0] : B - done;
     if (it >= 3) cudaStreamWaitEvent(s_in, ev_out[slot], 0);      // slot buffers free again
     cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in);
     if (t_host) cudaMemcpyAsync(m->pipe_t[slot], t_host + done * out, sizeof(float) * n * out, cudaMemcpyHostToDevice, s_in);
