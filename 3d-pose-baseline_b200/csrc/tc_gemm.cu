@@ -99,14 +99,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // RES: a residual operand is added;  CS: 1 = column sums of the result and its square are accumulated (BatchNorm
 // statistics of a forward layer); 2 = the result is dh of a hidden layer: column sums of da = dh * dropout * relu'
 // and of da * xhat (the BatchNorm backward sums, what train.cu's bwd_act_kernel computes in a pass of its own)
-template <int OUT, bool RES, int CS>
+// CG: 1 = single-CTA tiles, 2 = CTA pair along M (cta_group::2).  A template parameter, not a runtime flag: a kernel
+// that CONTAINS cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration"
+// otherwise, even if the instructions are never reached - measured), so the single-CTA kernels must not contain them.
+template <int OUT, bool RES, int CS, int CG = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
   const int STAGES = p.stages;
-  const int cg = p.cg;                           // 1, or 2 = cta_group::2 pair along M (cluster 1 x 2 x 1)
+  constexpr int cg = CG;                         // 1, or 2 = cta_group::2 pair along M (cluster 1 x 2 x 1)
   const int B_BYTES = (p.bn / cg) * BK * 2;      // this CTA's part of the B tile
   const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
@@ -135,7 +138,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (cg == 2) { tmem_alloc_2sm(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish_2sm(); }
+    if constexpr (cg == 2) { tmem_alloc_2sm(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish_2sm(); }
     else { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
   }
   tc_fence_before();
@@ -168,7 +171,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (is_a && p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
           const int part = p.a_bytes / p.cn, rows = part / (BK * 2);
           tma_load_2d_mcast(dst + crank * part, my_map, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>(a_mask));
-        } else if (cg == 2) {       // into this CTA's smem, bytes signalled on the LEADER's barrier
+        } else if constexpr (cg == 2) {       // into this CTA's smem, bytes signalled on the LEADER's barrier
           tma_load_2d_2sm(dst, my_map, &full[stage], c0, c1);
         } else {
           tma_load_2d(dst, my_map, &full[stage], c0, c1);
@@ -221,13 +224,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
           const uint64_t bd = p.b_mn ? desc_mn(bb + k * b_step) : desc_k(bb + k * b_step);
-          if (cg == 2) umma_bf16_ss_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (cg == 2) umma_bf16_ss_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           else umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (cg == 2) umma_commit_2sm(&empty[stage], 0x3);      // frees the slot in both CTAs of the pair
-        else if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
-        else umma_commit(&empty[stage]);
-        if (kb == nk - 1) { if (cg == 2) umma_commit_2sm(accf, 0x3); else umma_commit(accf); }
+        if constexpr (cg == 2) {
+          umma_commit_2sm(&empty[stage], 0x3);      // frees the slot in both CTAs of the pair
+          if (kb == nk - 1) umma_commit_2sm(accf, 0x3);
+        } else {
+          if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
+          else umma_commit(&empty[stage]);
+          if (kb == nk - 1) umma_commit(accf);
+        }
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -660,7 +667,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0) P3D_STAMP(7);
   if (warp == 1) {
     tc_fence_after();
-    if (cg == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.bn)); else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn));
+    if constexpr (cg == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.bn)); else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn));
   }
 }
 
@@ -782,7 +789,7 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   // L2 -> SM operand stream, which this cuts by a third.  Opt-in (P3D_GEMM_CG2=1) until measured.
   static const bool pair_env = [] { const char* e = getenv("P3D_GEMM_CG2"); return e && e[0] == '1'; }();
   int cg = 1;
-  if (pair_env && cn == 1 && !g.pdl && !g.fused_mode && g.M >= 2 * BM && bn >= 128) cg = 2;
+  if (pair_env && cn == 1 && !g.pdl && !g.fused_mode && !g.out_bf16 && g.M >= 2 * BM && bn >= 128) cg = 2;   // the fp32-output epilogues have pair instantiations
   int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
   if (cn > 1) a_rows = (a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn);     // every share is whole 8-row swizzle groups
   if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows / cn));
@@ -836,11 +843,13 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   const int cs = q.colsum ? (d->fused_mode == 5 ? 2 : 1) : 0;
   KernelFn fn = nullptr;
 #define P3D_TCG_PICK(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S>;
-  P3D_TCG_PICK(0, false, 0) P3D_TCG_PICK(0, false, 1) P3D_TCG_PICK(0, true, 0) P3D_TCG_PICK(0, true, 1)
+#define P3D_TCG_PICK2(O, R, S) if (out == O && res == R && cs == S) fn = q.cg == 2 ? tc_gemm_kernel<O, R, S, 2> : tc_gemm_kernel<O, R, S, 1>;
+  P3D_TCG_PICK2(0, false, 0) P3D_TCG_PICK2(0, false, 1) P3D_TCG_PICK2(0, true, 0) P3D_TCG_PICK2(0, true, 1)
   P3D_TCG_PICK(0, false, 2) P3D_TCG_PICK(0, true, 2)
-  P3D_TCG_PICK(1, false, 0) P3D_TCG_PICK(1, true, 0)
+  P3D_TCG_PICK2(1, false, 0) P3D_TCG_PICK2(1, true, 0)
   P3D_TCG_PICK(2, false, 0) P3D_TCG_PICK(2, true, 0)
 #undef P3D_TCG_PICK
+#undef P3D_TCG_PICK2
   if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
   if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
@@ -850,7 +859,9 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
                       tc_gemm_kernel<0, true, 1>, tc_gemm_kernel<0, false, 2>, tc_gemm_kernel<0, true, 2>,
                       tc_gemm_kernel<1, false, 0>, tc_gemm_kernel<1, true, 0>,
                       tc_gemm_kernel<2, false, 0>, tc_gemm_kernel<2, true, 0>,
-                      tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>};
+                      tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>,
+                      tc_gemm_kernel<0, false, 0, 2>, tc_gemm_kernel<0, false, 1, 2>, tc_gemm_kernel<0, true, 0, 2>,
+                      tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr.mark();
   }
