@@ -109,7 +109,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
   const int STAGES = p.stages;
-  constexpr int cg = CG;                         // 1, or 2 = cta_group::2 pair along M (cluster 1 x 2 x 1)
+  constexpr int cg = CG;                         // 1, or 2 = cta_group::2 pair along M (cluster 2 x 1 x 1, M tiles along x)
   const int B_BYTES = (p.bn / cg) * BK * 2;      // this CTA's part of the B tile
   const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
@@ -125,7 +125,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t crank = (p.cn > 1 || cg == 2) ? cluster_ctarank() : 0u;
   const bool leader = (cg == 1) || (crank == 0);   // of a pair: issues the MMAs, owns the "full" barriers
   if (warp == 0) P3D_STAMP(0);
-  const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
+  // pairs: the two CTAs of a cta_group::2 pair must be neighbours in x (a 1 x 2 x 1 cluster is refused at launch as
+  // "cluster misconfiguration" - measured), so the pair kernels take the M tile from blockIdx.x
+  const int n0 = (CG == 2 ? blockIdx.y : blockIdx.x) * p.bn, m0 = (CG == 2 ? blockIdx.x : blockIdx.y) * BM;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
   const int nk = (kend - kbeg + BK - 1) / BK;
@@ -828,7 +830,8 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   }
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
-  d->grid = dim3(nt, cg == 2 ? (mt + 1) / 2 * 2 : mt, splits);     // pairs: an odd last M tile gets an all-out-of-range partner
+  if (cg == 2) d->grid = dim3((mt + 1) / 2 * 2, nt, splits);       // pairs: M tiles along x, an odd last one gets an all-out-of-range partner
+  else d->grid = dim3(nt, mt, splits);
   out->valid = 1;
   return P3D_OK;
 }
@@ -870,7 +873,7 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   cudaLaunchAttribute attrs[2];
   if (d->p.cn > 1 || d->p.cg == 2) {
     attrs[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cn > 1 ? d->p.cn : 1; attrs[cfg.numAttrs].val.clusterDim.y = d->p.cg == 2 ? 2 : 1;
+    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cg == 2 ? 2 : d->p.cn; attrs[cfg.numAttrs].val.clusterDim.y = 1;
     attrs[cfg.numAttrs].val.clusterDim.z = 1;
     cfg.attrs = attrs; ++cfg.numAttrs;
   }
