@@ -303,3 +303,17 @@ def test_predict_14_training_step(mode, B):
     for name in ("linear_model/w4", "linear_model/b4", "linear_model/w1", "linear_model/two_linear_0/w3_0"):
         d = got[name].astype(np.float64) - gr[name]
         assert np.linalg.norm(d) <= tol_g * np.linalg.norm(gr[name]), (name, np.linalg.norm(d) / np.linalg.norm(gr[name]))
+
+
+def test_pair_gemm_variant_is_exact():
+    """The opt-in CTA-pair tc_gemm path (cta_group::2, P3D_GEMM_CG2=1; DESIGN 3.5) against float64 products of the
+    bf16-rounded operands for every operand layout / shape class of the training step.  The switch is read once per
+    process, so the diagnostics run in a process of their own."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, P3D_GEMM_CG2="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_tcgemm.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "TCGEMM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "P3D_GEMM_CG2 = 1" in r.stdout
