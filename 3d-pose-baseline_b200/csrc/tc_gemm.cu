@@ -36,6 +36,11 @@ constexpr int EPI_THREADS = 256;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
 constexpr int BAR_BYTES = 512;               // full[16] | empty[16] | accf | tmem slot
 constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
+// OCC = 2 instantiations: two CTAs share an SM (96 registers per thread, 106.5 KB of shared memory each, BN <= 128 so
+// that two accumulators fit the 512 TMEM columns).  One CTA's prologue / epilogue then runs under the other one's
+// mainloop - the overlap a one-tile-per-CTA kernel cannot give itself.
+constexpr int RING2_BYTES = 3 * (A_BYTES + 128 * BK * 2);  // 96 KB: 3 stages at BN=128, 4 at 64
+constexpr int SMEM2_BYTES = 1024 + RING2_BYTES + BAR_BYTES + 9 * 1024;
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
 
 
@@ -56,6 +61,7 @@ struct Params {
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
   int cn;                   // cluster size along N (1, 2, 4): the CTAs of one M tile share A - each fetches 1/cn of its rows and multicasts
+  int occ;                  // 2 = the OCC = 2 instantiation (two CTAs per SM, small ring); 1 otherwise
   int cg;                   // 2 = CTA pair along M (cta_group::2): one 256 x BN tile per pair, each CTA stages its own 128 rows of A
                             // and HALF of the B tile - a third less L2 -> SM operand traffic per FLOP (1 = single-CTA tiles)
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
@@ -102,8 +108,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // CG: 1 = single-CTA tiles, 2 = CTA pair along M (cta_group::2).  A template parameter, not a runtime flag: a kernel
 // that CONTAINS cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration"
 // otherwise, even if the instructions are never reached - measured), so the single-CTA kernels must not contain them.
-template <int OUT, bool RES, int CS, int CG = 1>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1>
+__global__ void __launch_bounds__(NTHREADS, OCC)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -114,11 +120,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_SLOT;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+  constexpr int RING = (OCC == 2) ? RING2_BYTES : RING_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* accf = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
-  float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES);
+  float* sbias = reinterpret_cast<float*>(smem + RING + BAR_BYTES);
   float* scol = sbias + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -766,10 +773,20 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   if (g.split_k && kblocks <= 4) { while (bn > 64 && mt * ((g.N + bn - 1) / bn) < 100) bn >>= 1; }
   // one short M tile (small-batch inference): 32-wide tiles put twice as many SMs on the weight stream
   if (bn == 64 && !g.b_mn && !g.split_k && mt == 1 && g.N >= 256 && (g.N % 32) == 0) bn = 32;
+  // Two CTAs per SM (P3D_GEMM_OCC2=1, opt-in until measured): for problems with more than one 128-wide tile per SM,
+  // 128 x 128 tiles with a 96 KB ring; the second resident CTA hides the first one's prologue and epilogue.
+  static const bool occ2_env = [] { const char* e = getenv("P3D_GEMM_OCC2"); return e && e[0] == '1'; }();
+  int occ = 1;
+  const int tiles128 = mt * ((g.N + 127) / 128);
+  if (occ2_env && !g.pdl && !g.fused_mode && !g.out_bf16 && bn >= 128 &&
+      (g.split_k ? (kblocks >= 16 && tiles128 >= 32) : (tiles128 > num_sms))) {
+    occ = 2;
+    bn = 128;
+  }
   const int nt = (g.N + bn - 1) / bn;
   int splits = 1;
   if (g.split_k) {
-    splits = num_sms / (mt * nt);
+    splits = occ * num_sms / (mt * nt);
     if (splits < 1) splits = 1;
     if (splits > kblocks) splits = kblocks;
     if (splits > 32) splits = 32;
@@ -791,7 +808,8 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   // L2 -> SM operand stream, which this cuts by a third.  Opt-in (P3D_GEMM_CG2=1) until measured.
   static const bool pair_env = [] { const char* e = getenv("P3D_GEMM_CG2"); return e && e[0] == '1'; }();
   int cg = 1;
-  if (pair_env && cn == 1 && !g.pdl && !g.fused_mode && !g.out_bf16 && g.M >= 2 * BM && bn >= 128) cg = 2;   // the fp32-output epilogues have pair instantiations
+  if (occ == 2) cn = 1;
+  if (pair_env && occ == 1 && cn == 1 && !g.pdl && !g.fused_mode && !g.out_bf16 && g.M >= 2 * BM && bn >= 128) cg = 2;   // the fp32-output epilogues have pair instantiations
   int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
   if (cn > 1) a_rows = (a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn);     // every share is whole 8-row swizzle groups
   if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows / cn));
@@ -807,8 +825,9 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
   p.cn = cn;
   p.cg = cg;
+  p.occ = occ;
   p.a_bytes = a_rows * BK * 2;
-  p.stages = RING_BYTES / (p.a_bytes + (bn / cg) * BK * 2);
+  p.stages = (occ == 2 ? RING2_BYTES : RING_BYTES) / (p.a_bytes + (bn / cg) * BK * 2);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
@@ -846,7 +865,8 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   const int cs = q.colsum ? (d->fused_mode == 5 ? 2 : 1) : 0;
   KernelFn fn = nullptr;
 #define P3D_TCG_PICK(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S>;
-#define P3D_TCG_PICK2(O, R, S) if (out == O && res == R && cs == S) fn = q.cg == 2 ? tc_gemm_kernel<O, R, S, 2> : tc_gemm_kernel<O, R, S, 1>;
+#define P3D_TCG_PICK2(O, R, S) if (out == O && res == R && cs == S) \
+    fn = q.cg == 2 ? tc_gemm_kernel<O, R, S, 2> : (q.occ == 2 ? tc_gemm_kernel<O, R, S, 1, 2> : tc_gemm_kernel<O, R, S, 1>);
   P3D_TCG_PICK2(0, false, 0) P3D_TCG_PICK2(0, false, 1) P3D_TCG_PICK2(0, true, 0) P3D_TCG_PICK2(0, true, 1)
   P3D_TCG_PICK(0, false, 2) P3D_TCG_PICK(0, true, 2)
   P3D_TCG_PICK2(1, false, 0) P3D_TCG_PICK2(1, true, 0)
@@ -866,10 +886,16 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
                       tc_gemm_kernel<0, false, 0, 2>, tc_gemm_kernel<0, false, 1, 2>, tc_gemm_kernel<0, true, 0, 2>,
                       tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    KernelFn two[] = {tc_gemm_kernel<0, false, 0, 1, 2>, tc_gemm_kernel<0, false, 1, 1, 2>, tc_gemm_kernel<0, true, 0, 1, 2>,
+                      tc_gemm_kernel<0, true, 1, 1, 2>, tc_gemm_kernel<1, false, 0, 1, 2>, tc_gemm_kernel<1, true, 0, 1, 2>};
+    for (KernelFn f : two) {
+      P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     attr.mark();
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = d->p.occ == 2 ? SMEM2_BYTES : SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   if (d->p.cn > 1 || d->p.cg == 2) {
     attrs[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;

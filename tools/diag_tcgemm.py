@@ -107,7 +107,7 @@ if __name__ == "__main__":
         dict(M=384, N=1024, K=512, a_mn=1, b_mn=1, split_k=1),                             # split-K keeps BN=256; 3 M tiles, MN-major A
         dict(M=32768, N=1024, K=1024, a_mn=0, b_mn=1, bias=True, colsum=True, time_it=True),
     ]
-    print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"))
+    print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"), " P3D_GEMM_OCC2 =", os.environ.get("P3D_GEMM_OCC2", "0"))
     bad = 0
     for c in cases:
         try:
