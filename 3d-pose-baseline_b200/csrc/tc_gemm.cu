@@ -618,7 +618,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       } else {
-        // ragged / unaligned tile (N = 48 or 42 output layer, odd pitches): element by element, not unrolled
+        // ragged / unaligned tile (N = 48 or 42 output layer, odd pitches): element by element; rows not unrolled.
+        // The column loop IS unrolled: with a runtime column index, bias / tv and - shared with the fast path above -
+        // cs1 / cs2 were demoted to local memory (ncu: STL/LDL of the column sums after every row of the hot loop).
         const float bias[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
@@ -626,9 +628,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (m >= p.M) continue;
           const float4 t = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
           const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (n + j >= p.N) break;
+            if (n + j >= p.N) continue;
             float o = alpha * tv[j] + bias[j];
             if (CS == 1) { cs1[j] += o; cs2[j] += o * o; }     // CS == 2 never takes the ragged path (checked by plan())
             if (OUT == 2) {
