@@ -405,7 +405,8 @@ def run_ours(args):
             _lib.check(lib.p3d_model_forward(model._handle, x1.data_ptr(), y1.data_ptr(), 1, sptr))
         torch.cuda.synchronize()
         ev, wall = [], []
-        for _ in range(2000):
+        LAT_ITERS = 10000                                   # >= 10 k iterations after warm-up
+        for _ in range(LAT_ITERS):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             w0 = time.perf_counter()
             a.record(stream)
@@ -415,7 +416,7 @@ def run_ours(args):
             wall.append((time.perf_counter() - w0) * 1e6)
             ev.append(a.elapsed_time(b) * 1e3)
         lat = {"p50_us_device": statistics.median(ev), "p50_us_wall": statistics.median(wall),
-               "p99_us_wall": sorted(wall)[int(0.99 * len(wall))], "iters": 2000}
+               "p99_us_wall": sorted(wall)[int(0.99 * len(wall))], "iters": LAT_ITERS}
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on the host cores, bounded sample
     cpu = None
