@@ -100,6 +100,25 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def cpu_forward(M, p, x, cfg, threads, block=2048):
+    """The CPU restatement with ALL host threads busy.  One NumPy call per op over the whole sample keeps only the
+    MatMuls multi-threaded (BLAS); the elementwise ops of the graph (BatchNorm, ReLU, residual) run on one core and
+    take most of the time (measured here: 10.0 K poses/s).  At inference every pose is independent, so the sample is
+    cut into row blocks that are pushed through the same forward by a thread pool, BLAS single-threaded inside a block
+    (NumPy releases the GIL in BLAS and ufuncs): 48.6 K poses/s on the same 8 cores, bit-identical outputs."""
+    if threads <= 1 or x.shape[0] <= block:
+        return M.forward(p, x, cfg, training=False)
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return M.forward(p, x, cfg, training=False)
+    from concurrent.futures import ThreadPoolExecutor
+    with threadpool_limits(limits=1):
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            parts = list(ex.map(lambda lo: M.forward(p, x[lo:lo + block], cfg, training=False), range(0, x.shape[0], block)))
+    return np.concatenate(parts, axis=0)
+
+
 def cpu_port_rate(sample, threads, repeats=1):
     """poses/s of the CPU restatement of the reference graph (fp32, op by op like the TF graph)."""
     from oracle import mlp_ref as M
@@ -110,7 +129,7 @@ def cpu_port_rate(sample, threads, repeats=1):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        y = M.forward(p, x, cfg, training=False)
+        y = cpu_forward(M, p, x, cfg, threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert y.dtype == np.float32 and np.isfinite(y).all()
@@ -135,7 +154,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = use_all_host_threads()
-    rate0, _ = cpu_port_rate(4096, threads)
+    rate0, _ = cpu_port_rate(16384, threads)
     # size the per-step sample so that the whole run stays within ~2 minutes
     budget = 120.0 / max(1, args.steps + args.warmup)
     sample = int(min(B_PER_GPU, max(4096, (rate0 * budget) // 4096 * 4096)))
@@ -145,10 +164,10 @@ def run_reference(args):
     p = {k: v.astype(np.float32) for k, v in M.init_params(L, NL, seed=1, bn="trained").items()}
     x, _ = synth.mlp_inputs(sample, seed=0)
     for _ in range(args.warmup):
-        M.forward(p, x, cfg, training=False)
+        cpu_forward(M, p, x, cfg, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        M.forward(p, x, cfg, training=False)
+        cpu_forward(M, p, x, cfg, threads)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {
@@ -158,7 +177,8 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "note": "TensorFlow not installable (no network): NumPy restatement of the "
                    "reference graph (oracle/mlp_ref.py) on the host cores; each step = a bounded sample"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} poses per step (of 2^20), fp32, NumPy/BLAS with {threads} threads"},
+                         "sample": f"{sample} poses per step (of 2^20), fp32, NumPy restatement of the TF graph, row blocks of 2048 "
+                                   f"poses over {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -422,11 +442,12 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = use_all_host_threads()
-        r0, _ = cpu_port_rate(4096, threads)
+        r0, _ = cpu_port_rate(16384, threads)
         sample = int(min(B, max(4096, (r0 * 15.0) // 4096 * 4096)))          # ~15 s of CPU work
         rate, secs = cpu_port_rate(sample, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{sample} of 2^20 poses, fp32 NumPy restatement of the TF graph, {secs:.1f} s"}
+               "sample": f"{sample} of 2^20 poses, fp32 NumPy restatement of the TF graph, row blocks of 2048 poses over "
+                         f"{threads} threads, {secs:.1f} s"}
 
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
