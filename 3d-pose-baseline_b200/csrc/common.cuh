@@ -220,7 +220,7 @@ struct GemmArgs {
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
 // and launched many times while the operand pointers/shapes stay the same.
-struct alignas(64) GemmPlan { unsigned char blob[768]; int valid = 0; };
+struct alignas(64) GemmPlan { unsigned char blob[1024]; int valid = 0; };
 int plan(const GemmArgs& g, GemmPlan* out);
 int launch(const GemmPlan& pl, cudaStream_t st);
 int gemm(const GemmArgs& g, cudaStream_t st);

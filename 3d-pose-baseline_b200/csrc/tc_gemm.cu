@@ -69,6 +69,7 @@ struct Params {
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
   unsigned long long* dbg;  // optional [ctas][16] globaltimer stamps (diagnostics)
   FusedTrain ft;            // OUT = 3 / 4 only
+  int ts;                   // 1 = the TS instantiation (the tile leaves through TMA stores, tm_c describes C)
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = gtime(); } while (0)
@@ -101,6 +102,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // OUT: 0 = fp32 store, 1 = fp32 reduction (split-K / accumulate), 2 = bf16 (relu, residual in bf16)
 // RES: a residual operand is added;  CS: 1 = column sums of the result and its square are accumulated (BatchNorm
 // statistics of a forward layer); 2 = the result is dh of a hidden layer: column sums of da = dh * dropout * relu'
@@ -108,9 +115,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // CG: 1 = single-CTA tiles, 2 = CTA pair along M (cta_group::2).  A template parameter, not a runtime flag: a kernel
 // that CONTAINS cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration"
 // otherwise, even if the instructions are never reached - measured), so the single-CTA kernels must not contain them.
-template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1>
+// TS: the fp32 tile leaves through TMA (cp.async.bulk.tensor / cp.reduce.async.bulk.tensor.add for split-K) instead of
+// per-lane st.global / red.global: 32 x 32 chunks staged row-per-lane (as tcgen05.ld delivers them) in 128B-swizzled
+// smem, edges clipped by the tensor map of C (tm_c; unused by the other instantiations).
+template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1, bool TS = false>
 __global__ void __launch_bounds__(NTHREADS, OCC)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_c, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
@@ -141,6 +152,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+    if constexpr (TS) tma_prefetch_desc(&tm_c);
     // a ring slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.cn); }
     mbar_init(accf, 1);
@@ -504,9 +516,74 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       sbias[j] = (first_split && p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
     }
     named_bar_sync(1, EPI_THREADS);
+    const uint32_t sbias_s = smem_u32(sbias);
+    if constexpr (TS) {
+      // ---------------------------------------------------------- TMA-store epilogue (OUT 0 / 1, no residual, CS 0 / 1)
+      // tcgen05.ld hands every lane one ROW of a 32 x 32 chunk; that is exactly how a TMA box lies in shared memory, so
+      // the chunk is written row-per-lane into a dense 32 x 128 B tile - 16-byte pieces XOR-swizzled by the row (the
+      // SWIZZLE_128B pattern of tm_c: conflict-free for the per-lane st.shared.v4 AND for the column reads of the
+      // statistics below) - and one lane sends it off.  No transpose, no per-lane global store, ragged M / N edges are
+      // clipped by the tensor map.  Two staging tiles per warp: chunk i+1 is written while the TMA engine still reads
+      // chunk i (cp.async.bulk.wait_group.read 1).  Column sums: lane = column, one conflict-free LDS per row.
+      static_assert(OUT <= 1 && !RES && CS <= 1 && CG == 1 && OCC == 1, "TS epilogue: fp32 store / reduction without residual only");
+      uint8_t* stg = smem + (warp - 2) * 8192;               // 2 x 4 KB per warp in the freed operand ring (1024-byte aligned)
+      const uint32_t stg_s = smem_u32(stg);
+      const int row_g = m0 + ew * 32;                        // first global row of this warp's TMEM lane quadrant
+      const int rows_live = (p.M - row_g) < 32 ? (p.M - row_g) : 32;   // <= 0: the whole quadrant lies below the matrix
+      mbar_wait(accf, 0, 3);
+      if (warp == 2) P3D_STAMP(5);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      uint32_t v[32];
+      if (cbeg < cend && n0 + cbeg < p.N) tmem_ld_32x32b_x32(taddr + cbeg, v);
+      int buf = 0;
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        if (n0 + c0 >= p.N) break;     // warp-uniform
+        const bool more = (c0 + 32 < cend) && (n0 + c0 + 32 < p.N);
+        tmem_ld_wait();
+        uint32_t o[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = lds128(sbias_s + (c0 + 4 * j) * 4);      // same address in every lane: broadcast
+          o[4 * j + 0] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 0]) + b4.x);
+          o[4 * j + 1] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 1]) + b4.y);
+          o[4 * j + 2] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 2]) + b4.z);
+          o[4 * j + 3] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 3]) + b4.w);
+        }
+        if (more) tmem_ld_32x32b_x32(taddr + c0 + 32, v);      // in flight while this chunk is staged and sent
+        if (lane == 0) tma_store_wait_read<1>();               // the store issued two chunks ago has read this staging tile
+        __syncwarp();                                          // ... and every lane is done with its column reads of it
+        const uint32_t tb = stg_s + buf * 4096;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(tb + lane * 128 + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && rows_live > 0) {
+          if (OUT == 1) tma_reduce_add_2d(&tm_c, stg + buf * 4096, n0 + c0, row_g);   // split-K / accumulate: C += tile, added in the L2
+          else tma_store_2d(&tm_c, stg + buf * 4096, n0 + c0, row_g);
+          tma_store_commit();
+        }
+        if (CS == 1) {
+          // lane = column c0 + lane: piece (lane / 4) of row r sits at piece index (lane / 4) ^ (r % 8) -> the 32 lanes of
+          // one row read hit 32 different banks.  Rows >= M hold bias (or stale operand rows of a short tile): skipped.
+          float s1 = 0.f, s2 = 0.f;
+          const uint32_t cb = tb + (lane & 3) * 4;
+          const uint32_t piece = static_cast<uint32_t>(lane >> 2);
+#pragma unroll 8
+          for (int r = 0; r < rows_live; ++r) {
+            const float q = lds32(cb + r * 128 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4));
+            s1 += q; s2 += q * q;
+          }
+          scol[ew * 512 + c0 + lane] = s1;                     // this quadrant's partial sums (one writer per slot)
+          scol[ew * 512 + 256 + c0 + lane] = s2;
+        }
+        buf ^= 1;
+      }
+      if (lane == 0) tma_store_wait<0>();                      // all of this warp's stores are complete before the CTA retires
+    } else {
     constexpr int TP = 36;                                   // tile pitch in floats (144 B): conflict-free both ways
     const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
-    const uint32_t sbias_s = smem_u32(sbias);
     const int rg = lane >> 3, cq = (lane & 7) * 4;           // row group (rows rg, rg+4, ...), first of this lane's 4 columns
     const int mrow0 = m0 + ew * 32 + rg;                     // this lane's rows: mrow0 + 4 i
     const bool use_res = RES && (OUT == 2 || first_split);
@@ -659,6 +736,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     }
+    }   // !TS
     if (CS) {
       named_bar_sync(1, EPI_THREADS);
       for (int j = et; j < p.bn; j += EPI_THREADS) {        // one global fp64 atomic per column per CTA
@@ -756,8 +834,24 @@ static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   return P3D_OK;
 }
 
+// fp32 row-major C [M][N] (pitch ldc elements) for the TS epilogue: box 32 columns (128 B) x 32 rows, 128B swizzle;
+// stores / reductions beyond M or N are clipped by the TMA engine
+static int make_map_c(CUtensorMap* out, const float* base, uint64_t N, uint64_t M, uint64_t ldc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return P3D_ERR_CUDA; }
+  cuuint64_t gdim[2] = {N, M};
+  cuuint64_t gstride[1] = {ldc * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (C) failed with CUresult %d", (int)r); return P3D_ERR_CUDA; }
+  return P3D_OK;
+}
+
 // A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
-struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; int pdl; int fused_mode; };
+struct PlanData { CUtensorMap ta, tb, tc; Params p; dim3 grid; int pdl; int fused_mode; };
 static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
 
 int plan(const GemmArgs& g, GemmPlan* out) {
@@ -828,6 +922,13 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.cn = cn;
   p.cg = cg;
   p.occ = occ;
+  // TMA-store epilogue (P3D_GEMM_TMASTORE=1, opt-in until measured on the GPU): fp32 C without a residual operand, pitch and
+  // base such that a tensor map can describe it; everything else keeps the st.global epilogues
+  static const bool ts_env = [] { const char* e = getenv("P3D_GEMM_TMASTORE"); return e && e[0] == '1'; }();
+  p.ts = (ts_env && g.C && !g.out_bf16 && !g.res && !g.fused_mode && cg == 1 && occ == 1 && cn == 1 && (g.ldc % 4) == 0 &&
+          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) ? 1 : 0;
+  memset(&d->tc, 0, sizeof(d->tc));
+  if (p.ts) P3D_TRY(make_map_c(&d->tc, g.C, static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.M), static_cast<uint64_t>(g.ldc)));
   p.a_bytes = a_rows * BK * 2;
   p.stages = (occ == 2 ? RING2_BYTES : RING_BYTES) / (p.a_bytes + (bn / cg) * BK * 2);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -860,7 +961,7 @@ int plan(const GemmArgs& g, GemmPlan* out) {
 int launch(const GemmPlan& pl, cudaStream_t st) {
   P3D_REQUIRE(pl.valid, "tc_gemm: launch of an unplanned GEMM");
   const PlanData* d = reinterpret_cast<const PlanData*>(pl.blob);
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Params);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
   const Params& q = d->p;
   const int out = q.out_b ? 2 : (q.atomic ? 1 : 0);
   const bool res = q.out_b ? (q.res_b != nullptr) : (q.res != nullptr);
@@ -875,6 +976,12 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
   P3D_TCG_PICK(2, false, 0) P3D_TCG_PICK(2, true, 0)
 #undef P3D_TCG_PICK
 #undef P3D_TCG_PICK2
+  if (q.ts) {      // plan() admits only these three combinations
+    fn = nullptr;
+    if (out == 0 && !res && cs == 0) fn = tc_gemm_kernel<0, false, 0, 1, 1, true>;
+    if (out == 0 && !res && cs == 1) fn = tc_gemm_kernel<0, false, 1, 1, 1, true>;
+    if (out == 1 && !res && cs == 0) fn = tc_gemm_kernel<1, false, 0, 1, 1, true>;
+  }
   if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
   if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
@@ -886,7 +993,9 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
                       tc_gemm_kernel<2, false, 0>, tc_gemm_kernel<2, true, 0>,
                       tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>,
                       tc_gemm_kernel<0, false, 0, 2>, tc_gemm_kernel<0, false, 1, 2>, tc_gemm_kernel<0, true, 0, 2>,
-                      tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>};
+                      tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>,
+                      tc_gemm_kernel<0, false, 0, 1, 1, true>, tc_gemm_kernel<0, false, 1, 1, 1, true>,
+                      tc_gemm_kernel<1, false, 0, 1, 1, true>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     KernelFn two[] = {tc_gemm_kernel<0, false, 0, 1, 2>, tc_gemm_kernel<0, false, 1, 1, 2>, tc_gemm_kernel<0, true, 0, 1, 2>,
                       tc_gemm_kernel<0, true, 1, 1, 2>, tc_gemm_kernel<1, false, 0, 1, 2>, tc_gemm_kernel<1, true, 0, 1, 2>};
@@ -912,7 +1021,7 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
     attrs[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs; ++cfg.numAttrs;
   }
-  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->p));
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->tc, d->p));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

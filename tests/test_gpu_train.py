@@ -6,6 +6,8 @@ The kernels compute in fp32: after a few steps the variables agree with the fp64
 relative to each tensor's scale (Adam's m/sqrt(v) normalisation amplifies fp32 rounding of tiny
 gradients, so biases that feed a BatchNorm - whose true gradient is exactly 0, SURVEY appendix A.4 -
 are pinned to "do not move at all")."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -317,3 +319,19 @@ def test_pair_gemm_variant_is_exact():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_tcgemm.py")], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "TCGEMM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "P3D_GEMM_CG2 = 1" in r.stdout
+
+
+@pytest.mark.skipif(os.environ.get("P3D_TEST_EXPERIMENTAL") != "1",
+                    reason="TMA-store epilogue of tc_gemm: written without GPU access at the end of round 1, "
+                           "opt-in and unmeasured - run with P3D_TEST_EXPERIMENTAL=1")
+def test_tma_store_gemm_variant_is_exact():
+    """The opt-in TMA-store epilogue of tc_gemm (P3D_GEMM_TMASTORE=1) against float64 products of the
+    bf16-rounded operands for every shape class of the training step plus its own edge cases (rows / columns clipped by
+    the tensor map of C, split-K through cp.reduce.async.bulk.tensor.add)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, P3D_GEMM_TMASTORE="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_tcgemm.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "TCGEMM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "P3D_GEMM_TMASTORE = 1" in r.stdout

@@ -106,8 +106,13 @@ if __name__ == "__main__":
         dict(M=4096, N=1024, K=48, a_mn=0, b_mn=0),                                        # dh = dy W4^T at batch 4096
         dict(M=384, N=1024, K=512, a_mn=1, b_mn=1, split_k=1),                             # split-K keeps BN=256; 3 M tiles, MN-major A
         dict(M=32768, N=1024, K=1024, a_mn=0, b_mn=1, bias=True, colsum=True, time_it=True),
+        # edges of the TMA-store epilogue (P3D_GEMM_TMASTORE=1): rows and columns clipped by the tensor map of C
+        dict(M=333, N=48, K=128, a_mn=0, b_mn=1, bias=True),                               # N ends inside the second 32-column box
+        dict(M=97, N=1024, K=64, a_mn=0, b_mn=1, bias=True, colsum=True, alpha=0.5),       # last quadrant holds one live row
+        dict(M=1000, N=96, K=1000, a_mn=1, b_mn=1, split_k=1),                             # reduce-add with ragged M, N and K
     ]
-    print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"), " P3D_GEMM_OCC2 =", os.environ.get("P3D_GEMM_OCC2", "0"))
+    print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"), " P3D_GEMM_OCC2 =", os.environ.get("P3D_GEMM_OCC2", "0"),
+          " P3D_GEMM_TMASTORE =", os.environ.get("P3D_GEMM_TMASTORE", "0"))
     bad = 0
     for c in cases:
         try:
