@@ -1,7 +1,11 @@
 // C ABI of libp3d.so (see include/p3d.h): model lifetime, variables by TF name, forward dispatch,
 // the host-buffer evaluation step, misc.
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -21,7 +25,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { launch_counter()->fetch_add(n); }
 long long launch_count_now() { return launch_counter()->load(); }
 
-namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const float*, __nv_bfloat16*, int64_t, cudaStream_t); }
+namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const float*, __nv_bfloat16*, int64_t, cudaStream_t);
+                 int pad_input(const __nv_bfloat16*, __nv_bfloat16*, int64_t, cudaStream_t); }
 namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t);
                int debug_umma_gemm(const void*, const void*, float*, int, int, cudaStream_t); }
 namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
@@ -113,6 +118,91 @@ static void drain() {
   g_pending.clear();
 }
 }  // namespace prof
+
+// ------------------------------------------------------------------ host-side bf16 rounding of the network input
+// The tensor-core forward rounds x to bf16 before the first MatMul (prep::pack_input).  Doing that rounding on the
+// HOST halves the bytes of x that cross PCIe in the host-buffer step (64 instead of 128 B per pose) and changes no
+// result bit: same round-to-nearest-even, NaN -> 0x7FFF, overflow -> inf as cvt.rn.bf16.f32.
+namespace hostpack {
+static inline uint16_t f2bf(uint32_t u) {
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fffu;                  // NaN: the canonical NaN cvt.rn.bf16.f32 produces
+  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+static void convert(const float* src, uint16_t* dst, int64_t n) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(src);
+  for (int64_t i = 0; i < n; ++i) dst[i] = f2bf(u[i]);
+}
+// A small persistent pool: parallel_for splits [0, n) into one contiguous block per participant (the caller is one of
+// them) and returns when all blocks are done.  One job at a time (callers serialise on run_mu).
+class Pool {
+ public:
+  explicit Pool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this, i] { loop(i + 1); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int participants() const { return static_cast<int>(th_.size()) + 1; }
+  void parallel_for(int64_t n, int parts, const std::function<void(int64_t, int64_t)>& fn) {
+    std::lock_guard<std::mutex> run(run_mu_);
+    if (parts > participants()) parts = participants();
+    if (parts <= 1 || n < 4096) { fn(0, n); return; }
+    { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; n_ = n; parts_ = parts; pending_ = parts - 1; ++gen_; }
+    cv_.notify_all();
+    block(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void block(int part) {
+    const int64_t per = (n_ + parts_ - 1) / parts_;
+    const int64_t lo = per * part, hi = lo + per < n_ ? lo + per : n_;
+    if (lo < hi) (*fn_)(lo, hi);
+  }
+  void loop(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      if (stop_) return;
+      if (id >= parts_) continue;           // not part of this job
+      lk.unlock();
+      block(id);
+      lk.lock();
+      if (--pending_ == 0) done_cv_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
+  int64_t n_ = 0;
+  int parts_ = 0, pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+static Pool& pool() {
+  static Pool p([] {
+    const char* e = getenv("P3D_PIPE_THREADS");
+    int t = e ? atoi(e) : 0;
+    if (t <= 0) { t = static_cast<int>(std::thread::hardware_concurrency()); if (t > 8) t = 8; }
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    return t - 1;                            // the caller is the first participant
+  }());
+  return p;
+}
+static void pack(const float* src, uint16_t* dst, int64_t n, int threads) {
+  Pool& p = pool();
+  if (threads <= 0) threads = p.participants();
+  p.parallel_for(n, threads, [&](int64_t lo, int64_t hi) { convert(src + lo, dst + lo, hi - lo); });
+}
+}  // namespace hostpack
 
 static NamedParam* find_param(p3d_model* m, const char* name) {
   for (auto& p : m->params)
@@ -278,6 +368,7 @@ void p3d_model_destroy(p3d_model* m) {
   for (int i = 0; i < 3; ++i) {
     if (m->pipe_streams[i]) cudaStreamDestroy(m->pipe_streams[i]);
     cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
+    if (m->pipe_hx[i]) cudaFreeHost(m->pipe_hx[i]);
   }
   delete m;
 }
@@ -344,6 +435,34 @@ int p3d_model_prepare_inference(p3d_model* m, void* stream) {
   return prep::prepare(m, static_cast<cudaStream_t>(stream));
 }
 
+// packed input buffer [cap][64] bf16 of the tensor-core paths
+static int ensure_xb(p3d_model* m, int64_t B) {
+  if (m->xb_cap < B) {
+    if (m->xb) cudaFree(m->xb);
+    m->xb = nullptr; m->xb_cap = 0;
+    const int64_t cap = B < 1024 ? 1024 : B;
+    P3D_CUDA(cudaMalloc(&m->xb, sizeof(__nv_bfloat16) * 64ull * cap));
+    m->xb_cap = cap;
+  }
+  return P3D_OK;
+}
+// the tensor-core forward from the packed input m->xb
+static int forward_packed(p3d_model* m, float* y, int64_t B, cudaStream_t st) {
+  // One tile of the fused persistent kernel takes ~100 us to walk all layers (a single SM pair streams every
+  // weight); below the crossover (measured: 77 vs 97 us at 4096 poses, 135 vs 101 us at 8192) the per-layer GEMMs,
+  // which split each layer over N, are faster.
+  static const int64_t layered_max = [] { const char* e = getenv("P3D_LAYERED_MAX"); return e ? atoll(e) : 6144LL; }();
+  const bool fused_ok = (m->L % 256) == 0 && m->L <= 4096;
+  if (!fused_ok || B < layered_max) return layered::forward(m, m->xb, y, B, st);
+  return tc::forward_bf16(m, m->xb, y, B, st);
+}
+
+int p3d_host_pack_bf16(const float* src_host, uint16_t* dst_host, int64_t n, int threads) {
+  P3D_REQUIRE(n >= 0 && (n == 0 || (src_host && dst_host)), "host_pack_bf16: bad argument");
+  hostpack::pack(src_host, dst_host, n, threads);
+  return P3D_OK;
+}
+
 int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* stream) {
   P3D_REQUIRE(m && x && y, "forward: null argument");
   P3D_REQUIRE(B >= 0, "forward: negative batch");
@@ -361,21 +480,9 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
     if (B <= kSmallBatchMax) return simt::forward_small(m, x, y, B, st);
     return simt::forward_fp32(m, x, y, B, st);
   }
-  if (m->xb_cap < B) {
-    if (m->xb) cudaFree(m->xb);
-    m->xb = nullptr; m->xb_cap = 0;
-    const int64_t cap = B < 1024 ? 1024 : B;
-    P3D_CUDA(cudaMalloc(&m->xb, sizeof(__nv_bfloat16) * 64ull * cap));
-    m->xb_cap = cap;
-  }
+  P3D_TRY(ensure_xb(m, B));
   P3D_TRY(prep::pack_input(x, m->xb, B, st));
-  // One tile of the fused persistent kernel takes ~100 us to walk all layers (a single SM pair streams every
-  // weight); below the crossover (measured: 77 vs 97 us at 4096 poses, 135 vs 101 us at 8192) the per-layer GEMMs,
-  // which split each layer over N, are faster.
-  static const int64_t layered_max = [] { const char* e = getenv("P3D_LAYERED_MAX"); return e ? atoll(e) : 6144LL; }();
-  const bool fused_ok = (L % 256) == 0 && L <= 4096;
-  if (!fused_ok || B < layered_max) return layered::forward(m, m->xb, y, B, st);
-  return tc::forward_bf16(m, m->xb, y, B, st);
+  return forward_packed(m, y, B, st);
 }
 
 int p3d_model_mse(p3d_model* m, const float* y, const float* t, int64_t B, float* loss, void* stream) {
@@ -408,6 +515,7 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
     for (int i = 0; i < 3; ++i) {
       cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
       m->pipe_x[i] = m->pipe_t[i] = m->pipe_y[i] = nullptr;
+      if (m->pipe_hx[i]) { cudaFreeHost(m->pipe_hx[i]); m->pipe_hx[i] = nullptr; }
     }
     m->pipe_chunk = 0;
     for (int i = 0; i < 3; ++i) {
@@ -416,6 +524,17 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
       P3D_CUDA(cudaMalloc(&m->pipe_y[i], sizeof(float) * chunk * out));
     }
     m->pipe_chunk = chunk;
+  }
+  // P3D_PIPE_XBF16=1 (opt-in until measured on the GPU): x is rounded to bf16 on the host (hostpack, a few threads, one
+  // chunk ahead of the copy engine) into pinned staging and crosses PCIe as 64 B per pose instead of 128 - the upload,
+  // which bounds this path, shrinks from 320 to 256 B per pose.  The forward rounds x to bf16 anyway, so no result bit
+  // changes.  Tensor-core paths only (bf16 mode, width a multiple of 8); single-pose chunks keep the fp32 route.
+  static const bool xbf16_env = [] { const char* e = getenv("P3D_PIPE_XBF16"); return e && e[0] == '1'; }();
+  const bool xbf16 = xbf16_env && m->cfg.mode != P3D_MODE_FP32 && (m->L % 8) == 0;
+  if (xbf16) {
+    for (int i = 0; i < 3; ++i)
+      if (!m->pipe_hx[i]) P3D_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->pipe_hx[i]), sizeof(uint16_t) * m->pipe_chunk * kIn, cudaHostAllocDefault));
+    P3D_TRY(ensure_xb(m, chunk));
   }
   cudaStream_t s_in = m->pipe_streams[0], s_cmp = m->pipe_streams[1], s_out = m->pipe_streams[2];
   cudaEvent_t ev_in[3], ev_cmp[3], ev_out[3];
@@ -441,12 +560,25 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
     if (it < 2 && head[it]) n = head[it];
     else if (done < body_end) n = (body_end - done < chunk) ? (body_end - done) : chunk;
     else n = (done == body_end && tail[0]) ? tail[0] : B - done;
+    const bool xb16 = xbf16 && n >= 2;
+    if (xb16) {
+      // the upload that read this staging slot three chunks ago must be over before the CPU overwrites it; the rounding
+      // of this chunk then runs while the copy engine is busy with the previous one
+      if (it >= 3 && cudaEventSynchronize(ev_in[slot]) != cudaSuccess) { rc = P3D_ERR_CUDA; set_error("step_eval_host: staging slot wait failed"); break; }
+      hostpack::pack(x_host + done * kIn, reinterpret_cast<uint16_t*>(m->pipe_hx[slot]), n * kIn, 0);
+    }
     if (it >= 3) cudaStreamWaitEvent(s_in, ev_out[slot], 0);      // slot buffers free again
-    cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in);
+    if (xb16) cudaMemcpyAsync(m->pipe_x[slot], m->pipe_hx[slot], sizeof(uint16_t) * n * kIn, cudaMemcpyHostToDevice, s_in);
+    else cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in);
     if (t_host) cudaMemcpyAsync(m->pipe_t[slot], t_host + done * out, sizeof(float) * n * out, cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(ev_in[slot], s_in);
     cudaStreamWaitEvent(s_cmp, ev_in[slot], 0);
-    rc = p3d_model_forward(m, m->pipe_x[slot], m->pipe_y[slot], n, s_cmp);
+    if (xb16) {
+      rc = prep::pad_input(reinterpret_cast<const __nv_bfloat16*>(m->pipe_x[slot]), m->xb, n, s_cmp);
+      if (rc == P3D_OK) rc = forward_packed(m, m->pipe_y[slot], n, s_cmp);
+    } else {
+      rc = p3d_model_forward(m, m->pipe_x[slot], m->pipe_y[slot], n, s_cmp);
+    }
     if (rc != P3D_OK) break;
     if (t_host) rc = sqerr_accumulate(m->pipe_y[slot], m->pipe_t[slot], static_cast<size_t>(n) * out, m->pipe_loss, s_cmp);
     cudaEventRecord(ev_cmp[slot], s_cmp);

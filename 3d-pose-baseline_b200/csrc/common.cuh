@@ -273,7 +273,7 @@ struct p3d_model {
   float* pipe_x[3] = {nullptr, nullptr, nullptr};
   float* pipe_t[3] = {nullptr, nullptr, nullptr};
   float* pipe_y[3] = {nullptr, nullptr, nullptr};
-  float* pipe_hx[3] = {nullptr, nullptr, nullptr};   // pinned staging (used when caller memory is pageable)
+  float* pipe_hx[3] = {nullptr, nullptr, nullptr};   // pinned staging: x rounded to bf16 on the host [chunk][32] (P3D_PIPE_XBF16=1)
   float* pipe_hy[3] = {nullptr, nullptr, nullptr};
   float* pipe_ht[3] = {nullptr, nullptr, nullptr};
   double* pipe_loss = nullptr;                        // device accumulator (sum of squared errors)

@@ -48,6 +48,11 @@ int p3d_profile_read(double* ms_total, int64_t* launches);
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 int p3d_host_alloc(void** out_host, size_t bytes);
 int p3d_host_free(void* host);
+/* fp32 -> bf16 on the HOST (round to nearest even, NaN -> 0x7FFF: bit-identical to the device's cvt.rn.bf16.f32), split
+ * over `threads` host threads (<= 0: the library's default, at most 8).  What p3d_model_step_eval_host uses under
+ * P3D_PIPE_XBF16=1 to send the network input - which the tensor-core forward rounds to bf16 anyway - across PCIe at
+ * half the bytes.  No GPU needed. */
+int p3d_host_pack_bf16(const float* src_host, uint16_t* dst_host, int64_t n, int threads);
 
 /* ---------------------------------------------------------------- LinearModel -----------------
  * linear_model.LinearModel.__init__ (src/linear_model.py:34-151): same flags. */
