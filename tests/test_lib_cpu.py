@@ -120,3 +120,29 @@ def test_host_pack_bf16_is_the_device_rounding(threads):
     assert np.array_equal(out[~nan], ref[~nan])
     assert nan.any() and np.all(out[nan] == 0x7FFF)
     _lib.check(_lib.lib.p3d_host_pack_bf16(None, None, 0, threads))         # empty input
+
+
+def test_host_pack_bf16_from_concurrent_callers():
+    """The library's host thread pool runs one job at a time; callers from several threads queue up behind each other
+    (distinct model handles may be driven from distinct threads, include/p3d.h) - no deadlock, no torn output."""
+    import ctypes as C
+    import threading
+
+    import torch
+    from p3d import _lib
+    rng = np.random.RandomState(5)
+    xs = [rng.standard_normal(300000 + 1000 * i).astype(np.float32) for i in range(4)]
+    outs = [np.zeros(x.size, dtype=np.uint16) for x in xs]
+
+    def work(i):
+        for _ in range(10):
+            _lib.check(_lib.lib.p3d_host_pack_bf16(xs[i].ctypes.data_as(C.c_void_p), outs[i].ctypes.data_as(C.c_void_p), xs[i].size, 0))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th)
+    for x, o in zip(xs, outs):
+        assert np.array_equal(o, torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
