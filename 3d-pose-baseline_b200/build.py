@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "p3d", "libp3d.so")
-SOURCES = ["api.cu", "mlp_prep.cu", "mlp_tc.cu", "tc_gemm.cu", "mlp_layered.cu", "mlp_simt.cu", "geometry.cu", "procrustes.cu", "train.cu", "p2p.cu", "realtime.cu"]
+SOURCES = ["api.cu", "mlp_prep.cu", "mlp_tc.cu", "tc_gemm.cu", "mlp_layered.cu", "mlp_simt.cu", "geometry.cu", "procrustes.cu", "train.cu", "p2p.cu", "realtime.cu", "hostpack.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -36,7 +36,7 @@ def _deps():
 
 
 def _compile(src):
-    obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+    obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
     cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, obj, r.returncode, r.stdout + r.stderr
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
     deps = _deps()
     todo = [s for s in SOURCES
-            if force or _newer([os.path.join(CSRC, s)] + deps, os.path.join(BUILD, s.replace(".cu", ".o")))]
+            if force or _newer([os.path.join(CSRC, s)] + deps, os.path.join(BUILD, os.path.splitext(s)[0] + ".o"))]
     logs = []
     if todo:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
                     raise RuntimeError(f"nvcc failed on {src}")
         with open(os.path.join(BUILD, "ptxas.log"), "a" if not force else "w") as f:
             f.write("\n".join(logs))
-    objs = [os.path.join(BUILD, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(BUILD, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     if todo or _newer(objs, OUT):
         cmd = [NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)

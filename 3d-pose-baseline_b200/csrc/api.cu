@@ -1,11 +1,7 @@
 // C ABI of libp3d.so (see include/p3d.h): model lifetime, variables by TF name, forward dispatch,
 // the host-buffer evaluation step, misc.
-#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
-#include <functional>
-#include <mutex>
-#include <thread>
 
 #include "common.cuh"
 
@@ -119,90 +115,7 @@ static void drain() {
 }
 }  // namespace prof
 
-// ------------------------------------------------------------------ host-side bf16 rounding of the network input
-// The tensor-core forward rounds x to bf16 before the first MatMul (prep::pack_input).  Doing that rounding on the
-// HOST halves the bytes of x that cross PCIe in the host-buffer step (64 instead of 128 B per pose) and changes no
-// result bit: same round-to-nearest-even, NaN -> 0x7FFF, overflow -> inf as cvt.rn.bf16.f32.
-namespace hostpack {
-static inline uint16_t f2bf(uint32_t u) {
-  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fffu;                  // NaN: the canonical NaN cvt.rn.bf16.f32 produces
-  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
-}
-static void convert(const float* src, uint16_t* dst, int64_t n) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(src);
-  for (int64_t i = 0; i < n; ++i) dst[i] = f2bf(u[i]);
-}
-// A small persistent pool: parallel_for splits [0, n) into one contiguous block per participant (the caller is one of
-// them) and returns when all blocks are done.  One job at a time (callers serialise on run_mu).
-class Pool {
- public:
-  explicit Pool(int workers) {
-    for (int i = 0; i < workers; ++i) th_.emplace_back([this, i] { loop(i + 1); });
-  }
-  ~Pool() {
-    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-  int participants() const { return static_cast<int>(th_.size()) + 1; }
-  void parallel_for(int64_t n, int parts, const std::function<void(int64_t, int64_t)>& fn) {
-    std::lock_guard<std::mutex> run(run_mu_);
-    if (parts > participants()) parts = participants();
-    if (parts <= 1 || n < 4096) { fn(0, n); return; }
-    { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; n_ = n; parts_ = parts; pending_ = parts - 1; ++gen_; }
-    cv_.notify_all();
-    block(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [this] { return pending_ == 0; });
-    fn_ = nullptr;
-  }
-
- private:
-  void block(int part) {
-    const int64_t per = (n_ + parts_ - 1) / parts_;
-    const int64_t lo = per * part, hi = lo + per < n_ ? lo + per : n_;
-    if (lo < hi) (*fn_)(lo, hi);
-  }
-  void loop(int id) {
-    unsigned long long seen = 0;
-    for (;;) {
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return gen_ != seen; });
-      seen = gen_;
-      if (stop_) return;
-      if (id >= parts_) continue;           // not part of this job
-      lk.unlock();
-      block(id);
-      lk.lock();
-      if (--pending_ == 0) done_cv_.notify_one();
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex mu_, run_mu_;
-  std::condition_variable cv_, done_cv_;
-  const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
-  int64_t n_ = 0;
-  int parts_ = 0, pending_ = 0;
-  unsigned long long gen_ = 0;
-  bool stop_ = false;
-};
-static Pool& pool() {
-  static Pool p([] {
-    const char* e = getenv("P3D_PIPE_THREADS");
-    int t = e ? atoi(e) : 0;
-    if (t <= 0) { t = static_cast<int>(std::thread::hardware_concurrency()); if (t > 8) t = 8; }
-    if (t < 1) t = 1;
-    if (t > 64) t = 64;
-    return t - 1;                            // the caller is the first participant
-  }());
-  return p;
-}
-static void pack(const float* src, uint16_t* dst, int64_t n, int threads) {
-  Pool& p = pool();
-  if (threads <= 0) threads = p.participants();
-  p.parallel_for(n, threads, [&](int64_t lo, int64_t hi) { convert(src + lo, dst + lo, hi - lo); });
-}
-}  // namespace hostpack
+namespace hostpack { void pack(const float* src, uint16_t* dst, int64_t n, int threads); }   // hostpack.cpp
 
 static NamedParam* find_param(p3d_model* m, const char* name) {
   for (auto& p : m->params)
