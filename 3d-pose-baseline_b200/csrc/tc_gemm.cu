@@ -70,6 +70,7 @@ struct Params {
   unsigned long long* dbg;  // optional [ctas][16] globaltimer stamps (diagnostics)
   FusedTrain ft;            // OUT = 3 / 4 only
   int ts;                   // 1 = the TS instantiation (the tile leaves through TMA stores, tm_c describes C)
+  int fi;                   // 1 = the FI instantiation (lean MMA issue path)
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = gtime(); } while (0)
@@ -118,7 +119,8 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 // TS: the fp32 tile leaves through TMA (cp.async.bulk.tensor / cp.reduce.async.bulk.tensor.add for split-K) instead of
 // per-lane st.global / red.global: 32 x 32 chunks staged row-per-lane (as tcgen05.ld delivers them) in 128B-swizzled
 // smem, edges clipped by the tensor map of C (tm_c; unused by the other instantiations).
-template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1, bool TS = false>
+// FI: lean MMA issue path (descriptors advanced by addition instead of rebuilt per k-block), see the MMA warp.
+template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1, bool TS = false, bool FI = false>
 __global__ void __launch_bounds__(NTHREADS, OCC)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_c, const Params p) {
@@ -232,6 +234,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K=16 slice
     int stage = 0; uint32_t phase = 0;
+    if constexpr (FI) {
+      // Lean issue path.  The general loop below rebuilds eight shared-memory descriptors per k-block from byte addresses
+      // (shift, mask, layout bits chosen by runtime flags: ~50 uniform-datapath instructions and 16 R2UR in the SASS) and
+      // walks two jump tables for the diagnostics stamps - ~110 instructions between the barrier and the first
+      // tcgen05.mma, against 4 x 56 cycles of tensor work at N <= 64 (0.14 us of fixed cost per k-block).
+      // A descriptor's start-address field is (address >> 4) in its low 14 bits and every operand address is a multiple
+      // of 16 below 256 KB, so the field advances LINEARLY: one descriptor per operand is built before the loop, a
+      // k-block adds stage * (slot >> 4), a K = 16 slice adds (step >> 4) - no carry can leave the field.
+      static_assert(CG == 1, "the lean issue path is single-CTA");
+      const uint64_t a0 = p.a_mn ? desc_mn(a_base) : desc_k(a_base), b0 = p.b_mn ? desc_mn(b_base) : desc_k(b_base);
+      const uint32_t a_slot16 = static_cast<uint32_t>(A_SLOT) >> 4, b_slot16 = static_cast<uint32_t>(B_BYTES) >> 4;
+      const uint32_t a_k16 = a_step >> 4, b_k16 = b_step >> 4;
+      const uint16_t cmask = static_cast<uint16_t>((1u << p.cn) - 1u);
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full[stage], phase, 2);
+        if (p.dbg) { if (kb == 0) P3D_STAMP(3); if (kb == 4) P3D_STAMP(11); if (kb == 8) P3D_STAMP(12); if (kb == 12) P3D_STAMP(13); }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = a0 + static_cast<uint32_t>(stage) * a_slot16, bd = b0 + static_cast<uint32_t>(stage) * b_slot16;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(tmem_base, ad + static_cast<uint32_t>(k) * a_k16, bd + static_cast<uint32_t>(k) * b_k16, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (p.cn > 1) umma_commit_mcast(&empty[stage], cmask);
+          else umma_commit(&empty[stage]);
+          if (kb == nk - 1) umma_commit(accf);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(&full[stage], phase, 2);
       if (kb == 0) P3D_STAMP(3);
@@ -927,6 +959,9 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   static const bool ts_env = [] { const char* e = getenv("P3D_GEMM_TMASTORE"); return e && e[0] == '1'; }();
   p.ts = (ts_env && g.C && !g.out_bf16 && !g.res && !g.fused_mode && cg == 1 && occ == 1 && cn == 1 && (g.ldc % 4) == 0 &&
           (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) ? 1 : 0;
+  // Lean MMA issue path (P3D_GEMM_FASTISSUE=1, opt-in until measured on the GPU): single-CTA, one-CTA-per-SM kernels
+  static const bool fi_env = [] { const char* e = getenv("P3D_GEMM_FASTISSUE"); return e && e[0] == '1'; }();
+  p.fi = (fi_env && cg == 1 && occ == 1 && g.fused_mode != 5) ? 1 : 0;
   memset(&d->tc, 0, sizeof(d->tc));
   if (p.ts) P3D_TRY(make_map_c(&d->tc, g.C, static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.M), static_cast<uint64_t>(g.ldc)));
   p.a_bytes = a_rows * BK * 2;
@@ -978,12 +1013,17 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
 #undef P3D_TCG_PICK2
   if (q.ts) {      // plan() admits only these three combinations
     fn = nullptr;
-    if (out == 0 && !res && cs == 0) fn = tc_gemm_kernel<0, false, 0, 1, 1, true>;
-    if (out == 0 && !res && cs == 1) fn = tc_gemm_kernel<0, false, 1, 1, 1, true>;
-    if (out == 1 && !res && cs == 0) fn = tc_gemm_kernel<1, false, 0, 1, 1, true>;
+    if (out == 0 && !res && cs == 0) fn = q.fi ? tc_gemm_kernel<0, false, 0, 1, 1, true, true> : tc_gemm_kernel<0, false, 0, 1, 1, true>;
+    if (out == 0 && !res && cs == 1) fn = q.fi ? tc_gemm_kernel<0, false, 1, 1, 1, true, true> : tc_gemm_kernel<0, false, 1, 1, 1, true>;
+    if (out == 1 && !res && cs == 0) fn = q.fi ? tc_gemm_kernel<1, false, 0, 1, 1, true, true> : tc_gemm_kernel<1, false, 0, 1, 1, true>;
+  } else if (q.fi) {
+#define P3D_TCG_PICKF(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S, 1, 1, false, true>;
+    P3D_TCG_PICKF(0, false, 0) P3D_TCG_PICKF(0, false, 1) P3D_TCG_PICKF(0, true, 0) P3D_TCG_PICKF(0, true, 1)
+    P3D_TCG_PICKF(1, false, 0) P3D_TCG_PICKF(1, true, 0) P3D_TCG_PICKF(2, false, 0) P3D_TCG_PICKF(2, true, 0)
+#undef P3D_TCG_PICKF
   }
-  if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
-  if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
+  if (d->fused_mode == 3) fn = q.fi ? tc_gemm_kernel<3, false, 0, 1, 1, false, true> : tc_gemm_kernel<3, false, 0>;
+  if (d->fused_mode == 4) fn = q.fi ? tc_gemm_kernel<4, false, 0, 1, 1, false, true> : tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
   static PerDeviceOnce attr;
   if (attr.needed()) {
@@ -995,7 +1035,14 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
                       tc_gemm_kernel<0, false, 0, 2>, tc_gemm_kernel<0, false, 1, 2>, tc_gemm_kernel<0, true, 0, 2>,
                       tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>,
                       tc_gemm_kernel<0, false, 0, 1, 1, true>, tc_gemm_kernel<0, false, 1, 1, 1, true>,
-                      tc_gemm_kernel<1, false, 0, 1, 1, true>};
+                      tc_gemm_kernel<1, false, 0, 1, 1, true>,
+                      tc_gemm_kernel<0, false, 0, 1, 1, true, true>, tc_gemm_kernel<0, false, 1, 1, 1, true, true>,
+                      tc_gemm_kernel<1, false, 0, 1, 1, true, true>,
+                      tc_gemm_kernel<0, false, 0, 1, 1, false, true>, tc_gemm_kernel<0, false, 1, 1, 1, false, true>,
+                      tc_gemm_kernel<0, true, 0, 1, 1, false, true>, tc_gemm_kernel<0, true, 1, 1, 1, false, true>,
+                      tc_gemm_kernel<1, false, 0, 1, 1, false, true>, tc_gemm_kernel<1, true, 0, 1, 1, false, true>,
+                      tc_gemm_kernel<2, false, 0, 1, 1, false, true>, tc_gemm_kernel<2, true, 0, 1, 1, false, true>,
+                      tc_gemm_kernel<3, false, 0, 1, 1, false, true>, tc_gemm_kernel<4, false, 0, 1, 1, false, true>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     KernelFn two[] = {tc_gemm_kernel<0, false, 0, 1, 2>, tc_gemm_kernel<0, false, 1, 1, 2>, tc_gemm_kernel<0, true, 0, 1, 2>,
                       tc_gemm_kernel<0, true, 1, 1, 2>, tc_gemm_kernel<1, false, 0, 1, 2>, tc_gemm_kernel<1, true, 0, 1, 2>};

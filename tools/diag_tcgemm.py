@@ -112,7 +112,7 @@ if __name__ == "__main__":
         dict(M=1000, N=96, K=1000, a_mn=1, b_mn=1, split_k=1),                             # reduce-add with ragged M, N and K
     ]
     print("P3D_GEMM_CG2 =", os.environ.get("P3D_GEMM_CG2", "0"), " P3D_GEMM_OCC2 =", os.environ.get("P3D_GEMM_OCC2", "0"),
-          " P3D_GEMM_TMASTORE =", os.environ.get("P3D_GEMM_TMASTORE", "0"))
+          " P3D_GEMM_TMASTORE =", os.environ.get("P3D_GEMM_TMASTORE", "0"), " P3D_GEMM_FASTISSUE =", os.environ.get("P3D_GEMM_FASTISSUE", "0"))
     bad = 0
     for c in cases:
         try:
