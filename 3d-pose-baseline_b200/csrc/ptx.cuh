@@ -98,6 +98,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same with shared-space addresses already at hand (no generic -> shared conversion per call)
+__device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst_s, const CUtensorMap* m, uint32_t bar_s, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst_s), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_s), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                                  int32_t c1, uint64_t hint) {
   asm volatile(

@@ -207,6 +207,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const int npre = p.b_independent ? (nk < STAGES ? nk : STAGES) : 0;
+    bool lean = false;
+    if constexpr (FI) lean = (p.cn == 1);
+    if (lean) {
+      // FI: everything that does not change from k-block to k-block - which box this lane fetches, through which map,
+      // into which offset of a slot, its fixed coordinate - is settled before the loop; a k-block is barrier wait,
+      // expect_tx, one TMA instruction per box-owning lane, and ONE test of p.dbg in front of the diagnostics stamps
+      // (the general loop below re-derives them through ~110 SASS instructions and a jump table per k-block).
+      const uint32_t dst0 = smem_u32(is_a ? sA : sB) + static_cast<uint32_t>(my_box) * BOX_BYTES;
+      const uint32_t slot = is_a ? static_cast<uint32_t>(A_SLOT) : static_cast<uint32_t>(B_BYTES);
+      const int fix = my_mn ? my_row0 + 64 * my_box : my_row0;             // MN-major: the row coordinate of this lane's box
+      const uint32_t full_s = smem_u32(full);
+      auto load = [&](int stg, int k0) {
+        tma_load_2d_s(dst0 + static_cast<uint32_t>(stg) * slot, my_map, full_s + static_cast<uint32_t>(stg) * 8u, my_mn ? fix : k0, my_mn ? k0 : fix);
+      };
+      for (int kb = 0; kb < npre; ++kb) {            // weights of the first ring pass, ahead of the dependency wait
+        if (lane == 0) mbar_arrive_expect_tx(&full[kb], bytes);
+        __syncwarp();
+        if (is_b) load(kb, kbeg + kb * BK);
+      }
+      __syncwarp();
+      grid_dependency_wait();
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1, 1);
+        if (kb >= npre && lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
+        __syncwarp();
+        if (is_a || (is_b && kb >= npre)) load(stage, kbeg + kb * BK);
+        if (p.dbg) { if (kb == 3) P3D_STAMP(8); if (kb == 7) P3D_STAMP(9); if (kb == 11) P3D_STAMP(10); }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else {
     for (int kb = 0; kb < npre; ++kb) {              // ring slots are free on the first pass
       expect(kb);
       __syncwarp();
@@ -225,6 +256,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (kb == 7) P3D_STAMP(9);
       if (kb == 11) P3D_STAMP(10);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
     }
     P3D_STAMP(2);
   } else if (warp == 1) {
