@@ -21,8 +21,7 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { launch_counter()->fetch_add(n); }
 long long launch_count_now() { return launch_counter()->load(); }
 
-namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const float*, __nv_bfloat16*, int64_t, cudaStream_t);
-                 int pad_input(const __nv_bfloat16*, __nv_bfloat16*, int64_t, cudaStream_t); }
+namespace prep { int prepare(p3d_model*, cudaStream_t); int pack_input(const float*, __nv_bfloat16*, int64_t, cudaStream_t); }
 namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t);
                int debug_umma_gemm(const void*, const void*, float*, int, int, cudaStream_t); }
 namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
@@ -115,7 +114,16 @@ static void drain() {
 }
 }  // namespace prof
 
-namespace hostpack { void pack(const float* src, uint16_t* dst, int64_t n, int threads); }   // hostpack.cpp
+int mark_model_work(p3d_model* m, cudaStream_t st) {
+  if (!m->ev_done) P3D_CUDA(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+  P3D_CUDA(cudaEventRecord(m->ev_done, st));
+  m->ev_done_recorded = true;
+  return P3D_OK;
+}
+int order_after_model_work(p3d_model* m, cudaStream_t st) {
+  if (m->ev_done_recorded) P3D_CUDA(cudaStreamWaitEvent(st, m->ev_done, 0));
+  return P3D_OK;
+}
 
 static NamedParam* find_param(p3d_model* m, const char* name) {
   for (auto& p : m->params)
@@ -278,10 +286,11 @@ void p3d_model_destroy(p3d_model* m) {
   cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
   cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
   cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act);
+  if (m->ev_done) cudaEventDestroy(m->ev_done);
+  for (auto& e : m->pipe_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; ++i) {
     if (m->pipe_streams[i]) cudaStreamDestroy(m->pipe_streams[i]);
     cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
-    if (m->pipe_hx[i]) cudaFreeHost(m->pipe_hx[i]);
   }
   delete m;
 }
@@ -370,18 +379,7 @@ static int forward_packed(p3d_model* m, float* y, int64_t B, cudaStream_t st) {
   return tc::forward_bf16(m, m->xb, y, B, st);
 }
 
-int p3d_host_pack_bf16(const float* src_host, uint16_t* dst_host, int64_t n, int threads) {
-  P3D_REQUIRE(n >= 0 && (n == 0 || (src_host && dst_host)), "host_pack_bf16: bad argument");
-  hostpack::pack(src_host, dst_host, n, threads);
-  return P3D_OK;
-}
-
-int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* stream) {
-  P3D_REQUIRE(m && x && y, "forward: null argument");
-  P3D_REQUIRE(B >= 0, "forward: negative batch");
-  if (B == 0) return P3D_OK;
-  P3D_CUDA(cudaSetDevice(m->cfg.device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int forward_on(p3d_model* m, const float* x, float* y, int64_t B, cudaStream_t st) {
   if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
   if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
   const int L = m->L;
@@ -396,6 +394,16 @@ int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* s
   P3D_TRY(ensure_xb(m, B));
   P3D_TRY(prep::pack_input(x, m->xb, B, st));
   return forward_packed(m, y, B, st);
+}
+
+int p3d_model_forward(p3d_model* m, const float* x, float* y, int64_t B, void* stream) {
+  P3D_REQUIRE(m && x && y, "forward: null argument");
+  P3D_REQUIRE(B >= 0, "forward: negative batch");
+  if (B == 0) return P3D_OK;
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  P3D_TRY(forward_on(m, x, y, B, st));
+  return mark_model_work(m, st);     // the host-buffer step / realtime frame (private streams) order themselves behind this
 }
 
 int p3d_model_mse(p3d_model* m, const float* y, const float* t, int64_t B, float* loss, void* stream) {
@@ -428,7 +436,6 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
     for (int i = 0; i < 3; ++i) {
       cudaFree(m->pipe_x[i]); cudaFree(m->pipe_t[i]); cudaFree(m->pipe_y[i]);
       m->pipe_x[i] = m->pipe_t[i] = m->pipe_y[i] = nullptr;
-      if (m->pipe_hx[i]) { cudaFreeHost(m->pipe_hx[i]); m->pipe_hx[i] = nullptr; }
     }
     m->pipe_chunk = 0;
     for (int i = 0; i < 3; ++i) {
@@ -438,27 +445,18 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
     }
     m->pipe_chunk = chunk;
   }
-  // P3D_PIPE_XBF16=1 (opt-in until measured on the GPU): x is rounded to bf16 on the host (hostpack, a few threads, one
-  // chunk ahead of the copy engine) into pinned staging and crosses PCIe as 64 B per pose instead of 128 - the upload,
-  // which bounds this path, shrinks from 320 to 256 B per pose.  The forward rounds x to bf16 anyway, so no result bit
-  // changes.  Tensor-core paths only (bf16 mode, width a multiple of 8); single-pose chunks keep the fp32 route.
-  static const bool xbf16_env = [] { const char* e = getenv("P3D_PIPE_XBF16"); return e && e[0] == '1'; }();
-  const bool xbf16 = xbf16_env && m->cfg.mode != P3D_MODE_FP32 && (m->L % 8) == 0;
-  if (xbf16) {
-    for (int i = 0; i < 3; ++i)
-      if (!m->pipe_hx[i]) P3D_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->pipe_hx[i]), sizeof(uint16_t) * m->pipe_chunk * kIn, cudaHostAllocDefault));
-    P3D_TRY(ensure_xb(m, chunk));
-  }
   cudaStream_t s_in = m->pipe_streams[0], s_cmp = m->pipe_streams[1], s_out = m->pipe_streams[2];
-  cudaEvent_t ev_in[3], ev_cmp[3], ev_out[3];
-  for (int i = 0; i < 3; ++i) {
-    P3D_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-    P3D_CUDA(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
-    P3D_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-  }
+  for (auto& e : m->pipe_ev) if (!e) P3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t* ev_in = m->pipe_ev; cudaEvent_t* ev_cmp = m->pipe_ev + 3; cudaEvent_t* ev_out = m->pipe_ev + 6;
+  // a training step / epoch / forward still running on the caller's stream owns the weights, the moving statistics and
+  // the forward scratch: the pipeline's streams start behind it
+  P3D_TRY(order_after_model_work(m, s_in));
+  P3D_TRY(order_after_model_work(m, s_cmp));
   int rc = P3D_OK;
+  cudaError_t ce = cudaSuccess;
+#define P3D_PIPE(call) do { if (rc == P3D_OK && ce == cudaSuccess) ce = (call); } while (0)
   if (!m->pack_valid) rc = prep::prepare(m, s_cmp);
-  if (rc == P3D_OK && cudaMemsetAsync(m->pipe_loss, 0, sizeof(double), s_cmp) != cudaSuccess) rc = P3D_ERR_CUDA;
+  P3D_PIPE(cudaMemsetAsync(m->pipe_loss, 0, sizeof(double), s_cmp));
   // Tapered schedule (P3D_PIPE_TAPER=0 switches it off): the first upload and the last forward + download are not
   // overlapped by anything, so the pipeline starts and ends on quarter / half chunks (16 K poses still fill the fused
   // kernel) and runs full chunks in between.  Measured on 2^20 poses, same box: 130.9 -> 134.3 M poses/s end to end.
@@ -467,44 +465,32 @@ int p3d_model_step_eval_host(p3d_model* m, const float* x_host, const float* t_h
   if (taper && B >= 4 * chunk && chunk >= 4096) { head[0] = chunk / 4; head[1] = chunk / 2; tail[0] = chunk / 2; tail[1] = chunk / 4; }
   const int64_t body_end = B - tail[0] - tail[1];
   int64_t done = 0;
-  for (int it = 0; rc == P3D_OK && done < B; ++it) {
+  for (int it = 0; rc == P3D_OK && ce == cudaSuccess && done < B; ++it) {
     const int slot = it % 3;
     int64_t n;
     if (it < 2 && head[it]) n = head[it];
     else if (done < body_end) n = (body_end - done < chunk) ? (body_end - done) : chunk;
     else n = (done == body_end && tail[0]) ? tail[0] : B - done;
-    const bool xb16 = xbf16 && n >= 2;
-    if (xb16) {
-      // the upload that read this staging slot three chunks ago must be over before the CPU overwrites it; the rounding
-      // of this chunk then runs while the copy engine is busy with the previous one
-      if (it >= 3 && cudaEventSynchronize(ev_in[slot]) != cudaSuccess) { rc = P3D_ERR_CUDA; set_error("step_eval_host: staging slot wait failed"); break; }
-      hostpack::pack(x_host + done * kIn, reinterpret_cast<uint16_t*>(m->pipe_hx[slot]), n * kIn, 0);
-    }
-    if (it >= 3) cudaStreamWaitEvent(s_in, ev_out[slot], 0);      // slot buffers free again
-    if (xb16) cudaMemcpyAsync(m->pipe_x[slot], m->pipe_hx[slot], sizeof(uint16_t) * n * kIn, cudaMemcpyHostToDevice, s_in);
-    else cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in);
-    if (t_host) cudaMemcpyAsync(m->pipe_t[slot], t_host + done * out, sizeof(float) * n * out, cudaMemcpyHostToDevice, s_in);
-    cudaEventRecord(ev_in[slot], s_in);
-    cudaStreamWaitEvent(s_cmp, ev_in[slot], 0);
-    if (xb16) {
-      rc = prep::pad_input(reinterpret_cast<const __nv_bfloat16*>(m->pipe_x[slot]), m->xb, n, s_cmp);
-      if (rc == P3D_OK) rc = forward_packed(m, m->pipe_y[slot], n, s_cmp);
-    } else {
-      rc = p3d_model_forward(m, m->pipe_x[slot], m->pipe_y[slot], n, s_cmp);
-    }
+    if (it >= 3) P3D_PIPE(cudaStreamWaitEvent(s_in, ev_out[slot], 0));      // slot buffers free again
+    P3D_PIPE(cudaMemcpyAsync(m->pipe_x[slot], x_host + done * kIn, sizeof(float) * n * kIn, cudaMemcpyHostToDevice, s_in));
+    if (t_host) P3D_PIPE(cudaMemcpyAsync(m->pipe_t[slot], t_host + done * out, sizeof(float) * n * out, cudaMemcpyHostToDevice, s_in));
+    P3D_PIPE(cudaEventRecord(ev_in[slot], s_in));
+    P3D_PIPE(cudaStreamWaitEvent(s_cmp, ev_in[slot], 0));
+    if (ce != cudaSuccess) break;
+    rc = forward_on(m, m->pipe_x[slot], m->pipe_y[slot], n, s_cmp);
     if (rc != P3D_OK) break;
     if (t_host) rc = sqerr_accumulate(m->pipe_y[slot], m->pipe_t[slot], static_cast<size_t>(n) * out, m->pipe_loss, s_cmp);
-    cudaEventRecord(ev_cmp[slot], s_cmp);
-    cudaStreamWaitEvent(s_out, ev_cmp[slot], 0);
-    cudaMemcpyAsync(y_host + done * out, m->pipe_y[slot], sizeof(float) * n * out, cudaMemcpyDeviceToHost, s_out);
-    cudaEventRecord(ev_out[slot], s_out);
+    P3D_PIPE(cudaEventRecord(ev_cmp[slot], s_cmp));
+    P3D_PIPE(cudaStreamWaitEvent(s_out, ev_cmp[slot], 0));
+    P3D_PIPE(cudaMemcpyAsync(y_host + done * out, m->pipe_y[slot], sizeof(float) * n * out, cudaMemcpyDeviceToHost, s_out));
+    P3D_PIPE(cudaEventRecord(ev_out[slot], s_out));
     done += n;
   }
+#undef P3D_PIPE
   cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
-  for (int i = 0; i < 3; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_cmp[i]); cudaEventDestroy(ev_out[i]); }
   if (rc != P3D_OK) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  if (ce != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    cudaError_t e = ce != cudaSuccess ? ce : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
     set_error("step_eval_host: %s", cudaGetErrorString(e));
     return P3D_ERR_CUDA;
   }

@@ -101,6 +101,7 @@ struct TrainWorkspace {
   float* mean = nullptr;    // [nhidden][L]
   float* rstd = nullptr;    // [nhidden][L]
   double* red = nullptr;    // [nhidden][2][L] backward sums (dgamma, dbeta) + misc scalars
+  unsigned* gcount = nullptr;   // [2 nhidden][2] arrival counter + completion flag of the grid-synchronised fused epilogues
   float* scal = nullptr;    // small device scalars: loss, lr, clip dots...
   // bf16 operands of the tensor-core path (P3D_MODE_BF16)
   __nv_bfloat16* xb = nullptr;    // [B][32]
@@ -166,7 +167,19 @@ namespace simt {
 int forward_latency_cluster_rt(p3d_model* m, const rt::Fused& f, float* y, cudaStream_t st);
 }
 namespace p2p {
+// One rank's exchange buffer for the latency-bound reductions of the data-parallel step (SyncBN sums, loss), mapped by
+// every rank of the node through CUDA IPC (p2p.cu).  Written by peers with NVLink stores, flags carry sequence numbers.
+constexpr int NSLOTS = 4;
+constexpr int MAXN = 8192;          // doubles per reduction (2 x linear_size <= 4096)
+constexpr int MAXW = 16;
+struct Layout {
+  double data[NSLOTS][MAXW][MAXN];
+  unsigned long long flag[NSLOTS][MAXW];
+  unsigned long long seq;           // last completed sequence number (local)
+};
+struct Peers { Layout* p[MAXW]; };
 bool ready(const p3d_model* m);
+const Peers* device_peers(const p3d_model* m);     // device copy of the peer table (null until attached)
 struct BnFinalize {                 // optional fused tail: BatchNorm statistics from the reduced [sum | sumsq]
   double invB = 0.0;
   float* mean = nullptr; float* rstd = nullptr; float* mm = nullptr; float* mv = nullptr;
@@ -175,12 +188,18 @@ int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st, const 
 void destroy(p3d_model* m);
 }  // namespace p2p
 namespace tcg {
-// Extra operands of the small-batch (M <= 128: the whole batch is one tile, so per-column batch statistics are
-// CTA-local) fused training epilogues of tc_gemm.cu.
+// Extra operands of the fused training epilogues of tc_gemm.cu: the BatchNorm / ReLU / dropout arithmetic of a hidden
+// layer inside the GEMM that produces its input, forward and backward.
 //   mode 3, forward : acc = h_in W;  z = alpha acc + bias -> C;  BN batch statistics over the rows (mean / rstd /
 //                     moving averages written), ReLU, dropout (Philox or injected mask), + residual -> h, hb, mask
 //   mode 4, backward: acc = dz_next W^T;  dh = alpha acc (+ res) (-> dh_out);  da = dh * dropout * relu';  BN backward
-//                     with CTA-local column sums -> dzb (bf16), dgamma / dbeta (or the bias gradient without BN)
+//                     with the column sums of da and da * xhat -> dzb (bf16), dgamma / dbeta (or the bias gradient)
+// The accumulator stays in TMEM between the two passes the column statistics need.  With one M tile (batch <= 128, one
+// GPU) the column sums are CTA-local.  Otherwise (`gsum` set) every CTA adds its partial sums to gsum, the grid meets
+// at an arrival counter (cooperative launch: all tiles are resident, so the grid must not exceed the SM count), and -
+// data parallel - the CTA that arrives last pushes this rank's sums into every peer's exchange buffer over NVLink and
+// raises the flags all CTAs of all ranks wait on: the SyncBN all-reduce happens INSIDE the GEMM, between its mainloop
+// and its second epilogue pass, summed in rank order (bit-identical statistics on every rank).
 struct FusedTrain {
   const void* sc = nullptr;               // train::StepScalars (device)
   const float* gamma = nullptr; const float* beta = nullptr;
@@ -190,7 +209,15 @@ struct FusedTrain {
   const float* z = nullptr; float* dh_out = nullptr; void* dzb = nullptr;                                                       // mode 4, [M][N]
   float* ggamma = nullptr; float* gbeta = nullptr; float* gbias = nullptr;                                                      // mode 4, [N]
   int has_bn = 0, dropout = 0, layer = 0;
-  float invB = 1.f;
+  float invB = 1.f;                       // 1 / GLOBAL batch
+  double* gsum = nullptr;                 // [2][N] doubles, zero when the kernel starts (grid-synchronised form)
+  unsigned* gcount = nullptr;             // [2]: arrival counter, completion flag; zero when the kernel starts
+  const void* peers = nullptr;            // device p2p::Peers (world > 1)
+  int rank = 0, world = 1;
+  long long row0 = 0;                     // global row of this rank's row 0 (dropout counters use global rows)
+  double* xsum = nullptr;                 // optional scalar summed over the ranks on the same exchange (the step's loss sum)
+  float pg_scale = 1.f;                   // 1 / world: gradients every rank computes in full (dgamma, dbeta, bias) are
+                                          // pre-divided so that the flat gradient all-reduce (a sum) restores them once
 };
 // tcgen05 GEMM (tc_gemm.cu): C[M,N] (+)= alpha * A B^T-form product of bf16 operands, fp32 result.
 struct GemmArgs {
@@ -213,9 +240,7 @@ struct GemmArgs {
   // must not depend on that predecessor - its first tiles are fetched ahead of the dependency wait
   int pdl = 0;
   void* dbg = nullptr;                // diagnostics: [ctas][8] globaltimer stamps
-  int fused_mode = 0;                 // 0, or 3 / 4: small-batch fused training epilogue (needs M <= 128, unsplit K);
-                                      // 5 (any M): C = dh of a hidden layer, colsum += BatchNorm backward sums
-                                      // [sum da | sum da*xhat] of that layer (fused.z/mask/mean/rstd/gamma/beta/sc/dropout)
+  int fused_mode = 0;                 // 0, or 3 / 4: fused training epilogue (unsplit K; every tile resident at once)
   FusedTrain fused;
 };
 // A planned GEMM: tensor maps + kernel parameters, built once (host cost of two cuTensorMapEncodeTiled calls)
@@ -224,8 +249,11 @@ struct alignas(64) GemmPlan { unsigned char blob[1024]; int valid = 0; };
 int plan(const GemmArgs& g, GemmPlan* out);
 int launch(const GemmPlan& pl, cudaStream_t st);
 int gemm(const GemmArgs& g, cudaStream_t st);
+bool fused_fits(int M, int N, int K, int num_sms);   // can the fused training epilogues serve an M x N layer (all tiles resident)?
 }  // namespace tcg
 int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st);
+int mark_model_work(p3d_model* m, cudaStream_t st);          // record ev_done on st
+int order_after_model_work(p3d_model* m, cudaStream_t st);   // st waits for the last recorded ev_done
 
 }  // namespace p3d
 
@@ -255,6 +283,7 @@ struct p3d_model {
   int num_sms = 0;
   __nv_bfloat16* act_scratch = nullptr;  // [2][grid*128][L] bf16 (tcgen05 path)
   int act_grid = 0;
+  bool l2_persist_used = false;          // the fused kernel left persisting lines in the L2 (reset before a training step)
   __nv_bfloat16* xb = nullptr;           // packed input [cap][64]
   int64_t xb_cap = 0;
   // layered (one tcgen05 GEMM per layer) forward for small/medium batches: plans cached per batch size
@@ -273,11 +302,15 @@ struct p3d_model {
   float* pipe_x[3] = {nullptr, nullptr, nullptr};
   float* pipe_t[3] = {nullptr, nullptr, nullptr};
   float* pipe_y[3] = {nullptr, nullptr, nullptr};
-  float* pipe_hx[3] = {nullptr, nullptr, nullptr};   // pinned staging: x rounded to bf16 on the host [chunk][32] (P3D_PIPE_XBF16=1)
-  float* pipe_hy[3] = {nullptr, nullptr, nullptr};
-  float* pipe_ht[3] = {nullptr, nullptr, nullptr};
   double* pipe_loss = nullptr;                        // device accumulator (sum of squared errors)
   int64_t pipe_chunk = 0;
+  cudaEvent_t pipe_ev[9] = {};                        // in / compute / out events of the three pipeline slots (cached)
+  // Ordering between the caller's stream and the library's private streams: every asynchronous operation that writes
+  // model state (training steps, epochs, forwards: weights, moving statistics, packed weights, scratch) records
+  // `ev_done` on its stream; the host-buffer step and the realtime frame, which run on private non-blocking streams,
+  // wait for it before they fold weights or launch (p3d::order_after_model_work).
+  cudaEvent_t ev_done = nullptr;
+  bool ev_done_recorded = false;
   // training
   p3d::TrainWorkspace tw;
   void* nccl_comm = nullptr;

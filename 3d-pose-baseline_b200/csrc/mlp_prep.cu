@@ -138,22 +138,6 @@ int prepare(p3d_model* m, cudaStream_t st) {
   return P3D_OK;
 }
 
-// x already bf16 [B,32] (rounded on the host, see api.cu host_pack_bf16) -> bf16 [B,64], columns 32..63 zero
-__global__ void pad_input_kernel(const uint4* __restrict__ xh, uint4* __restrict__ xb, long long B) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;   // one 8-element group
-  if (idx >= B * 8) return;
-  const long long row = idx >> 3;
-  const int g = static_cast<int>(idx & 7);
-  xb[idx] = g < 4 ? __ldg(xh + row * 4 + g) : make_uint4(0, 0, 0, 0);
-}
-
-int pad_input(const __nv_bfloat16* xh, __nv_bfloat16* xb, int64_t B, cudaStream_t st) {
-  const long long groups = B * 8;
-  pad_input_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(xh), reinterpret_cast<uint4*>(xb), B);
-  P3D_LAUNCH_CHECK();
-  return P3D_OK;
-}
-
 int pack_input(const float* x, __nv_bfloat16* xb, int64_t B, cudaStream_t st) {
   const long long groups = B * 8;
   pack_input_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, st>>>(x, xb, B);

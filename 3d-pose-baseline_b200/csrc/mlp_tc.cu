@@ -445,12 +445,13 @@ static int launch_forward(p3d_model* m, const __nv_bfloat16* xb, float* y, int64
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  // P3D_L2_PERSIST=1 (opt-in until measured on the GPU): the per-CTA activation scratch (2 x 128 x L bf16 per CTA, 77.6 MB for
-  // 148 CTAs at L = 1024) is written and re-read five times per tile and never needed after the launch, yet ncu shows
-  // 4.1 GB of DRAM traffic per 2^20-pose launch against 0.34 GB of compulsory x / y bytes: the streaming x / y lines push
-  // dirty scratch lines out of the L2 (the evict_last hints on the TMA operations do not prevent it).  An access-policy
-  // window on the scratch with a persisting-L2 set-aside of the same size keeps those lines resident.
-  static const bool l2_persist = [] { const char* e = getenv("P3D_L2_PERSIST"); return e && e[0] == '1'; }();
+  // The per-CTA activation scratch (2 x 128 x L bf16 per CTA, 77.6 MB for 148 CTAs at L = 1024) is written and re-read
+  // five times per tile and never needed after the launch, yet without help the streaming x / y lines push dirty scratch
+  // lines out of the L2 (the evict_last hints on the TMA operations do not prevent it): ncu measured 4.86 GB of DRAM
+  // traffic per 2^20-pose launch against 0.34 GB of compulsory x / y bytes.  An access-policy window on the scratch with
+  // a persisting-L2 set-aside keeps those lines resident: 2.42 GB, and 156.6 -> 159.7 M poses/s on the same box
+  // (round 2, profiles/r2_l2persist.md).  P3D_L2_PERSIST=0 switches it off.
+  static const bool l2_persist = [] { const char* e = getenv("P3D_L2_PERSIST"); return !(e && e[0] == '0'); }();
   if (l2_persist) {
     int dev = 0, max_persist = 0, max_window = 0;
     P3D_CUDA(cudaGetDevice(&dev));
@@ -473,6 +474,7 @@ static int launch_forward(p3d_model* m, const __nv_bfloat16* xb, float* y, int64
       attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
       cfg.numAttrs = 2;
+      m->l2_persist_used = true;
     }
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -12,24 +12,18 @@
 // the launches replay inside the step's CUDA graph.  Slot reuse is safe with >= 2 slots: nobody can be more than one
 // reduction ahead of the slowest rank (it needs that rank's flag), and a rank issues reduction seq+1 only after its
 // own kernel for seq has finished reading.  The big gradient all-reduce stays with NCCL (bandwidth bound).
+//
+// The fused training epilogues of tc_gemm.cu run the same protocol on the same buffers from INSIDE the GEMM that needs
+// the sums (FusedTrain in common.cuh); this kernel remains for the unfused path (batches whose tiles do not all fit the
+// SMs) and for vectors that belong to no GEMM.  Exchanges of one model must not run concurrently (one sequence counter).
+// Like an NCCL collective the kernels wait for their peers without a timeout: ranks must stay in lockstep (same number
+// of steps in the same order).  P3D_SYNC_TIMEOUT_S=<seconds> turns a longer wait into a message + trap (diagnostics).
 #include <cstring>
 
 #include "common.cuh"
 
 namespace p3d {
 namespace p2p {
-
-constexpr int NSLOTS = 4;
-constexpr int MAXN = 8192;          // doubles per reduction (2 x linear_size <= 4096)
-constexpr int MAXW = 16;
-
-struct Layout {                     // one rank's exchange buffer
-  double data[NSLOTS][MAXW][MAXN];
-  unsigned long long flag[NSLOTS][MAXW];
-  unsigned long long seq;           // next sequence number (local)
-};
-
-struct Peers { Layout* p[MAXW]; };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -43,7 +37,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // Optional tail of a forward SyncBN reduction: the BatchNorm finalisation (mean / biased variance over the global
 // batch, moving averages with momentum .99 - train.cu's bn_finalize_kernel) runs on the freshly summed columns.
 __global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int rank, int world, double* __restrict__ buf, int n,
-                                                        const BnFinalize fin) {
+                                                        const BnFinalize fin, long long wait_limit_ns) {
   Layout* me = peers.p[rank];
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) s_seq = me->seq + 1;           // sequence numbers start at 1 (flags are zero-initialised)
@@ -63,9 +57,16 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int r
   // 2. raise my flag on every rank   3. wait for everybody's flag here
   if (threadIdx.x < world) {
     st_release_sys(&peers.p[threadIdx.x]->flag[slot][rank], seq);
-    unsigned long long spins = 0;
+    unsigned long long t0 = 0;
+    if (wait_limit_ns > 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (ld_acquire_sys(&me->flag[slot][threadIdx.x]) < seq) {
-      if (++spins > (1ull << 24)) { printf("p3d: peer all-reduce timed out (rank %d waits for %d, seq %llu)\n", rank, (int)threadIdx.x, seq); __trap(); }
+      if (wait_limit_ns > 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > static_cast<unsigned long long>(wait_limit_ns)) {
+          printf("p3d: peer all-reduce timed out (rank %d waits for %d, seq %llu)\n", rank, (int)threadIdx.x, seq); __trap();
+        }
+      }
     }
   }
   __syncthreads();
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const Peers peers, int r
 
 struct State {
   Layout* local = nullptr;
-  Peers peers;
+  Peers peers{};
+  Peers* dev_peers = nullptr;       // device copy, for kernels that take the table by pointer (tc_gemm's fused epilogues)
   int world = 0, rank = 0;
   bool ready = false;
 };
@@ -121,10 +123,13 @@ int local_handle(p3d_model* m, uint8_t* handle64) {
   return P3D_OK;
 }
 
+int detach(p3d_model* m);
+
 int attach(p3d_model* m, const uint8_t* handles, int rank, int world) {
   State* s = state_of(m);
   P3D_REQUIRE(s && s->local, "p2p attach: call p3d_model_p2p_handle first");
   P3D_REQUIRE(world >= 2 && world <= MAXW && rank >= 0 && rank < world, "p2p attach: bad rank/world");
+  for (int r = 0; r < MAXW; ++r) s->peers.p[r] = nullptr;
   for (int r = 0; r < world; ++r) {
     if (r == rank) { s->peers.p[r] = s->local; continue; }
     cudaIpcMemHandle_t h;
@@ -134,21 +139,39 @@ int attach(p3d_model* m, const uint8_t* handles, int rank, int world) {
     if (e != cudaSuccess) {
       cudaGetLastError();
       set_error("peer memory of rank %d is not reachable (%s): the step keeps NCCL for the small reductions", r, cudaGetErrorString(e));
+      detach(m);                        // close what was opened so far
       return P3D_ERR_CUDA;
     }
     s->peers.p[r] = static_cast<Layout*>(ptr);
   }
-  s->world = world; s->rank = rank; s->ready = true;
+  s->world = world; s->rank = rank;
+  if (!s->dev_peers) P3D_CUDA(cudaMalloc(&s->dev_peers, sizeof(Peers)));
+  P3D_CUDA(cudaMemcpy(s->dev_peers, &s->peers, sizeof(Peers), cudaMemcpyHostToDevice));
+  s->ready = true;
+  return P3D_OK;
+}
+
+// Undo a (possibly partial) attach: close what was opened, keep the local buffer.  The step then uses NCCL.
+int detach(p3d_model* m) {
+  State* s = state_of(m);
+  if (!s) return P3D_OK;
+  for (int r = 0; r < MAXW; ++r) {
+    if (s->peers.p[r] && s->peers.p[r] != s->local) cudaIpcCloseMemHandle(s->peers.p[r]);
+    s->peers.p[r] = nullptr;
+  }
+  s->world = 0; s->ready = false;
   return P3D_OK;
 }
 
 bool ready(const p3d_model* m) { return m->p2p_state && static_cast<const State*>(m->p2p_state)->ready; }
+const Peers* device_peers(const p3d_model* m) { return ready(m) ? static_cast<const State*>(m->p2p_state)->dev_peers : nullptr; }
 
 int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st, const BnFinalize* fin) {
   State* s = state_of(m);
   P3D_REQUIRE(s && s->ready && n >= 1 && n <= MAXN, "peer all-reduce: not attached or vector too long");
   P3D_REQUIRE(!fin || (n % 2) == 0, "peer all-reduce: the BatchNorm tail needs [sum | sumsq]");
-  allreduce_kernel<<<1, 512, 0, st>>>(s->peers, s->rank, s->world, buf, static_cast<int>(n), fin ? *fin : BnFinalize());
+  static const long long wait_ns = [] { const char* e = getenv("P3D_SYNC_TIMEOUT_S"); return e ? static_cast<long long>(atof(e) * 1e9) : 0LL; }();
+  allreduce_kernel<<<1, 512, 0, st>>>(s->peers, s->rank, s->world, buf, static_cast<int>(n), fin ? *fin : BnFinalize(), wait_ns);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -156,8 +179,9 @@ int allreduce_small(p3d_model* m, double* buf, size_t n, cudaStream_t st, const 
 void destroy(p3d_model* m) {
   State* s = state_of(m);
   if (!s) return;
-  for (int r = 0; r < s->world; ++r)
-    if (r != s->rank && s->peers.p[r]) cudaIpcCloseMemHandle(s->peers.p[r]);
+  for (int r = 0; r < MAXW; ++r)
+    if (s->peers.p[r] && s->peers.p[r] != s->local) cudaIpcCloseMemHandle(s->peers.p[r]);
+  cudaFree(s->dev_peers);
   cudaFree(s->local);
   delete s;
   m->p2p_state = nullptr;
@@ -180,6 +204,12 @@ int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, in
   P3D_REQUIRE(m && handles_host, "p2p_attach: null argument");
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   return p2p::attach(m, handles_host, rank, world);
+}
+
+int p3d_model_p2p_detach(p3d_model* m) {
+  P3D_REQUIRE(m, "p2p_detach: null argument");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  return p2p::detach(m);
 }
 
 }  // extern "C"

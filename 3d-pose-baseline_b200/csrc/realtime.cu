@@ -151,6 +151,7 @@ int p3d_realtime_step_host(p3d_realtime* r, const double* xy36_host, float* enc_
   p3d_model* m = r->model;
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   const int out = m->out_size;
+  P3D_TRY(order_after_model_work(m, r->stream));     // a training step still running on the caller's stream owns the weights
   if (!m->pack_valid) { P3D_TRY(prep::prepare(m, r->stream)); }
   rt::HostIO* io = r->io;
   memcpy(io->kp, xy36_host, sizeof(double) * 36);
@@ -178,6 +179,7 @@ int p3d_realtime_step_host(p3d_realtime* r, const double* xy36_host, float* enc_
     return P3D_OK;
   }
   // generic route (width != 1024, fp32 mode, or a 16-CTA cluster cannot be scheduled): staged copies around the kernels
+  P3D_TRY(order_after_model_work(r->model, r->stream));
   P3D_CUDA(cudaMemcpyAsync(r->d_kp, io->kp, sizeof(double) * 36, cudaMemcpyHostToDevice, r->stream));
   P3D_TRY(rt::step_device(r, r->d_kp, r->d_enc, r->d_y, r->d_pose, 1, r->stream));
   P3D_CUDA(cudaMemcpyAsync(io->pose, r->d_pose, sizeof(double) * 96, cudaMemcpyDeviceToHost, r->stream));

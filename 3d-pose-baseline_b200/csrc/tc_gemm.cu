@@ -10,11 +10,20 @@
 // copies exist anywhere.  MN-major tiles are fetched as 64-column TMA boxes (128B swizzle) and consumed
 // through the MN-major canonical UMMA layout ((8,n),(8,k)):((1,LBO),(8,SBO)) [16-byte units].
 //
-// One CTA per 128 x BN output tile (BN = 64/128/256 chosen per problem so the grid covers the SMs),
+// One CTA per 128 x BN output tile (BN = 32/64/128/256 chosen per problem so the grid covers the SMs),
 // optional split-K over gridDim.z (fp32 atomics into a zeroed C - the weight-gradient GEMMs have only
 // (L/128)*(L/BN) tiles but K = batch).  Warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (TMEM -> registers -> alpha/bias/residual -> global).  Out-of-range rows/cols
+// warps 2-9 = epilogue (TMEM -> registers -> alpha/bias/residual -> global).  Out-of-range rows/cols
 // and the K tail are zero-filled by TMA, so M, N, K need no padding (K=32 input layer, N=48 output).
+//
+// Fused training epilogues (OUT = 3 / 4): the BatchNorm / ReLU / dropout arithmetic of a hidden layer, forward and
+// backward, runs on the accumulator while it sits in TMEM; the per-column batch statistics they need are CTA-local
+// for one M tile and otherwise meet at a grid barrier - with the data-parallel SyncBN exchange over NVLink peer
+// memory in the same place (see FusedTrain in common.cuh).
+//
+// Variants measured on B200 and removed again (numbers in DESIGN.md 3.5): CTA pairs (cta_group::2), two CTAs per SM,
+// A-tile multicast across a cluster, BatchNorm-backward sums in the dh epilogue of one-tile CTAs, TMA-store epilogue,
+// and the general (descriptor-rebuilding) MMA issue loop that the lean one below replaced.
 #include <cstring>
 
 #include "common.cuh"
@@ -34,19 +43,15 @@ constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box 
 constexpr int NTHREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int EPI_THREADS = 256;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
-constexpr int BAR_BYTES = 512;               // full[16] | empty[16] | accf | tmem slot
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + 9 * 1024;   // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256]
-// OCC = 2 instantiations: two CTAs share an SM (96 registers per thread, 106.5 KB of shared memory each, BN <= 128 so
-// that two accumulators fit the 512 TMEM columns).  One CTA's prologue / epilogue then runs under the other one's
-// mainloop - the overlap a one-tile-per-CTA kernel cannot give itself.
-constexpr int RING2_BYTES = 3 * (A_BYTES + 128 * BK * 2);  // 96 KB: 3 stages at BN=128, 4 at 64
-constexpr int SMEM2_BYTES = 1024 + RING2_BYTES + BAR_BYTES + 9 * 1024;
+constexpr int BAR_BYTES = 512;               // full[16] | empty[16] | accf | tmem slot | grid-sync scratch
+// align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256] | per-column finals [2][256] f32 | totals [2][256] f64
+constexpr int TAIL_BYTES = 1024 + 8192 + 2048 + 4096;
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + TAIL_BYTES;
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
-
 
 struct Params {
   int M, N, K;
-  int bn;            // 64 / 128 / 256
+  int bn;            // 32 / 64 / 128 / 256
   int k_per_split;   // multiple of BK
   int a_mn, b_mn;
   float* C; int ldc;
@@ -60,17 +65,12 @@ struct Params {
   __nv_bfloat16* out_b; int ldob;
   const __nv_bfloat16* res_b; int ldrb;
   int relu;
-  int cn;                   // cluster size along N (1, 2, 4): the CTAs of one M tile share A - each fetches 1/cn of its rows and multicasts
-  int occ;                  // 2 = the OCC = 2 instantiation (two CTAs per SM, small ring); 1 otherwise
-  int cg;                   // 2 = CTA pair along M (cta_group::2): one 256 x BN tile per pair, each CTA stages its own 128 rows of A
-                            // and HALF of the B tile - a third less L2 -> SM operand traffic per FLOP (1 = single-CTA tiles)
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
   unsigned long long* dbg;  // optional [ctas][16] globaltimer stamps (diagnostics)
   FusedTrain ft;            // OUT = 3 / 4 only
-  int ts;                   // 1 = the TS instantiation (the tile leaves through TMA stores, tm_c describes C)
-  int fi;                   // 1 = the FI instantiation (lean MMA issue path)
+  long long wait_limit_ns;  // > 0: a wait for peers / the grid longer than this traps (diagnostics; 0 = wait like NCCL does)
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = gtime(); } while (0)
@@ -103,69 +103,166 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+// ------------------------------------------------------------------ grid / peer synchronisation of the fused epilogues
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
-// OUT: 0 = fp32 store, 1 = fp32 reduction (split-K / accumulate), 2 = bf16 (relu, residual in bf16)
-// RES: a residual operand is added;  CS: 1 = column sums of the result and its square are accumulated (BatchNorm
-// statistics of a forward layer); 2 = the result is dh of a hidden layer: column sums of da = dh * dropout * relu'
-// and of da * xhat (the BatchNorm backward sums, what train.cu's bwd_act_kernel computes in a pass of its own)
-// CG: 1 = single-CTA tiles, 2 = CTA pair along M (cta_group::2).  A template parameter, not a runtime flag: a kernel
-// that CONTAINS cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration"
-// otherwise, even if the instructions are never reached - measured), so the single-CTA kernels must not contain them.
-// TS: the fp32 tile leaves through TMA (cp.async.bulk.tensor / cp.reduce.async.bulk.tensor.add for split-K) instead of
-// per-lane st.global / red.global: 32 x 32 chunks staged row-per-lane (as tcgen05.ld delivers them) in 128B-swizzled
-// smem, edges clipped by the tensor map of C (tm_c; unused by the other instantiations).
-// FI: lean MMA issue path (descriptors advanced by addition instead of rebuilt per k-block), see the MMA warp.
-template <int OUT, bool RES, int CS, int CG = 1, int OCC = 1, bool TS = false, bool FI = false>
-__global__ void __launch_bounds__(NTHREADS, OCC)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               const __grid_constant__ CUtensorMap tm_c, const Params p) {
+// Column sums of the whole (global) batch for the columns n0 .. n0 + bn of this CTA, called by the 256 epilogue threads
+// after pass 1 has left this CTA's per-quadrant partial sums in scol ([4][2][256] floats).  Result: tot[j], tot[256 + j]
+// (doubles, shared memory) for column n0 + j.
+//   one M tile, one GPU : the four quadrant partials are the batch.
+//   otherwise           : partials -> gsum (fp64 atomics) -> arrival counter; the CTA that arrives last owns the complete
+//                         sums of this GPU.  One GPU: it raises the completion flag the others spin on.  Data parallel: it
+//                         stores the vector into slot [seq % NSLOTS][rank] of EVERY rank's exchange buffer (16-byte NVLink
+//                         stores), then one thread per peer raises that peer's flag with st.release.sys (cumulative: the
+//                         block barrier before it orders the whole CTA's stores); all CTAs of all ranks spin on their own
+//                         rank's flags (ld.acquire.sys) and add the `world` vectors in rank order - every rank gets
+//                         bit-identical sums.  Slot reuse is safe with >= 2 slots: nobody can be more than one exchange
+//                         ahead of the slowest rank (it needs that rank's flag).  No timeout by default: like an NCCL
+//                         collective this waits for its peers (Params::wait_limit_ns is the diagnostics switch).
+__device__ __forceinline__ void column_totals(const Params& p, int n0, int et, const float* scol, double* tot, uint32_t* sflag,
+                                              unsigned long long seq) {
+  const FusedTrain& ft = p.ft;
+  const int N = p.N;
+  if (ft.gsum == nullptr) {
+    for (int j = et; j < p.bn; j += EPI_THREADS) {
+      tot[j] = static_cast<double>((scol[j] + scol[512 + j]) + (scol[1024 + j] + scol[1536 + j]));
+      tot[256 + j] = static_cast<double>((scol[256 + j] + scol[768 + j]) + (scol[1280 + j] + scol[1792 + j]));
+    }
+    named_bar_sync(1, EPI_THREADS);
+    return;
+  }
+  for (int j = et; j < p.bn; j += EPI_THREADS) {
+    if (n0 + j < N) {
+      atomicAdd(ft.gsum + n0 + j, static_cast<double>((scol[j] + scol[512 + j]) + (scol[1024 + j] + scol[1536 + j])));
+      atomicAdd(ft.gsum + N + n0 + j, static_cast<double>((scol[256 + j] + scol[768 + j]) + (scol[1280 + j] + scol[1792 + j])));
+    }
+  }
+  __threadfence();
+  named_bar_sync(1, EPI_THREADS);
+  const unsigned nctas = gridDim.x * gridDim.y;
+  if (et == 0) *sflag = (atomicAdd(ft.gcount, 1u) == nctas - 1u) ? 1u : 0u;
+  named_bar_sync(1, EPI_THREADS);
+  const bool last = *sflag != 0u;
+  const p2p::Peers* peers = static_cast<const p2p::Peers*>(ft.peers);
+  const int slot = static_cast<int>(seq % p2p::NSLOTS);
+  if (last) {
+    __threadfence();
+    if (ft.world > 1) {
+      const int n2 = N;                                  // 2 N doubles = N double2
+      for (int r = 0; r < ft.world; ++r) {
+        double2* dst = reinterpret_cast<double2*>(peers->p[r]->data[slot][ft.rank]);
+        for (int i = et; i < n2; i += EPI_THREADS) {
+          double2 v;
+          v.x = ld_cg_f64(ft.gsum + 2 * i); v.y = ld_cg_f64(ft.gsum + 2 * i + 1);
+          dst[i] = v;
+        }
+      }
+      // one more scalar rides along (the step's loss sum on the first backward exchange)
+      if (ft.xsum && et < ft.world) peers->p[et]->data[slot][ft.rank][2 * N] = ld_cg_f64(ft.xsum);
+      named_bar_sync(1, EPI_THREADS);
+      if (et < ft.world) st_release_sys(&peers->p[et]->flag[slot][ft.rank], seq);
+      if (et == 0) peers->p[ft.rank]->seq = seq;
+    } else if (et == 0) {
+      st_release_gpu(ft.gcount + 1, 1u);
+    }
+  }
+  // wait: the other CTAs of this GPU (one GPU) / every rank's vector (data parallel)
+  const unsigned long long t0 = p.wait_limit_ns > 0 ? gtime() : 0ull;
+  if (ft.world > 1) {
+    if (et < ft.world) {
+      const unsigned long long* f = &peers->p[ft.rank]->flag[slot][et];
+      while (ld_acquire_sys(f) < seq) {
+        if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) {
+          printf("p3d: SyncBN exchange timed out (rank %d waits for rank %d, seq %llu)\n", ft.rank, et, seq); __trap();
+        }
+      }
+    }
+  } else if (et == 0 && !last) {
+    while (ld_acquire_gpu(ft.gcount + 1) == 0u) {
+      if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) { printf("p3d: grid barrier timed out\n"); __trap(); }
+    }
+  }
+  named_bar_sync(1, EPI_THREADS);
+  for (int j = et; j < p.bn; j += EPI_THREADS) {
+    double s1 = 0.0, s2 = 0.0;
+    if (n0 + j < N) {
+      if (ft.world > 1) {
+        const p2p::Layout* me = peers->p[ft.rank];
+        for (int r = 0; r < ft.world; ++r) { s1 += ld_cg_f64(&me->data[slot][r][n0 + j]); s2 += ld_cg_f64(&me->data[slot][r][N + n0 + j]); }
+      } else {
+        s1 = ld_cg_f64(ft.gsum + n0 + j); s2 = ld_cg_f64(ft.gsum + N + n0 + j);
+      }
+    }
+    tot[j] = s1; tot[256 + j] = s2;
+  }
+  if (ft.xsum && ft.world > 1 && et == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    const p2p::Layout* me = peers->p[ft.rank];
+    double s = 0.0;
+    for (int r = 0; r < ft.world; ++r) s += ld_cg_f64(&me->data[slot][r][2 * N]);
+    *ft.xsum = s;
+  }
+  named_bar_sync(1, EPI_THREADS);
+}
+
+// OUT: 0 = fp32 store, 1 = fp32 reduction (split-K / accumulate), 2 = bf16 (relu, residual in bf16), 3 / 4 = fused
+// training epilogues (forward / backward).  RES: a residual operand is added.  CS: column sums of the result and its
+// square are accumulated (BatchNorm statistics of a forward layer on the unfused path).
+template <int OUT, bool RES, int CS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
   const int STAGES = p.stages;
-  constexpr int cg = CG;                         // 1, or 2 = cta_group::2 pair along M (cluster 2 x 1 x 1, M tiles along x)
-  const int B_BYTES = (p.bn / cg) * BK * 2;      // this CTA's part of the B tile
+  const int B_BYTES = p.bn * BK * 2;
   const int A_SLOT = p.a_bytes;                  // slots are as large as what is fetched (multiple of 1024 B)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_SLOT;
-  constexpr int RING = (OCC == 2) ? RING2_BYTES : RING_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* accf = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
-  float* sbias = reinterpret_cast<float*>(smem + RING + BAR_BYTES);
+  uint32_t* sflag = tmem_slot + 1;
+  float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES);
   float* scol = sbias + 256;
+  float* sfin = scol + 2048;                     // [2][256] per-column finals of the fused epilogues
+  double* stot = reinterpret_cast<double*>(sfin + 512);   // [2][256] column totals of the global batch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = (p.cn > 1 || cg == 2) ? cluster_ctarank() : 0u;
-  const bool leader = (cg == 1) || (crank == 0);   // of a pair: issues the MMAs, owns the "full" barriers
   if (warp == 0) P3D_STAMP(0);
-  // pairs: the two CTAs of a cta_group::2 pair must be neighbours in x (a 1 x 2 x 1 cluster is refused at launch as
-  // "cluster misconfiguration" - measured), so the pair kernels take the M tile from blockIdx.x
-  const int n0 = (CG == 2 ? blockIdx.y : blockIdx.x) * p.bn, m0 = (CG == 2 ? blockIdx.x : blockIdx.y) * BM;
+  const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * BM;
   const int kbeg = blockIdx.z * p.k_per_split;
   const int kend = (kbeg + p.k_per_split < p.K) ? kbeg + p.k_per_split : p.K;
   const int nk = (kend - kbeg + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
-    if constexpr (TS) tma_prefetch_desc(&tm_c);
-    // a ring slot is free again when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.cn); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(accf, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
-    if constexpr (cg == 2) { tmem_alloc_2sm(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish_2sm(); }
-    else { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
-  }
+  if (warp == 1) { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
   tc_fence_before();
-  if (p.cn > 1 || cg == 2) cluster_sync(); else __syncthreads();     // peers must see initialised barriers before the first multicast
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_launch_dependents();     // the next kernel of a programmatic-dependent chain may start its prologue now
@@ -173,157 +270,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
-    // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
-    const uint32_t bytes = p.a_bytes + B_BYTES;
     // Every TMA operation of a stage belongs to its own lane and all of them leave in ONE instruction: issuing them
     // one after the other from a single thread costs ~0.12 us each, which is what bounded short-M GEMMs (16 serial
     // k-blocks x 2 operations = 4.3 us of a 7.6 us kernel).  Lanes [0, na) fetch A boxes, lanes [na, na + nb) B boxes.
-    const int na = p.a_mn ? 2 : 1, nb = p.b_mn ? (p.bn / cg) / 64 : 1;
+    // Everything that does not change from k-block to k-block - which box this lane fetches, through which map, into
+    // which offset of a slot, its fixed coordinate - is settled before the loop; a k-block is barrier wait, expect_tx,
+    // one TMA instruction per box-owning lane.
+    const uint32_t bytes = p.a_bytes + B_BYTES;
+    const int na = p.a_mn ? 2 : 1, nb = p.b_mn ? p.bn / 64 : 1;
     const bool is_a = lane < na, is_b = lane >= na && lane < na + nb;
-    const int bi = lane - na;                                         // B box index of this lane
     const CUtensorMap* my_map = is_a ? &tm_a : &tm_b;
     const bool my_mn = is_a ? (p.a_mn != 0) : (p.b_mn != 0);
-    const int my_box = is_a ? lane : bi;
-    const int my_row0 = is_a ? m0 : n0 + (cg == 2 ? static_cast<int>(crank) * (p.bn / 2) : 0);   // pair: this CTA's half of the N tile
-    const uint32_t a_mask = static_cast<uint16_t>((1u << p.cn) - 1u);
-    auto issue = [&](int stage, int k0, bool with_a, bool with_b) {
-      if ((is_a && with_a) || (is_b && with_b)) {
-        uint8_t* dst = (is_a ? sA + stage * A_SLOT : sB + stage * B_BYTES) + my_box * BOX_BYTES;
-        const int c0 = my_mn ? my_row0 + 64 * my_box : k0, c1 = my_mn ? k0 : my_row0;
-        if (is_a && p.cn > 1) {     // this CTA's share of the rows, delivered to every CTA of the cluster (same smem offset, same barrier)
-          const int part = p.a_bytes / p.cn, rows = part / (BK * 2);
-          tma_load_2d_mcast(dst + crank * part, my_map, &full[stage], k0, m0 + static_cast<int>(crank) * rows, static_cast<uint16_t>(a_mask));
-        } else if constexpr (cg == 2) {       // into this CTA's smem, bytes signalled on the LEADER's barrier
-          tma_load_2d_2sm(dst, my_map, &full[stage], c0, c1);
-        } else {
-          tma_load_2d(dst, my_map, &full[stage], c0, c1);
-        }
-      }
+    const int my_box = is_a ? lane : lane - na;
+    const int my_row0 = is_a ? m0 : n0;
+    const uint32_t dst0 = smem_u32(is_a ? sA : sB) + static_cast<uint32_t>(my_box) * BOX_BYTES;
+    const uint32_t slot = is_a ? static_cast<uint32_t>(A_SLOT) : static_cast<uint32_t>(B_BYTES);
+    const int fix = my_mn ? my_row0 + 64 * my_box : my_row0;             // MN-major: the row coordinate of this lane's box
+    const uint32_t full_s = smem_u32(full);
+    auto load = [&](int stg, int k0) {
+      tma_load_2d_s(dst0 + static_cast<uint32_t>(stg) * slot, my_map, full_s + static_cast<uint32_t>(stg) * 8u, my_mn ? fix : k0, my_mn ? k0 : fix);
     };
-    // pair: both CTAs' bytes are accounted on the leader's barrier (the peer's complete_tx may precede this arrive -
-    // the phase cannot complete before the one pending arrival has happened)
-    auto expect = [&](int stage) { if (lane == 0 && leader) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(cg) * bytes); };
     // Programmatic dependent launch: when B is marked independent of the preceding kernels (weights), its tiles for
     // the first ring pass are requested BEFORE griddepcontrol.wait, i.e. while the previous layer is still running.
     const int npre = p.b_independent ? (nk < STAGES ? nk : STAGES) : 0;
-    bool lean = false;
-    if constexpr (FI) lean = (p.cn == 1);
-    if (lean) {
-      // FI: everything that does not change from k-block to k-block - which box this lane fetches, through which map,
-      // into which offset of a slot, its fixed coordinate - is settled before the loop; a k-block is barrier wait,
-      // expect_tx, one TMA instruction per box-owning lane, and ONE test of p.dbg in front of the diagnostics stamps
-      // (the general loop below re-derives them through ~110 SASS instructions and a jump table per k-block).
-      const uint32_t dst0 = smem_u32(is_a ? sA : sB) + static_cast<uint32_t>(my_box) * BOX_BYTES;
-      const uint32_t slot = is_a ? static_cast<uint32_t>(A_SLOT) : static_cast<uint32_t>(B_BYTES);
-      const int fix = my_mn ? my_row0 + 64 * my_box : my_row0;             // MN-major: the row coordinate of this lane's box
-      const uint32_t full_s = smem_u32(full);
-      auto load = [&](int stg, int k0) {
-        tma_load_2d_s(dst0 + static_cast<uint32_t>(stg) * slot, my_map, full_s + static_cast<uint32_t>(stg) * 8u, my_mn ? fix : k0, my_mn ? k0 : fix);
-      };
-      for (int kb = 0; kb < npre; ++kb) {            // weights of the first ring pass, ahead of the dependency wait
-        if (lane == 0) mbar_arrive_expect_tx(&full[kb], bytes);
-        __syncwarp();
-        if (is_b) load(kb, kbeg + kb * BK);
-      }
+    for (int kb = 0; kb < npre; ++kb) {            // ring slots are free on the first pass
+      if (lane == 0) mbar_arrive_expect_tx(&full[kb], bytes);
       __syncwarp();
-      grid_dependency_wait();
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1, 1);
-        if (kb >= npre && lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
-        __syncwarp();
-        if (is_a || (is_b && kb >= npre)) load(stage, kbeg + kb * BK);
-        if (p.dbg) { if (kb == 3) P3D_STAMP(8); if (kb == 7) P3D_STAMP(9); if (kb == 11) P3D_STAMP(10); }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    } else {
-    for (int kb = 0; kb < npre; ++kb) {              // ring slots are free on the first pass
-      expect(kb);
-      __syncwarp();
-      issue(kb, kbeg + kb * BK, false, true);
+      if (is_b) load(kb, kbeg + kb * BK);
     }
     __syncwarp();
     grid_dependency_wait();
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < nk; ++kb) {
-      const int k0 = kbeg + kb * BK;
       mbar_wait(&empty[stage], phase ^ 1, 1);
-      if (kb >= npre) expect(stage);
+      if (kb >= npre && lane == 0) mbar_arrive_expect_tx(&full[stage], bytes);
       __syncwarp();
-      issue(stage, k0, true, kb >= npre);
-      if (kb == 3) P3D_STAMP(8);
-      if (kb == 7) P3D_STAMP(9);
-      if (kb == 11) P3D_STAMP(10);
+      if (is_a || (is_b && kb >= npre)) load(stage, kbeg + kb * BK);
+      if (p.dbg) { if (kb == 3) P3D_STAMP(8); if (kb == 7) P3D_STAMP(9); if (kb == 11) P3D_STAMP(10); }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
     }
     P3D_STAMP(2);
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (of a pair: the leader CTA only)
-    if (leader) {
-    const uint32_t idesc = umma_idesc_bf16_f32(BM * cg, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+    // ------------------------------------------------------------ MMA issuer
+    // A descriptor's start-address field is (address >> 4) in its low 14 bits and every operand address is a multiple
+    // of 16 below 256 KB, so the field advances LINEARLY: one descriptor per operand is built before the loop, a
+    // k-block adds stage * (slot >> 4), a K = 16 slice adds (step >> 4) - no carry can leave the field.  (Rebuilding
+    // eight descriptors per k-block from byte addresses cost ~110 SASS instructions between the barrier and the first
+    // tcgen05.mma, against 4 x 56 cycles of tensor work at N <= 64; measured: 16.9 -> 14.7 us for a 4096 x 1024 x 1024
+    // GEMM, 48 -> 40 us for the six-layer batch-64 inference chain.)
+    const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
     const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
     const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K=16 slice
+    const uint64_t a0 = p.a_mn ? desc_mn(a_base) : desc_k(a_base), b0 = p.b_mn ? desc_mn(b_base) : desc_k(b_base);
+    const uint32_t a_slot16 = static_cast<uint32_t>(A_SLOT) >> 4, b_slot16 = static_cast<uint32_t>(B_BYTES) >> 4;
+    const uint32_t a_k16 = a_step >> 4, b_k16 = b_step >> 4;
     int stage = 0; uint32_t phase = 0;
-    if constexpr (FI) {
-      // Lean issue path.  The general loop below rebuilds eight shared-memory descriptors per k-block from byte addresses
-      // (shift, mask, layout bits chosen by runtime flags: ~50 uniform-datapath instructions and 16 R2UR in the SASS) and
-      // walks two jump tables for the diagnostics stamps - ~110 instructions between the barrier and the first
-      // tcgen05.mma, against 4 x 56 cycles of tensor work at N <= 64 (0.14 us of fixed cost per k-block).
-      // A descriptor's start-address field is (address >> 4) in its low 14 bits and every operand address is a multiple
-      // of 16 below 256 KB, so the field advances LINEARLY: one descriptor per operand is built before the loop, a
-      // k-block adds stage * (slot >> 4), a K = 16 slice adds (step >> 4) - no carry can leave the field.
-      static_assert(CG == 1, "the lean issue path is single-CTA");
-      const uint64_t a0 = p.a_mn ? desc_mn(a_base) : desc_k(a_base), b0 = p.b_mn ? desc_mn(b_base) : desc_k(b_base);
-      const uint32_t a_slot16 = static_cast<uint32_t>(A_SLOT) >> 4, b_slot16 = static_cast<uint32_t>(B_BYTES) >> 4;
-      const uint32_t a_k16 = a_step >> 4, b_k16 = b_step >> 4;
-      const uint16_t cmask = static_cast<uint16_t>((1u << p.cn) - 1u);
-      for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(&full[stage], phase, 2);
-        if (p.dbg) { if (kb == 0) P3D_STAMP(3); if (kb == 4) P3D_STAMP(11); if (kb == 8) P3D_STAMP(12); if (kb == 12) P3D_STAMP(13); }
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = a0 + static_cast<uint32_t>(stage) * a_slot16, bd = b0 + static_cast<uint32_t>(stage) * b_slot16;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(tmem_base, ad + static_cast<uint32_t>(k) * a_k16, bd + static_cast<uint32_t>(k) * b_k16, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (p.cn > 1) umma_commit_mcast(&empty[stage], cmask);
-          else umma_commit(&empty[stage]);
-          if (kb == nk - 1) umma_commit(accf);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    } else
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(&full[stage], phase, 2);
-      if (kb == 0) P3D_STAMP(3);
-      if (kb == 4) P3D_STAMP(11);
-      if (kb == 8) P3D_STAMP(12);
-      if (kb == 12) P3D_STAMP(13);
+      if (p.dbg) { if (kb == 0) P3D_STAMP(3); if (kb == 4) P3D_STAMP(11); if (kb == 8) P3D_STAMP(12); if (kb == 12) P3D_STAMP(13); }
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t aa = a_base + stage * A_SLOT, bb = b_base + stage * B_BYTES;
+        const uint64_t ad = a0 + static_cast<uint32_t>(stage) * a_slot16, bd = b0 + static_cast<uint32_t>(stage) * b_slot16;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = p.a_mn ? desc_mn(aa + k * a_step) : desc_k(aa + k * a_step);
-          const uint64_t bd = p.b_mn ? desc_mn(bb + k * b_step) : desc_k(bb + k * b_step);
-          if constexpr (cg == 2) umma_bf16_ss_2sm(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        if constexpr (cg == 2) {
-          umma_commit_2sm(&empty[stage], 0x3);      // frees the slot in both CTAs of the pair
-          if (kb == nk - 1) umma_commit_2sm(accf, 0x3);
-        } else {
-          if (p.cn > 1) umma_commit_mcast(&empty[stage], static_cast<uint16_t>((1u << p.cn) - 1u));
-          else umma_commit(&empty[stage]);
-          if (kb == nk - 1) umma_commit(accf);
-        }
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16_ss(tmem_base, ad + static_cast<uint32_t>(k) * a_k16, bd + static_cast<uint32_t>(k) * b_k16, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (kb == nk - 1) umma_commit(accf);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
     }
     P3D_STAMP(4);
   } else {
@@ -334,25 +349,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // global access (C, residual, bf16 output, fp32 reductions) is then 4 full 128-byte lines per instruction, bias
     // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
     if constexpr (OUT == 3 || OUT == 4) {
-      // ------------------------------------------------------------ small-batch fused training epilogues
-      // M <= 128: this CTA holds ALL rows of its columns, so the batch statistics of BatchNorm (forward) and the
-      // column sums of its backward pass are CTA-local: two passes over the TMEM accumulator with a named barrier
-      // in between replace the GEMM + statistics + finalize + activation kernels (3 launches -> 1, both directions).
+      // ------------------------------------------------------------ fused training epilogues
+      // Two passes over the TMEM accumulator with the column statistics of the (global) batch in between
+      // (column_totals): GEMM + statistics + finalize + activation kernels -> 1 launch, both directions.
       const int ew = warp & 3, half = (warp - 2) >> 2;
       const int hw = p.bn >= 64 ? p.bn / 2 : 32;
       const int cbeg = half * hw, cend = (cbeg + hw < p.bn) ? cbeg + hw : p.bn;
       const train::StepScalars* sc = static_cast<const train::StepScalars*>(p.ft.sc);
+      const int et = (warp - 2) * 32 + lane;
+      // data parallel: the sequence number of this exchange - read before anybody of this grid can have advanced it
+      unsigned long long seq = 0;
+      if (p.ft.world > 1) seq = static_cast<const p2p::Peers*>(p.ft.peers)->p[p.ft.rank]->seq + 1;
       grid_dependency_wait();
       const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
-      const int et = (warp - 2) * 32 + lane;
       for (int j = et; j < p.bn; j += EPI_THREADS) sbias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       named_bar_sync(1, EPI_THREADS);
       constexpr int TP = 36;
       const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
       const uint32_t sbias_s = smem_u32(sbias);
       const int rg = lane >> 3, cq = (lane & 7) * 4;
-      const int mrow0 = ew * 32 + rg;                          // m0 == 0
+      const int mrow0 = m0 + ew * 32 + rg;
       const float keep = sc->keep, inv_keep = sc->inv_keep;
+      const bool writer = (blockIdx.y == 0);                   // of the CTAs that share a column: the one that stores per-column results
       mbar_wait(accf, 0, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
@@ -384,16 +402,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           *reinterpret_cast<float4*>(q1 + 256) = make_float4(s2[0], s2[1], s2[2], s2[3]);
         }
       };
-      auto totals = [&](int c0, float (&S1)[4], float (&S2)[4]) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = c0 + cq + j;
-          S1[j] = (scol[c] + scol[512 + c]) + (scol[1024 + c] + scol[1536 + c]);
-          S2[j] = (scol[256 + c] + scol[768 + c]) + (scol[1280 + c] + scol[1792 + c]);
-        }
-      };
       const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
-      const float invB = p.ft.invB;
+      const double invB = static_cast<double>(p.ft.invB);
       if constexpr (OUT == 3) {
         // ---- forward: z = alpha acc + bias; batch statistics; BN, ReLU, dropout, residual
         if (has_bn) {
@@ -408,36 +418,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             publish(c0, s1, s2);
           }
+          named_bar_sync(1, EPI_THREADS);
+          column_totals(p, n0, et, scol, stot, sflag, seq);
+          // mean / biased variance over the global batch in double, as train.cu's bn_finalize_kernel does it;
+          // moving averages with momentum .99 (one writer per column)
+          for (int j = et; j < p.bn; j += EPI_THREADS) {
+            const int n = n0 + j;
+            const double mu = stot[j] * invB;
+            double var = stot[256 + j] * invB - mu * mu;
+            if (var < 0) var = 0;
+            const float muf = static_cast<float>(mu), rsf = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+            sfin[j] = muf; sfin[256 + j] = rsf;
+            if (writer && n < p.N) {
+              p.ft.mean[n] = muf; p.ft.rstd[n] = rsf;
+              p.ft.mov_mean[n] = p.ft.mov_mean[n] * kBnMomentum + muf * (1.f - kBnMomentum);
+              p.ft.mov_var[n] = p.ft.mov_var[n] * kBnMomentum + static_cast<float>(var) * (1.f - kBnMomentum);
+            }
+          }
+          named_bar_sync(1, EPI_THREADS);
         }
-        named_bar_sync(1, EPI_THREADS);
         for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
           float o[8][4];
           chunk(c0, o);
           const int n = n0 + c0 + cq;
           float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
           if (has_bn) {
-            float S1[4], S2[4];
-            totals(c0, S1, S2);
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
             ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
-            float var[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              mu[j] = S1[j] * invB;
-              var[j] = fmaxf(S2[j] * invB - mu[j] * mu[j], 0.f);        // biased, as TF's non-fused path
-              rs[j] = 1.f / sqrtf(var[j] + kBnEps);
-            }
-            if (ew == 0 && rg == 0) {                                   // one writer per column
-              *reinterpret_cast<float4*>(p.ft.mean + n) = make_float4(mu[0], mu[1], mu[2], mu[3]);
-              *reinterpret_cast<float4*>(p.ft.rstd + n) = make_float4(rs[0], rs[1], rs[2], rs[3]);
-              float4 mm = *reinterpret_cast<const float4*>(p.ft.mov_mean + n), mv = *reinterpret_cast<const float4*>(p.ft.mov_var + n);
-              mm.x = mm.x * kBnMomentum + mu[0] * (1.f - kBnMomentum); mm.y = mm.y * kBnMomentum + mu[1] * (1.f - kBnMomentum);
-              mm.z = mm.z * kBnMomentum + mu[2] * (1.f - kBnMomentum); mm.w = mm.w * kBnMomentum + mu[3] * (1.f - kBnMomentum);
-              mv.x = mv.x * kBnMomentum + var[0] * (1.f - kBnMomentum); mv.y = mv.y * kBnMomentum + var[1] * (1.f - kBnMomentum);
-              mv.z = mv.z * kBnMomentum + var[2] * (1.f - kBnMomentum); mv.w = mv.w * kBnMomentum + var[3] * (1.f - kBnMomentum);
-              *reinterpret_cast<float4*>(p.ft.mov_mean + n) = mm;
-              *reinterpret_cast<float4*>(p.ft.mov_var + n) = mv;
-            }
+            const float4 m4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), r4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
+            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
           }
           float4 hr[8];
           uchar4 mi[8];
@@ -463,7 +472,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (dropout) {
               uint8_t kb[4] = {mi[i].x, mi[i].y, mi[i].z, mi[i].w};
               if (!p.ft.mask_in) {
-                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer), static_cast<uint32_t>(m), static_cast<uint32_t>(n >> 2));
+                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer),
+                                                      static_cast<uint32_t>(p.ft.row0 + m), static_cast<uint32_t>(n >> 2));
                 kb[0] = train::keep_bit(w4.x, keep); kb[1] = train::keep_bit(w4.y, keep); kb[2] = train::keep_bit(w4.z, keep); kb[3] = train::keep_bit(w4.w, keep);
               }
 #pragma unroll
@@ -471,14 +481,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               *reinterpret_cast<uchar4*>(p.ft.mask + off) = make_uchar4(kb[0], kb[1], kb[2], kb[3]);
             }
             r[0] += hr[i].x; r[1] += hr[i].y; r[2] += hr[i].z; r[3] += hr[i].w;
-            *reinterpret_cast<float4*>(p.ft.h + off) = make_float4(r[0], r[1], r[2], r[3]);
+            if (p.ft.h) *reinterpret_cast<float4*>(p.ft.h + off) = make_float4(r[0], r[1], r[2], r[3]);
             __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.ft.hb) + off) = pk;
           }
         }
       } else {
-        // ---- backward: dh = alpha acc (+ res); da = dh * dropout * relu'(act); BN backward with CTA-local sums
+        // ---- backward: dh = alpha acc (+ res); da = dh * dropout * relu'(act); BN backward with the global column sums
         auto da_of = [&](int c0, float (&o)[8][4], float (&xh)[8][4], const float (&mu)[4], const float (&rs)[4], const float (&ga)[4],
                          const float (&be)[4], bool store_dh) {
           const int n = n0 + c0 + cq;
@@ -535,28 +545,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           publish(c0, s1, s2);
         }
         named_bar_sync(1, EPI_THREADS);
+        column_totals(p, n0, et, scol, stot, sflag, seq);
+        // sum da (= dbeta, or the bias gradient) and sum da * xhat (= dgamma) over the global batch; every rank holds
+        // them in full, so they enter the flat gradient pre-divided by the world size
+        for (int j = et; j < p.bn; j += EPI_THREADS) {
+          const int n = n0 + j;
+          const float P = static_cast<float>(stot[j]), Q = static_cast<float>(stot[256 + j]);
+          sfin[j] = P; sfin[256 + j] = Q;
+          if (writer && n < p.N) {
+            if (has_bn) { p.ft.gbeta[n] = P * p.ft.pg_scale; p.ft.ggamma[n] = Q * p.ft.pg_scale; }
+            else p.ft.gbias[n] = P * p.ft.pg_scale;
+          }
+        }
+        named_bar_sync(1, EPI_THREADS);
+        const float invBf = p.ft.invB;
         for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4], P[4], Q[4];
+          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4];
           chunk(c0, o);
           bn_consts(c0, mu, rs, ga, be);
           da_of(c0, o, xh, mu, rs, ga, be, false);
-          totals(c0, P, Q);
+          const float4 P4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), Q4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
+          const float P[4] = {P4.x, P4.y, P4.z, P4.w}, Q[4] = {Q4.x, Q4.y, Q4.z, Q4.w};
           const int n = n0 + c0 + cq;
-          if (ew == 0 && rg == 0) {                                     // one writer per column
-            if (has_bn) {
-              *reinterpret_cast<float4*>(p.ft.gbeta + n) = make_float4(P[0], P[1], P[2], P[3]);
-              *reinterpret_cast<float4*>(p.ft.ggamma + n) = make_float4(Q[0], Q[1], Q[2], Q[3]);
-            } else {
-              *reinterpret_cast<float4*>(p.ft.gbias + n) = make_float4(P[0], P[1], P[2], P[3]);
-            }
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
             if (m >= p.M) continue;
             float d[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = has_bn ? ga[j] * rs[j] * (o[i][j] - P[j] * invB - xh[i][j] * (Q[j] * invB)) : o[i][j];
+            for (int j = 0; j < 4; ++j) d[j] = has_bn ? ga[j] * rs[j] * (o[i][j] - P[j] * invBf - xh[i][j] * (Q[j] * invBf)) : o[i][j];
             __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.ft.dzb) + static_cast<size_t>(m) * p.N + n) = pk;
@@ -574,78 +591,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const bool first_split = (blockIdx.z == 0);
     grid_dependency_wait();       // residual / alpha / C written by earlier kernels
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
-    const float inv_keep2 = (CS == 2 && p.ft.dropout) ? static_cast<const train::StepScalars*>(p.ft.sc)->inv_keep : 1.f;
     const int et = (warp - 2) * 32 + lane;       // 0..255
     for (int j = et; j < p.bn; j += EPI_THREADS) {
       sbias[j] = (first_split && p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
     }
     named_bar_sync(1, EPI_THREADS);
     const uint32_t sbias_s = smem_u32(sbias);
-    if constexpr (TS) {
-      // ---------------------------------------------------------- TMA-store epilogue (OUT 0 / 1, no residual, CS 0 / 1)
-      // tcgen05.ld hands every lane one ROW of a 32 x 32 chunk; that is exactly how a TMA box lies in shared memory, so
-      // the chunk is written row-per-lane into a dense 32 x 128 B tile - 16-byte pieces XOR-swizzled by the row (the
-      // SWIZZLE_128B pattern of tm_c: conflict-free for the per-lane st.shared.v4 AND for the column reads of the
-      // statistics below) - and one lane sends it off.  No transpose, no per-lane global store, ragged M / N edges are
-      // clipped by the tensor map.  Two staging tiles per warp: chunk i+1 is written while the TMA engine still reads
-      // chunk i (cp.async.bulk.wait_group.read 1).  Column sums: lane = column, one conflict-free LDS per row.
-      static_assert(OUT <= 1 && !RES && CS <= 1 && CG == 1 && OCC == 1, "TS epilogue: fp32 store / reduction without residual only");
-      uint8_t* stg = smem + (warp - 2) * 8192;               // 2 x 4 KB per warp in the freed operand ring (1024-byte aligned)
-      const uint32_t stg_s = smem_u32(stg);
-      const int row_g = m0 + ew * 32;                        // first global row of this warp's TMEM lane quadrant
-      const int rows_live = (p.M - row_g) < 32 ? (p.M - row_g) : 32;   // <= 0: the whole quadrant lies below the matrix
-      mbar_wait(accf, 0, 3);
-      if (warp == 2) P3D_STAMP(5);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      uint32_t v[32];
-      if (cbeg < cend && n0 + cbeg < p.N) tmem_ld_32x32b_x32(taddr + cbeg, v);
-      int buf = 0;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        if (n0 + c0 >= p.N) break;     // warp-uniform
-        const bool more = (c0 + 32 < cend) && (n0 + c0 + 32 < p.N);
-        tmem_ld_wait();
-        uint32_t o[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = lds128(sbias_s + (c0 + 4 * j) * 4);      // same address in every lane: broadcast
-          o[4 * j + 0] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 0]) + b4.x);
-          o[4 * j + 1] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 1]) + b4.y);
-          o[4 * j + 2] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 2]) + b4.z);
-          o[4 * j + 3] = __float_as_uint(alpha * __uint_as_float(v[4 * j + 3]) + b4.w);
-        }
-        if (more) tmem_ld_32x32b_x32(taddr + c0 + 32, v);      // in flight while this chunk is staged and sent
-        if (lane == 0) tma_store_wait_read<1>();               // the store issued two chunks ago has read this staging tile
-        __syncwarp();                                          // ... and every lane is done with its column reads of it
-        const uint32_t tb = stg_s + buf * 4096;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(tb + lane * 128 + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0 && rows_live > 0) {
-          if (OUT == 1) tma_reduce_add_2d(&tm_c, stg + buf * 4096, n0 + c0, row_g);   // split-K / accumulate: C += tile, added in the L2
-          else tma_store_2d(&tm_c, stg + buf * 4096, n0 + c0, row_g);
-          tma_store_commit();
-        }
-        if (CS == 1) {
-          // lane = column c0 + lane: piece (lane / 4) of row r sits at piece index (lane / 4) ^ (r % 8) -> the 32 lanes of
-          // one row read hit 32 different banks.  Rows >= M hold bias (or stale operand rows of a short tile): skipped.
-          float s1 = 0.f, s2 = 0.f;
-          const uint32_t cb = tb + (lane & 3) * 4;
-          const uint32_t piece = static_cast<uint32_t>(lane >> 2);
-#pragma unroll 8
-          for (int r = 0; r < rows_live; ++r) {
-            const float q = lds32(cb + r * 128 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4));
-            s1 += q; s2 += q * q;
-          }
-          scol[ew * 512 + c0 + lane] = s1;                     // this quadrant's partial sums (one writer per slot)
-          scol[ew * 512 + 256 + c0 + lane] = s2;
-        }
-        buf ^= 1;
-      }
-      if (lane == 0) tma_store_wait<0>();                      // all of this warp's stores are complete before the CTA retires
-    } else {
+    {
     constexpr int TP = 36;                                   // tile pitch in floats (144 B): conflict-free both ways
     const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
     const int rg = lane >> 3, cq = (lane & 7) * 4;           // row group (rows rg, rg+4, ...), first of this lane's 4 columns
@@ -676,24 +628,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const float4 b4 = lds128(sbias_s + (c0 + cq) * 4);
       float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
       if (fast) {
-        // CS == 2: this chunk's pre-activations / keep-mask and the per-column BatchNorm constants; none of them
-        // depends on the accumulator, so the loads are in flight while the tile is read back from shared memory
-        float4 z4[CS == 2 ? 8 : 1];
-        uchar4 mk[CS == 2 ? 8 : 1];
-        float4 bmu, brs, bga, bbe;
-        if (CS == 2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = mrow0 + 4 * i;
-            z4[i] = make_float4(0.f, 0.f, 0.f, 0.f); mk[i] = make_uchar4(1, 1, 1, 1);
-            if (m < p.M) {
-              z4[i] = __ldg(reinterpret_cast<const float4*>(p.ft.z + static_cast<size_t>(m) * p.N + n));
-              if (p.ft.dropout) mk[i] = *reinterpret_cast<const uchar4*>(p.ft.mask + static_cast<size_t>(m) * p.N + n);
-            }
-          }
-          bmu = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)); brs = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
-          bga = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)); bbe = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
-        }
         float4 t4[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t4[i] = lds128(tile_s + ((i * 4 + rg) * TP + cq) * 4);
@@ -735,22 +669,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (live) *reinterpret_cast<uint2*>(p.out_b + static_cast<size_t>(m) * p.ldob + n) = q;
           } else {
             if (use_res) { o[0] += r4[i].x; o[1] += r4[i].y; o[2] += r4[i].z; o[3] += r4[i].w; }
-            if (CS == 2) {
-              // o = dh of this hidden layer (the gradient that bypassed the block included): pass A of the BatchNorm backward
-              const float zz[4] = {z4[i].x, z4[i].y, z4[i].z, z4[i].w};
-              const unsigned char kk[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
-              const float mu[4] = {bmu.x, bmu.y, bmu.z, bmu.w}, rs[4] = {brs.x, brs.y, brs.z, brs.w};
-              const float ga[4] = {bga.x, bga.y, bga.z, bga.w}, be[4] = {bbe.x, bbe.y, bbe.z, bbe.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float xh = (zz[j] - mu[j]) * rs[j];
-                const float act = ga[j] * xh + be[j];
-                float gr = o[j];
-                if (p.ft.dropout) gr = kk[j] ? gr * inv_keep2 : 0.f;
-                const float da = (live && act > 0.f) ? gr : 0.f;
-                cs1[j] += da; cs2[j] += da * xh;
-              }
-            }
             float* crow = p.C + static_cast<size_t>(m) * p.ldc + n;
             if (live) {
               if (OUT == 1) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
@@ -773,7 +691,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int j = 0; j < 4; ++j) {
             if (n + j >= p.N) continue;
             float o = alpha * tv[j] + bias[j];
-            if (CS == 1) { cs1[j] += o; cs2[j] += o * o; }     // CS == 2 never takes the ragged path (checked by plan())
+            if (CS == 1) { cs1[j] += o; cs2[j] += o * o; }
             if (OUT == 2) {
               __nv_bfloat16 ob = __float2bfloat16_rn(p.relu ? fmaxf(o, 0.f) : o);
               if (use_res) ob = __float2bfloat16_rn(__bfloat162float(ob) + __bfloat162float(p.res_b[static_cast<size_t>(m) * p.ldrb + n + j]));
@@ -800,7 +718,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     }
-    }   // !TS
+    }
     if (CS) {
       named_bar_sync(1, EPI_THREADS);
       for (int j = et; j < p.bn; j += EPI_THREADS) {        // one global fp64 atomic per column per CTA
@@ -816,12 +734,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   if (warp == 2) P3D_STAMP(6);
   tc_fence_before();
-  if (p.cn > 1 || cg == 2) cluster_sync(); else __syncthreads();     // no CTA may leave while a peer can still arrive on its barriers
+  __syncthreads();
   if (warp == 0) P3D_STAMP(7);
-  if (warp == 1) {
-    tc_fence_after();
-    if constexpr (cg == 2) tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.bn)); else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn));
-  }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
 }
 
 // ----------------------------------------------------------------------------- MMA issue-rate probe
@@ -898,55 +813,45 @@ static int make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t
   return P3D_OK;
 }
 
-// fp32 row-major C [M][N] (pitch ldc elements) for the TS epilogue: box 32 columns (128 B) x 32 rows, 128B swizzle;
-// stores / reductions beyond M or N are clipped by the TMA engine
-static int make_map_c(CUtensorMap* out, const float* base, uint64_t N, uint64_t M, uint64_t ldc) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return P3D_ERR_CUDA; }
-  cuuint64_t gdim[2] = {N, M};
-  cuuint64_t gstride[1] = {ldc * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (C) failed with CUresult %d", (int)r); return P3D_ERR_CUDA; }
-  return P3D_OK;
+// A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
+struct PlanData { CUtensorMap ta, tb; Params p; dim3 grid; int pdl; int fused_mode; int coop; };
+static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
+
+// tile width: the widest BN that still gives the grid about one CTA per SM; a split-K problem keeps the
+// wide tile (better MMA efficiency) and fills the machine through gridDim.z instead
+static int pick_bn(int M, int N, int K, bool split_k, bool b_mn) {
+  const int mt = (M + BM - 1) / BM;
+  const int n64 = (N + 63) / 64 * 64;
+  const int kblocks = (K + BK - 1) / BK;
+  int bn = 256;
+  while (bn > 64 && (bn > n64 || (!split_k && mt * ((N + bn - 1) / bn) < 100))) bn >>= 1;
+  // a split-K problem whose K is only a few blocks long (weight gradients of a small batch) is all epilogue:
+  // narrow tiles spread it over the machine instead
+  if (split_k && kblocks <= 4) { while (bn > 64 && mt * ((N + bn - 1) / bn) < 100) bn >>= 1; }
+  // one short M tile (small-batch inference): 32-wide tiles put twice as many SMs on the weight stream
+  if (bn == 64 && !b_mn && !split_k && mt == 1 && N >= 256 && (N % 32) == 0) bn = 32;
+  return bn;
 }
 
-// A: a_mn ? [K][M] : [M][K];  B: b_mn ? [K][N] : [N][K]  (bf16, pitches lda/ldb in elements)
-struct PlanData { CUtensorMap ta, tb, tc; Params p; dim3 grid; int pdl; int fused_mode; };
-static_assert(sizeof(PlanData) <= sizeof(GemmPlan::blob), "GemmPlan::blob too small");
+// Can the fused training epilogues (modes 3 / 4) serve an M x N layer?  Every tile must be resident at once (the grid
+// meets at a barrier while the accumulators wait in TMEM), i.e. tiles <= SMs.
+bool fused_fits(int M, int N, int K, int num_sms) {
+  if ((N % 32) != 0) return false;
+  const int bn = pick_bn(M, N, K, false, true);
+  return ((M + BM - 1) / BM) * ((N + bn - 1) / bn) <= num_sms;
+}
 
 int plan(const GemmArgs& g, GemmPlan* out) {
   P3D_REQUIRE(g.M >= 1 && g.N >= 1 && g.K >= 1 && g.A && g.B && (g.C || g.out_bf16), "tc_gemm: bad argument");
-  const int num_sms = 148;
+  int num_sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int mt = (g.M + BM - 1) / BM;
-  const int n64 = (g.N + 63) / 64 * 64;
   const int kblocks = (g.K + BK - 1) / BK;
-  // tile width: the widest BN that still gives the grid about one CTA per SM; a split-K problem keeps the
-  // wide tile (better MMA efficiency) and fills the machine through gridDim.z instead
-  int bn = 256;
-  while (bn > 64 && (bn > n64 || (!g.split_k && mt * ((g.N + bn - 1) / bn) < 100))) bn >>= 1;
-  // a split-K problem whose K is only a few blocks long (weight gradients of a small batch) is all epilogue:
-  // narrow tiles spread it over the machine instead
-  if (g.split_k && kblocks <= 4) { while (bn > 64 && mt * ((g.N + bn - 1) / bn) < 100) bn >>= 1; }
-  // one short M tile (small-batch inference): 32-wide tiles put twice as many SMs on the weight stream
-  if (bn == 64 && !g.b_mn && !g.split_k && mt == 1 && g.N >= 256 && (g.N % 32) == 0) bn = 32;
-  // Two CTAs per SM (P3D_GEMM_OCC2=1, opt-in until measured): for problems with more than one 128-wide tile per SM,
-  // 128 x 128 tiles with a 96 KB ring; the second resident CTA hides the first one's prologue and epilogue.
-  static const bool occ2_env = [] { const char* e = getenv("P3D_GEMM_OCC2"); return e && e[0] == '1'; }();
-  int occ = 1;
-  const int tiles128 = mt * ((g.N + 127) / 128);
-  if (occ2_env && !g.pdl && !g.fused_mode && !g.out_bf16 && bn >= 128 &&
-      (g.split_k ? (kblocks >= 16 && tiles128 >= 32) : (tiles128 > num_sms))) {
-    occ = 2;
-    bn = 128;
-  }
+  const int bn = pick_bn(g.M, g.N, g.K, g.split_k != 0, g.b_mn != 0);
   const int nt = (g.N + bn - 1) / bn;
   int splits = 1;
   if (g.split_k) {
-    splits = occ * num_sms / (mt * nt);
+    splits = num_sms / (mt * nt);
     if (splits < 1) splits = 1;
     if (splits > kblocks) splits = kblocks;
     if (splits > 32) splits = 32;
@@ -956,25 +861,10 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   PlanData* d = reinterpret_cast<PlanData*>(out->blob);
   // K-major A of a short problem: fetch only the rows that exist (the MMA still reads 128 smem rows; what it makes
   // of the stale ones lands in accumulator rows >= M, which are never stored)
-  // The CTAs of one M tile (adjacent N tiles) read the same A tile: in a cluster of cn of them each fetches 1/cn of
-  // the rows and TMA-multicasts it to all.  Measured on B200 (M=64, N=K=1024): the mainloop got SLOWER (5.7 -> 6.2 us)
-  // although every CTA fetches half the bytes - a k-block costs ~0.2 us + 0.5 ns per 128-byte row whatever its size,
-  // so bytes are not what bounds a short-M GEMM.  Kept behind P3D_GEMM_MCAST=1 for the large-M experiments of round 2.
-  int cn = 1;
-  static const bool mcast = [] { const char* e = getenv("P3D_GEMM_MCAST"); return e && e[0] == '1'; }();
-  if (!g.a_mn && mcast) cn = (nt % 4 == 0) ? 4 : ((nt % 2 == 0) ? 2 : 1);
-  // CTA pairs along M (cta_group::2): a 256 x BN tile per pair, each CTA fetches its own A rows and half of the B tile,
-  // i.e. 32 KB instead of 48 KB per k-block at BN = 256.  The large-M GEMMs of the training step are bound by the
-  // L2 -> SM operand stream, which this cuts by a third.  Opt-in (P3D_GEMM_CG2=1) until measured.
-  static const bool pair_env = [] { const char* e = getenv("P3D_GEMM_CG2"); return e && e[0] == '1'; }();
-  int cg = 1;
-  if (occ == 2) cn = 1;
-  if (pair_env && occ == 1 && cn == 1 && !g.pdl && !g.fused_mode && !g.out_bf16 && g.M >= 2 * BM && bn >= 128) cg = 2;   // the fp32-output epilogues have pair instantiations
-  int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
-  if (cn > 1) a_rows = (a_rows + 8 * cn - 1) / (8 * cn) * (8 * cn);     // every share is whole 8-row swizzle groups
-  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows / cn));
+  const int a_rows = (!g.a_mn && g.M < BM) ? ((g.M + 7) / 8 * 8) : BM;
+  if (!g.a_mn) P3D_TRY(make_map(&d->ta, g.A, g.K, g.M, g.lda, a_rows));
   else P3D_TRY(make_map(&d->ta, g.A, g.M, g.K, g.lda, BK));
-  if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn / cg));
+  if (!g.b_mn) P3D_TRY(make_map(&d->tb, g.B, g.K, g.N, g.ldb, bn));
   else P3D_TRY(make_map(&d->tb, g.B, g.N, g.K, g.ldb, BK));
   Params& p = d->p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.bn = bn; p.k_per_split = kps; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
@@ -983,44 +873,37 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   p.colsum = g.colsum;
   p.out_b = static_cast<__nv_bfloat16*>(g.out_bf16); p.ldob = g.ld_out_bf16;
   p.res_b = static_cast<const __nv_bfloat16*>(g.res_bf16); p.ldrb = g.ld_res_bf16; p.relu = g.relu;
-  p.cn = cn;
-  p.cg = cg;
-  p.occ = occ;
-  // TMA-store epilogue (P3D_GEMM_TMASTORE=1, opt-in until measured on the GPU): fp32 C without a residual operand, pitch and
-  // base such that a tensor map can describe it; everything else keeps the st.global epilogues
-  static const bool ts_env = [] { const char* e = getenv("P3D_GEMM_TMASTORE"); return e && e[0] == '1'; }();
-  p.ts = (ts_env && g.C && !g.out_bf16 && !g.res && !g.fused_mode && cg == 1 && occ == 1 && cn == 1 && (g.ldc % 4) == 0 &&
-          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) ? 1 : 0;
-  // Lean MMA issue path (P3D_GEMM_FASTISSUE=1, opt-in until measured on the GPU): single-CTA, one-CTA-per-SM kernels
-  static const bool fi_env = [] { const char* e = getenv("P3D_GEMM_FASTISSUE"); return e && e[0] == '1'; }();
-  p.fi = (fi_env && cg == 1 && occ == 1 && g.fused_mode != 5) ? 1 : 0;
-  memset(&d->tc, 0, sizeof(d->tc));
-  if (p.ts) P3D_TRY(make_map_c(&d->tc, g.C, static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.M), static_cast<uint64_t>(g.ldc)));
   p.a_bytes = a_rows * BK * 2;
-  p.stages = (occ == 2 ? RING2_BYTES : RING_BYTES) / (p.a_bytes + (bn / cg) * BK * 2);
+  p.stages = RING_BYTES / (p.a_bytes + bn * BK * 2);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
+  // diagnostics: P3D_SYNC_TIMEOUT_S=<seconds> makes a grid / peer wait that long trap with a message; by default
+  // the fused epilogues wait for their peers like an NCCL collective does (ranks must stay in lockstep)
+  static const long long wait_ns = [] { const char* e = getenv("P3D_SYNC_TIMEOUT_S"); return e ? static_cast<long long>(atof(e) * 1e9) : 0LL; }();
+  p.wait_limit_ns = wait_ns;
   d->pdl = g.pdl;
   p.ft = g.fused;
   d->fused_mode = g.fused_mode;
-  if (g.fused_mode == 5) {
-    // any batch: the dh-producing GEMM also accumulates the BatchNorm backward sums of the layer it feeds
-    P3D_REQUIRE(g.colsum && g.C && !g.out_bf16 && splits == 1 && !g.accumulate, "tc_gemm: backward-sum epilogue needs colsum, fp32 C, unsplit K");
-    P3D_REQUIRE((g.N % 256) == 0 && g.ldc == g.N && (!g.res || g.ldres == g.N) && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0,
-                "tc_gemm: backward-sum epilogue needs N %% 256 == 0 and dense, aligned C / residual");
-    P3D_REQUIRE(g.fused.z && g.fused.mean && g.fused.rstd && g.fused.gamma && g.fused.beta && g.fused.sc && (!g.fused.dropout || g.fused.mask),
-                "tc_gemm: backward-sum epilogue operands missing");
-  } else if (g.fused_mode) {
+  d->coop = 0;
+  if (g.fused_mode) {
     P3D_REQUIRE(g.fused_mode == 3 || g.fused_mode == 4, "tc_gemm: unknown fused mode %d", g.fused_mode);
-    P3D_REQUIRE(mt == 1 && splits == 1 && (g.N % 32) == 0 && g.ldc == g.N && !g.out_bf16 && !g.colsum,
-                "tc_gemm: fused training epilogues need M <= 128, N %% 32 == 0, unsplit K, dense C");
+    P3D_REQUIRE(splits == 1 && (g.N % 32) == 0 && g.ldc == g.N && !g.out_bf16 && !g.colsum && !g.pdl,
+                "tc_gemm: fused training epilogues need N %% 32 == 0, unsplit K, dense C");
     P3D_REQUIRE(!g.res || g.ldres == g.N, "tc_gemm: fused epilogue residual must be dense");
+    const bool grid_sync = mt > 1 || g.fused.world > 1;
+    if (grid_sync) {
+      P3D_REQUIRE(g.fused.gsum && g.fused.gcount, "tc_gemm: grid-synchronised fused epilogue needs gsum / gcount");
+      P3D_REQUIRE(mt * nt <= num_sms, "tc_gemm: fused epilogue needs every tile resident (%d tiles, %d SMs)", mt * nt, num_sms);
+      P3D_REQUIRE(g.fused.world == 1 || (g.fused.peers && 2 * g.N + 1 <= p2p::MAXN), "tc_gemm: peer exchange not attached / vector too long");
+      d->coop = 1;
+    } else {
+      p.ft.gsum = nullptr;       // one tile: the column sums are CTA-local
+    }
   }
   P3D_REQUIRE(!(p.colsum && splits > 1), "tc_gemm: column sums need an unsplit K");
   P3D_REQUIRE(!(p.out_b && splits > 1), "tc_gemm: bf16 output needs an unsplit K");
-  if (cg == 2) d->grid = dim3((mt + 1) / 2 * 2, nt, splits);       // pairs: M tiles along x, an odd last one gets an all-out-of-range partner
-  else d->grid = dim3(nt, mt, splits);
+  d->grid = dim3(nt, mt, splits);
   out->valid = 1;
   return P3D_OK;
 }
@@ -1028,71 +911,32 @@ int plan(const GemmArgs& g, GemmPlan* out) {
 int launch(const GemmPlan& pl, cudaStream_t st) {
   P3D_REQUIRE(pl.valid, "tc_gemm: launch of an unplanned GEMM");
   const PlanData* d = reinterpret_cast<const PlanData*>(pl.blob);
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const Params);
   const Params& q = d->p;
   const int out = q.out_b ? 2 : (q.atomic ? 1 : 0);
   const bool res = q.out_b ? (q.res_b != nullptr) : (q.res != nullptr);
-  const int cs = q.colsum ? (d->fused_mode == 5 ? 2 : 1) : 0;
+  const int cs = q.colsum ? 1 : 0;
   KernelFn fn = nullptr;
 #define P3D_TCG_PICK(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S>;
-#define P3D_TCG_PICK2(O, R, S) if (out == O && res == R && cs == S) \
-    fn = q.cg == 2 ? tc_gemm_kernel<O, R, S, 2> : (q.occ == 2 ? tc_gemm_kernel<O, R, S, 1, 2> : tc_gemm_kernel<O, R, S, 1>);
-  P3D_TCG_PICK2(0, false, 0) P3D_TCG_PICK2(0, false, 1) P3D_TCG_PICK2(0, true, 0) P3D_TCG_PICK2(0, true, 1)
-  P3D_TCG_PICK(0, false, 2) P3D_TCG_PICK(0, true, 2)
-  P3D_TCG_PICK2(1, false, 0) P3D_TCG_PICK2(1, true, 0)
+  P3D_TCG_PICK(0, false, 0) P3D_TCG_PICK(0, false, 1) P3D_TCG_PICK(0, true, 0) P3D_TCG_PICK(0, true, 1)
+  P3D_TCG_PICK(1, false, 0) P3D_TCG_PICK(1, true, 0)
   P3D_TCG_PICK(2, false, 0) P3D_TCG_PICK(2, true, 0)
 #undef P3D_TCG_PICK
-#undef P3D_TCG_PICK2
-  if (q.ts) {      // plan() admits only these three combinations
-    fn = nullptr;
-    if (out == 0 && !res && cs == 0) fn = q.fi ? tc_gemm_kernel<0, false, 0, 1, 1, true, true> : tc_gemm_kernel<0, false, 0, 1, 1, true>;
-    if (out == 0 && !res && cs == 1) fn = q.fi ? tc_gemm_kernel<0, false, 1, 1, 1, true, true> : tc_gemm_kernel<0, false, 1, 1, 1, true>;
-    if (out == 1 && !res && cs == 0) fn = q.fi ? tc_gemm_kernel<1, false, 0, 1, 1, true, true> : tc_gemm_kernel<1, false, 0, 1, 1, true>;
-  } else if (q.fi) {
-#define P3D_TCG_PICKF(O, R, S) if (out == O && res == R && cs == S) fn = tc_gemm_kernel<O, R, S, 1, 1, false, true>;
-    P3D_TCG_PICKF(0, false, 0) P3D_TCG_PICKF(0, false, 1) P3D_TCG_PICKF(0, true, 0) P3D_TCG_PICKF(0, true, 1)
-    P3D_TCG_PICKF(1, false, 0) P3D_TCG_PICKF(1, true, 0) P3D_TCG_PICKF(2, false, 0) P3D_TCG_PICKF(2, true, 0)
-#undef P3D_TCG_PICKF
-  }
-  if (d->fused_mode == 3) fn = q.fi ? tc_gemm_kernel<3, false, 0, 1, 1, false, true> : tc_gemm_kernel<3, false, 0>;
-  if (d->fused_mode == 4) fn = q.fi ? tc_gemm_kernel<4, false, 0, 1, 1, false, true> : tc_gemm_kernel<4, false, 0>;
+  if (d->fused_mode == 3) fn = tc_gemm_kernel<3, false, 0>;
+  if (d->fused_mode == 4) fn = tc_gemm_kernel<4, false, 0>;
   P3D_REQUIRE(fn != nullptr, "tc_gemm: unsupported epilogue combination (out %d res %d colsum %d)", out, (int)res, (int)cs);
   static PerDeviceOnce attr;
   if (attr.needed()) {
     KernelFn all[] = {tc_gemm_kernel<0, false, 0>, tc_gemm_kernel<0, false, 1>, tc_gemm_kernel<0, true, 0>,
-                      tc_gemm_kernel<0, true, 1>, tc_gemm_kernel<0, false, 2>, tc_gemm_kernel<0, true, 2>,
-                      tc_gemm_kernel<1, false, 0>, tc_gemm_kernel<1, true, 0>,
+                      tc_gemm_kernel<0, true, 1>, tc_gemm_kernel<1, false, 0>, tc_gemm_kernel<1, true, 0>,
                       tc_gemm_kernel<2, false, 0>, tc_gemm_kernel<2, true, 0>,
-                      tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>,
-                      tc_gemm_kernel<0, false, 0, 2>, tc_gemm_kernel<0, false, 1, 2>, tc_gemm_kernel<0, true, 0, 2>,
-                      tc_gemm_kernel<0, true, 1, 2>, tc_gemm_kernel<1, false, 0, 2>, tc_gemm_kernel<1, true, 0, 2>,
-                      tc_gemm_kernel<0, false, 0, 1, 1, true>, tc_gemm_kernel<0, false, 1, 1, 1, true>,
-                      tc_gemm_kernel<1, false, 0, 1, 1, true>,
-                      tc_gemm_kernel<0, false, 0, 1, 1, true, true>, tc_gemm_kernel<0, false, 1, 1, 1, true, true>,
-                      tc_gemm_kernel<1, false, 0, 1, 1, true, true>,
-                      tc_gemm_kernel<0, false, 0, 1, 1, false, true>, tc_gemm_kernel<0, false, 1, 1, 1, false, true>,
-                      tc_gemm_kernel<0, true, 0, 1, 1, false, true>, tc_gemm_kernel<0, true, 1, 1, 1, false, true>,
-                      tc_gemm_kernel<1, false, 0, 1, 1, false, true>, tc_gemm_kernel<1, true, 0, 1, 1, false, true>,
-                      tc_gemm_kernel<2, false, 0, 1, 1, false, true>, tc_gemm_kernel<2, true, 0, 1, 1, false, true>,
-                      tc_gemm_kernel<3, false, 0, 1, 1, false, true>, tc_gemm_kernel<4, false, 0, 1, 1, false, true>};
+                      tc_gemm_kernel<3, false, 0>, tc_gemm_kernel<4, false, 0>};
     for (KernelFn f : all) P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    KernelFn two[] = {tc_gemm_kernel<0, false, 0, 1, 2>, tc_gemm_kernel<0, false, 1, 1, 2>, tc_gemm_kernel<0, true, 0, 1, 2>,
-                      tc_gemm_kernel<0, true, 1, 1, 2>, tc_gemm_kernel<1, false, 0, 1, 2>, tc_gemm_kernel<1, true, 0, 1, 2>};
-    for (KernelFn f : two) {
-      P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      P3D_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
     attr.mark();
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = d->p.occ == 2 ? SMEM2_BYTES : SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
-  if (d->p.cn > 1 || d->p.cg == 2) {
-    attrs[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    attrs[cfg.numAttrs].val.clusterDim.x = d->p.cg == 2 ? 2 : d->p.cn; attrs[cfg.numAttrs].val.clusterDim.y = 1;
-    attrs[cfg.numAttrs].val.clusterDim.z = 1;
-    cfg.attrs = attrs; ++cfg.numAttrs;
-  }
   if (d->pdl) {
     // programmatic dependent launch: this kernel may start while its predecessor in the stream drains; it orders
     // itself behind the predecessor's memory with griddepcontrol.wait
@@ -1100,7 +944,13 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
     attrs[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs; ++cfg.numAttrs;
   }
-  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->tc, d->p));
+  if (d->coop) {
+    // the grid meets at a barrier inside the kernel: the runtime must place every CTA before any of them waits
+    attrs[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
+    attrs[cfg.numAttrs].val.cooperative = 1;
+    cfg.attrs = attrs; ++cfg.numAttrs;
+  }
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, d->ta, d->tb, d->p));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

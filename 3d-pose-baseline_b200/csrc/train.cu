@@ -517,9 +517,10 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
     }
   }
   if (!w.stats) {
-    // doubles: stats [nh][2][L] | bwd sums [nh][2][L] | dots [nl] | loss [1]
-    P3D_CUDA(cudaMalloc(&w.stats, sizeof(double) * (4ull * nh * L + nl + 1)));
+    // doubles: stats [nh][2][L] | bwd sums [nh][2][L] | dots [nl] | loss [1] | grid-barrier words [2 nh][2] (unsigned)
+    P3D_CUDA(cudaMalloc(&w.stats, sizeof(double) * (4ull * nh * L + nl + 1 + 2ull * nh)));
     w.red = w.stats + 2ull * nh * L;
+    w.gcount = reinterpret_cast<unsigned*>(w.stats + 4ull * nh * L + nl + 1);
     P3D_CUDA(cudaMalloc(&w.mean, sizeof(float) * static_cast<size_t>(nh) * L));
     P3D_CUDA(cudaMalloc(&w.rstd, sizeof(float) * static_cast<size_t>(nh) * L));
     P3D_CUDA(cudaMalloc(&w.scal, sizeof(float) * (nl + 8)));
@@ -540,36 +541,21 @@ static int ensure_workspace(p3d_model* m, int64_t B) {
   return P3D_OK;
 }
 
-static bool fused_enabled() {
-  static const bool on = [] { const char* e = getenv("P3D_TRAIN_FUSED"); return !(e && e[0] == '0'); }();
-  return on;
-}
-// Bucketed gradient all-reduce overlapped with the backward pass: opt-in (P3D_DP_OVERLAP=1).  Measured, it costs more
-// than it hides on this node: 2 GPUs 610 -> 647 us and 8 GPUs 622 -> 657 us at 4096 poses, 869 -> 906 us at 32768 -
-// five NCCL launches instead of one, and their CTAs compete with the remaining GEMMs while the 17 MB exchange itself
-// is short over NVSwitch.  The default is one flat call after the backward pass.
-static bool overlap_enabled(int world) {
-  static const int force = [] { const char* e = getenv("P3D_DP_OVERLAP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
-  (void)world;
-  return force == 1;
-}
-// Pass A of the BatchNorm backward inside the dh-producing GEMM's epilogue (tc_gemm fused_mode 5): opt-in
-// (P3D_TRAIN_ACTFUSE=1).  Parity-green, but measured SLOWER on B200: 508 -> 561 us per step at 4096 poses, 2645 -> 3069 us
-// at 32768.  A tc_gemm CTA owns one tile, so nothing overlaps its epilogue; reading z and the keep-mask there (160 KB per
-// tile, a chunk at a time) runs at ~13 GB/s per SM, while bwd_act_kernel streams the same bytes at HBM speed.
-static bool act_fuse_enabled() {
-  static const bool on = [] { const char* e = getenv("P3D_TRAIN_ACTFUSE"); return e && e[0] == '1'; }();
-  return on;
-}
+// P3D_TRAIN_FUSED=0 forces the unfused path (GEMM + statistics + finalize + activation kernels) at every batch size; read
+// at every step so that tests can cover both paths in one process.
+static bool fused_enabled() { const char* e = getenv("P3D_TRAIN_FUSED"); return !(e && e[0] == '0'); }
 static inline dim3 colgrid(int cols, int64_t B) { return dim3((cols + 31) / 32, static_cast<unsigned>((B + RCH - 1) / RCH)); }
 static inline int egrid(long long n) { long long g = (n + 255) / 256; if (g > 148 * 8) g = 148 * 8; return static_cast<int>(g < 1 ? 1 : g); }
 
-// Forward + backward of a small batch (B <= 128, one GPU) with the BatchNorm / ReLU / dropout math fused into the
-// GEMM epilogues (tc_gemm.cu modes 3 and 4): the whole batch is one M tile, so the per-column batch statistics and
-// the column sums of the BN backward are CTA-local.  Per hidden layer: 1 forward launch (was GEMM + finalize +
-// activation) and 2 backward launches (weight gradient; data gradient fused with the previous layer's activation /
-// BN backward - was 4).
-static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, const uint8_t* mask_in, float* y, cudaStream_t st) {
+// Forward + backward with the BatchNorm / ReLU / dropout math fused into the GEMM epilogues (tc_gemm.cu modes 3 and 4).
+// Per hidden layer: 1 forward launch (was GEMM + finalize + activation) and 2 backward launches (weight gradient; data
+// gradient fused with the previous layer's activation / BN backward - was 4).  One M tile on one GPU: the column
+// statistics are CTA-local.  More tiles (every tile of a layer resident at once, i.e. up to ~4700 poses at width 1024)
+// and / or data parallel: the CTAs meet at a grid barrier between the two epilogue passes, and the SyncBN exchange
+// over NVLink peer memory happens right there, inside the GEMM (FusedTrain in common.cuh) - no separate reduction
+// launches, no NCCL call until the flat gradient all-reduce.
+static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, const uint8_t* mask_in, int64_t Bg, int64_t row0,
+                         float* y, cudaStream_t st) {
   using tcg::GemmArgs;
   TrainWorkspace& w = m->tw;
   const StepScalars* sc = static_cast<const StepScalars*>(w.sc);
@@ -578,8 +564,16 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
   const bool clip = m->cfg.max_norm != 0, residual = m->cfg.residual != 0;
   float* scale = w.scal;
   double* lossacc = w.red + 2ull * nh * L + nlay;
-  const float invB = 1.f / static_cast<float>(B);
+  const float invB = 1.f / static_cast<float>(Bg);
   const int Bi = static_cast<int>(B);
+  const bool dp = m->world > 1;
+  // grid-synchronised form: per layer and direction [2][L] doubles of column sums (w.stats forward, w.red backward,
+  // both zeroed at the top of the step) and an arrival counter + completion flag
+  auto grid_operands = [&](tcg::FusedTrain& f, double* sums, int which) {
+    f.gsum = sums; f.gcount = w.gcount + 2 * which;
+    f.row0 = row0; f.world = m->world; f.rank = m->rank; f.pg_scale = 1.f / static_cast<float>(m->world);
+    f.peers = dp ? p2p::device_peers(m) : nullptr;
+  };
   // ---------------------------------------------------------------- forward
   for (int li = 0; li < nh; ++li) {
     const Layer& ly = m->layers[li];
@@ -596,8 +590,11 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
       f.mean = w.mean + static_cast<size_t>(li) * L; f.rstd = w.rstd + static_cast<size_t>(li) * L;
       f.mov_mean = m->moving + ly.off_mm; f.mov_var = m->moving + ly.off_mv;
     }
-    f.h = w.h + li * bl; f.hb = w.hb + li * bl; f.mask = w.maskbuf + li * bl; f.mask_in = mask_in ? mask_in + li * bl : nullptr;
+    // the fp32 copy of h is only read back as a residual (by layer li + 2)
+    const bool h_needed = residual && (li % 2) == 0 && li + 2 < nh;
+    f.h = h_needed ? w.h + li * bl : nullptr; f.hb = w.hb + li * bl; f.mask = w.maskbuf + li * bl; f.mask_in = mask_in ? mask_in + li * bl : nullptr;
     f.hres = (residual && li >= 2 && (li % 2) == 0) ? w.h + (li - 2) * bl : nullptr;
+    grid_operands(f, w.stats + 2ull * li * L, li);
     P3D_TRY(tcg::gemm(g, st));
   }
   {
@@ -613,6 +610,7 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
   loss_dy_kernel<<<egrid(static_cast<long long>(ny)), 256, 0, st>>>(y, t, ny, 2.0f * invB / out, w.dy, lossacc, w.dyb, out, kOutPad);
   P3D_LAUNCH_CHECK();
   // ---------------------------------------------------------------- backward
+  // (data parallel: the loss sum rides on the first backward exchange, see fused_dgrad)
   __nv_bfloat16* dzb[2] = {w.dzb, w.dzb + bl};
   float* DH[2] = {w.dh, w.dres};
   int db = 0, keep = -1;
@@ -642,6 +640,8 @@ static int fwd_bwd_fused(p3d_model* m, const float* t, int64_t B, bool dropout, 
     } else {
       f.gbias = m->grad + lt.off_b;
     }
+    grid_operands(f, w.red + 2ull * tl * L, nh + tl);
+    if (dp && li == nh) f.xsum = lossacc;
     P3D_TRY(tcg::gemm(g, st));
     if (add) keep = -1;
     if (save) keep = slot;
@@ -718,7 +718,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   float* scale = w.scal;   // [nlay] clip scales
   const double invBg = 1.0 / static_cast<double>(Bg);
 
-  P3D_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * (4ull * nh * L + nlay + 1), st));
+  P3D_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * (4ull * nh * L + nlay + 1 + 2ull * nh), st));
   P3D_CUDA(cudaMemsetAsync(m->grad, 0, sizeof(float) * m->n_train, st));
   if (clip) P3D_CUDA(cudaMemsetAsync(m->norm2, 0, sizeof(double) * nlay, st));
   if (clip || tc) {
@@ -735,10 +735,13 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     to_bf16_kernel<<<egrid(static_cast<long long>(B) * kIn / 4 + 1), 256, 0, st>>>(x, w.xb, B, kIn, kIn);
     P3D_LAUNCH_CHECK();
   }
-  const bool fused = tc && m->world == 1 && B <= 128 && (L % 32) == 0 && fused_enabled();
-  bool overlap = false;
+  // fused epilogues: every tile of a hidden layer must be resident at once; data parallel they need the peer-memory
+  // exchange (otherwise the unfused path reduces through NCCL).  Every rank decides alike: B is the same everywhere up
+  // to one row and the host layer attaches peer memory on all ranks or on none.
+  const bool fused = tc && fused_enabled() && tcg::fused_fits(static_cast<int>(B + (m->world > 1 ? 1 : 0)), L, L, m->num_sms) &&
+                     (m->world == 1 || (p2p::ready(m) && 2 * L + 1 <= p2p::MAXN));
   if (fused) {
-    P3D_TRY(fwd_bwd_fused(m, t, B, dropout, mask_in, y, st));
+    P3D_TRY(fwd_bwd_fused(m, t, B, dropout, mask_in, Bg, row0, y, st));
   } else {
   // ---------------------------------------------------------------- forward
   for (int li = 0; li < nh; ++li) {
@@ -811,40 +814,6 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   // ---------------------------------------------------------------- backward
   float* G[3] = {w.dh, w.dres, w.dres + bl};
   int cur = 0, keepi = -1;
-  // Pass A of a BatchNorm layer's backward (da = dh * dropout * relu', column sums of da and da * xhat) rides in the
-  // epilogue of the GEMM that produces dh (tc_gemm fused_mode 5): one elementwise pass over [B, L] less per layer.
-  bool act_sums_fused = false;
-  auto fuse_act_sums = [&](GemmArgs& gd, int tl) -> bool {     // gd writes dh of hidden layer tl
-    const Layer& lt = m->layers[tl];
-    if (!tc || !lt.has_bn || (L % 256) != 0 || !act_fuse_enabled()) return false;
-    gd.fused_mode = 5;
-    gd.colsum = w.red + 2ull * tl * L;
-    tcg::FusedTrain& f = gd.fused;
-    f.sc = sc; f.has_bn = 1; f.dropout = dropout ? 1 : 0; f.layer = tl;
-    f.z = w.z + tl * bl; f.mask = maskbuf + tl * bl;
-    f.mean = w.mean + static_cast<size_t>(tl) * L; f.rstd = w.rstd + static_cast<size_t>(tl) * L;
-    f.gamma = m->theta + lt.off_gamma; f.beta = m->theta + lt.off_beta;
-    return true;
-  };
-  // Data parallel: a layer's weight gradient (the flat buffer is [all W | b, gamma, beta per layer]) is complete as
-  // soon as its GEMM has run, so its all-reduce starts right there on the side stream (a parallel branch of the
-  // captured graph) and travels over NVLink while the remaining layers are still being differentiated.
-  // Buckets: [W of the last hidden + output layer] | one per middle layer | [W of the first two layers], then the
-  // short vector tail (b, gamma, beta of every layer).  Only when the small reductions go over peer memory: then
-  // these buckets are the communicator's only operations and they all sit on one stream.
-  overlap = overlap_enabled(m->world) && m->world > 1 && p2p::ready(m) && nh >= 3;
-  int nev = 0;
-  auto bucket = [&](int lo, int hi) -> int {   // all-reduce the segments of layers lo..hi (inclusive)
-    if (!overlap) return P3D_OK;
-    const size_t n_w = m->layers[nh].off_w + static_cast<size_t>(m->layers[nh].K) * m->layers[nh].N;
-    const size_t beg = lo < 0 ? n_w : m->layers[lo].off_w;                       // lo < 0: the vector tail
-    const size_t end = lo < 0 ? m->n_train : (hi + 1 < nlay ? m->layers[hi + 1].off_w : n_w);
-    cudaEvent_t ready = w.ev[nev++ % 16];
-    P3D_CUDA(cudaEventRecord(ready, st));
-    P3D_CUDA(cudaStreamWaitEvent(w.side_stream, ready, 0));
-    P3D_NCCL(nccl()->AllReduce(m->grad + beg, m->grad + beg, end - beg, ncclFloat, ncclSum, static_cast<ncclComm_t>(m->nccl_comm), w.side_stream));
-    return P3D_OK;
-  };
   {
     const Layer& ly = m->layers[nh];
     if (tc) {
@@ -866,7 +835,6 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       gd.A = w.dyb; gd.lda = kOutPad;
       gd.B = w.wb + ly.off_w; gd.ldb = kOutPad;
       gd.C = G[cur]; gd.ldc = L; gd.alpha_dev = clip ? scale + nh : nullptr;
-      act_sums_fused = fuse_act_sums(gd, nh - 1);
       P3D_TRY(tcg::gemm(gd, st));
     } else {
       Epilogue e1; e1.alpha_dev = clip ? scale + nh : nullptr;
@@ -882,11 +850,8 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
     a.mask = maskbuf + li * bl; a.dz = (tc && ly.has_bn) ? nullptr : w.dz;   // tensor-core + BN: pass B recomputes da
     a.dzb = (tc && !ly.has_bn) ? w.dzb : nullptr; a.sums = w.red + 2ull * li * L; a.sc = sc;
     a.B = B; a.L = L; a.has_bn = ly.has_bn; a.dropout = dropout;
-    if (!act_sums_fused) {
-      bwd_act_kernel<<<dim3((L / 4 + 31) / 32, static_cast<unsigned>((B + RCH4 - 1) / RCH4)), dim3(32, 8), 0, st>>>(a);
-      P3D_LAUNCH_CHECK();
-    }
-    act_sums_fused = false;
+    bwd_act_kernel<<<dim3((L / 4 + 31) / 32, static_cast<unsigned>((B + RCH4 - 1) / RCH4)), dim3(32, 8), 0, st>>>(a);
+    P3D_LAUNCH_CHECK();
     if (ly.has_bn) {
       P3D_TRY(allreduce(m, a.sums, 2ull * L, ncclDouble, st));
       // dz (bf16 only on the tensor-core path) + dgamma / dbeta.  The sums are already global after the all-reduce,
@@ -915,9 +880,6 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       Epilogue e0;
       P3D_TRY(sgemm(true, false, ly.K, L, static_cast<int>(B), in, lda, w.dz, L, m->grad + ly.off_w, L, e0, st));
     }
-    if (li == nh - 1) P3D_TRY(bucket(nh - 1, nh));
-    else if (li >= 2) P3D_TRY(bucket(li, li));
-    else if (li == 0) { P3D_TRY(bucket(0, 1)); P3D_TRY(bucket(-1, -1)); }
     if (li > 0) {
       int nxt = 0;
       while (nxt == cur || nxt == keepi) ++nxt;
@@ -929,7 +891,6 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
         gd.B = w.wb + ly.off_w; gd.ldb = L;
         gd.C = G[nxt]; gd.ldc = L; gd.alpha_dev = clip ? scale + li : nullptr;
         if (add) { gd.res = G[keepi]; gd.ldres = L; }
-        act_sums_fused = fuse_act_sums(gd, li - 1);
         P3D_TRY(tcg::gemm(gd, st));
       } else {
         Epilogue e1; e1.alpha_dev = clip ? scale + li : nullptr;
@@ -940,14 +901,9 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
       cur = nxt;
     }
   }
-  if (overlap) {   // join: the optimizer needs every bucket
-    cudaEvent_t joined = w.ev[nev++ % 16];
-    P3D_CUDA(cudaEventRecord(joined, w.side_stream));
-    P3D_CUDA(cudaStreamWaitEvent(st, joined, 0));
-  }
   }   // unfused path
   // ---------------------------------------------------------------- gradient exchange + update
-  if (!overlap) P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
+  P3D_TRY(allreduce(m, m->grad, m->n_train, ncclFloat, st));
   if (clip) {
     clipdot_kernel<<<dim3(148, nlay), 256, 0, st>>>(m->theta, m->grad, tab, dots);
     P3D_LAUNCH_CHECK();
@@ -1029,6 +985,10 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
                int64_t Bg, int64_t row0, float* loss, float* lr_used, float* y, cudaStream_t st) {
   P3D_TRY(ensure_workspace(m, B));
   TrainWorkspace& w = m->tw;
+  if (m->l2_persist_used) {     // hand the L2 set-aside of the fused inference kernel back to normal traffic
+    cudaCtxResetPersistingL2Cache();
+    m->l2_persist_used = false;
+  }
   P3D_TRY(push_scalars(m, keep, seed, st));
   // data parallel: the NCCL all-reduces (SyncBN sums, gradient) are captured into the graph with everything else
   static const bool dp_graph = [] { const char* e = getenv("P3D_TRAIN_GRAPH_DP"); return !(e && e[0] == '0'); }();
@@ -1046,7 +1006,7 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   }
   m->global_step += 1;
   m->pack_valid = false;
-  return P3D_OK;
+  return mark_model_work(m, st);
 }
 
 // rows perm[start + i] (or start + i) of X / T -> the staging buffers; publishes the previous step's loss
@@ -1086,7 +1046,7 @@ int train_epoch(p3d_model* m, const float* X, const float* T, int64_t n, const l
     m->global_step += 1;
   }
   m->pack_valid = false;
-  return P3D_OK;
+  return mark_model_work(m, st);
 }
 
 }  // namespace train
@@ -1116,6 +1076,14 @@ int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t 
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   return train::train_epoch(m, X, T, n, reinterpret_cast<const long long*>(perm_or_null), batch_size, keep_prob, seed, losses,
                             lr_last_or_null, static_cast<cudaStream_t>(stream));
+}
+
+int p3d_debug_dp_part(p3d_model* m, int what, void* stream) {
+  P3D_REQUIRE(m && m->world > 1 && m->tw.stats, "debug_dp_part: needs an attached data-parallel model that has stepped once");
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (what == 0) return train::allreduce(m, m->grad, m->n_train, ncclFloat, st);          // the flat gradient exchange
+  return train::allreduce(m, m->tw.stats, 2ull * m->L, ncclDouble, st);                   // one SyncBN-sized exchange
 }
 
 int p3d_nccl_unique_id(uint8_t* id_host) {

@@ -50,7 +50,6 @@ PROTOTYPES = {
     "p3d_profile_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_int64)]),
     "p3d_host_alloc": (c_int, [C.POINTER(c_void_p), c_size_t]),
     "p3d_host_free": (c_int, [c_void_p]),
-    "p3d_host_pack_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
     "p3d_model_create": (c_int, [C.POINTER(Cfg), C.POINTER(c_void_p)]),
     "p3d_model_destroy": (None, [c_void_p]),
     "p3d_model_set_param_host": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
@@ -93,6 +92,8 @@ PROTOTYPES = {
     "p3d_realtime_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "p3d_model_p2p_handle": (c_int, [c_void_p, c_void_p]),
     "p3d_model_p2p_attach": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "p3d_model_p2p_detach": (c_int, [c_void_p]),
+    "p3d_debug_dp_part": (c_int, [c_void_p, c_int, c_void_p]),
     "p3d_model_train_epoch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, C.c_uint64,
                                       c_void_p, c_void_p, c_void_p]),
     "p3d_debug_tc_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,

@@ -164,6 +164,7 @@ class LinearModel(object):
         self._names = self._query_names()
         self._init_variables(np.random.RandomState(self._seed))
         self.saver = _Saver(self, max_to_keep=10)                     # linear_model.py:151
+        self.err_mm = np.float32(0.0)                                  # :133, the 'error_mm' placeholder
         # data parallel (one process per GPU, torch.distributed for the rendezvous only)
         self.rank, self.world = 0, 1
         if dist is not None:
@@ -235,9 +236,12 @@ class LinearModel(object):
 
     # tf.train.Saver stand-in (linear_model.py:151; predict_3dpose.py:158-186,328): one .npz keyed by TF names
     def save(self, path):
+        path = path if path.endswith(".npz") else path + ".npz"      # np.savez would append it silently
         np.savez(path, **{k.replace("/", "|"): v for k, v in self.get_variables(include_optimizer=True).items()})
+        return path
 
     def restore(self, path):
+        path = path if path.endswith(".npz") or os.path.exists(path) else path + ".npz"
         if not os.path.exists(path):
             raise ValueError("Asked to load checkpoint {0}, but it does not seem to exist".format(path))
         with np.load(path) as z:
@@ -266,6 +270,12 @@ class LinearModel(object):
         t = torch.from_numpy(ident).cuda(self.device) if dist.get_backend() == "nccl" else torch.from_numpy(ident)
         dist.broadcast(t, src=0)
         ident = t.cpu().numpy().copy()
+        # one dropout seed for the whole job: masks are keyed by (seed, step, layer, GLOBAL row, column), so with rank 0's
+        # seed a data-parallel step draws exactly the mask of the single-device step on the global batch
+        sd = torch.tensor([self._seed], dtype=torch.int64)
+        sd = sd.cuda(self.device) if dist.get_backend() == "nccl" else sd
+        dist.broadcast(sd, src=0)
+        self._seed = int(sd.item())
         # identical initial variables on every rank
         for name in self._names:
             if name == "global_step" or name.endswith("/gradient"):
@@ -289,9 +299,10 @@ class LinearModel(object):
             allh = np.ascontiguousarray(np.concatenate([h.cpu().numpy() for h in hs]))
             self.p2p = lib.p3d_model_p2p_attach(self._handle, _lib.np_ptr(allh), self.rank, self.world) == 0
             ok = torch.tensor([1 if self.p2p else 0], device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
-            if int(ok.item()) == 0 and self.p2p:
-                raise RuntimeError("peer-memory attach succeeded on some ranks only; set P3D_P2P=0")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none: every rank acts on the reduced flag
+            if int(ok.item()) == 0:
+                check(lib.p3d_model_p2p_detach(self._handle))   # closes what this rank had opened; the step keeps NCCL
+                self.p2p = False
 
     # ------------------------------------------------------------------ step
     def step(self, session, encoder_inputs, decoder_outputs, dropout_keep_prob, isTraining=True, *,
@@ -334,6 +345,7 @@ class LinearModel(object):
                     check(lib.p3d_model_forward(self._handle, x.data_ptr(), y.data_ptr(), B, st))
                     if B and not no_target:
                         check(lib.p3d_model_mse(self._handle, y.data_ptr(), t.data_ptr(), B, loss.data_ptr(), st))
+                self._last_outputs, self._last_loss = y, loss
                 return loss, Summary("loss/loss", loss), y
             if out is not None:
                 if out.shape != (B, self.output_size) or out.dtype != np.float32 or not out.flags.c_contiguous:
@@ -344,6 +356,7 @@ class LinearModel(object):
             loss = C.c_float(0.0)
             check(lib.p3d_model_step_eval_host(self._handle, _lib.np_ptr(x), None if no_target else _lib.np_ptr(t),
                                                _lib.np_ptr(y), C.byref(loss), B))
+            self._last_outputs, self._last_loss = y, np.float32(loss.value)
             return np.float32(loss.value), Summary("loss/loss", np.float32(loss.value)), y
 
         # ---- training
@@ -374,10 +387,13 @@ class LinearModel(object):
                 self._dist.all_gather(parts, y)
                 y = torch.cat(parts, 0)
             if is_torch:
+                self._last_outputs, self._last_loss = y, scal[0]
                 return scal[0], Summary("loss/loss", scal[0]), Summary("learning_rate/learning_rate", scal[1]), y
             s = scal.cpu().numpy()
+            yh = y.cpu().numpy()
+            self._last_outputs, self._last_loss = yh, np.float32(s[0])
             return (np.float32(s[0]), Summary("loss/loss", np.float32(s[0])),
-                    Summary("learning_rate/learning_rate", np.float32(s[1])), y.cpu().numpy())
+                    Summary("learning_rate/learning_rate", np.float32(s[1])), yh)
 
     def train_epoch(self, encoder_inputs, decoder_outputs, dropout_keep_prob, shuffle=True, perm=None):
         """The batch loop of the reference's train() (src/predict_3dpose.py:231-259) without the host in it:
@@ -438,10 +454,43 @@ class LinearModel(object):
         n_batches = n // self.batch_size
         return np.split(encoder_inputs, n_batches), np.split(decoder_outputs, n_batches)
 
-    def err_mm_summary(self, err_mm):
+    # ------------------------------------------------------------------ graph handles (linear_model.py:128-148)
+    # The reference's callers hold on to graph tensors of the model.  There is no graph here; the attributes exist and
+    # carry what a `session.run` on them would have returned for the LAST step:
+    #   model.outputs   (:128)      predictions of the last step() [B, out]
+    #   model.loss      (:129)      its loss
+    #   model.gradients (:143-144)  [[gradient, variable name], ...] of the last training step, in the order of the
+    #                               trainable variables (the reference stores [grad, var] pairs)
+    #   model.updates   (:145)      the train op: a callable that runs one training step, `model.updates(x, t, keep)`
+    #   model.err_mm    (:133)      the 'error_mm' placeholder: a settable slot; `model.err_mm_summary` (:134) is BOTH
+    #                               callable with a value (this repo's callers) and, called without one, the summary
+    #                               of whatever model.err_mm holds (what sess.run(model.err_mm_summary,
+    #                               {model.err_mm: e}) returns, predict_3dpose.py:295,322)
+    @property
+    def outputs(self):
+        return getattr(self, "_last_outputs", None)
+
+    @property
+    def loss(self):
+        return getattr(self, "_last_loss", None)
+
+    @property
+    def gradients(self):
+        g = self.get_gradients()
+        return [[g[n], n] for n in self.get_variable_names() if n in g]
+
+    @property
+    def updates(self):
+        return lambda encoder_inputs, decoder_outputs, dropout_keep_prob: self.step(
+            None, encoder_inputs, decoder_outputs, dropout_keep_prob, isTraining=True)
+
+    def err_mm_summary(self, err_mm=None):
         """The 'loss/error_mm' summary of linear_model.py:133-134.  The reference evaluates it with
         `sess.run(model.err_mm_summary, {model.err_mm: total_err})` (predict_3dpose.py:295,322); without a session
-        it is a call: `model.test_writer.add_summary(model.err_mm_summary(total_err), current_step)`."""
+        it is a call: `model.test_writer.add_summary(model.err_mm_summary(total_err), current_step)`, or
+        `model.err_mm = total_err; model.err_mm_summary()`."""
+        if err_mm is None:
+            err_mm = self.err_mm
         return Summary("loss/error_mm", np.float32(err_mm))
 
     def close(self):

@@ -2,12 +2,17 @@
 """bench.py - headline benchmark of the B200 hot path (BASELINE.json: "poses/sec (fused MLP inference,
 bf16) at 1/2/4/8 B200; batch-1 p50 latency").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mlp|preprocess|eval|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of LinearModel(1024, 2, residual, batch_norm, max_norm) inference over one
 batch of 2^20 synthetic poses per GPU (configs[1]).  N > 1 is launched by torch.distributed.run, one
 process per GPU; the pose batch is sharded by rows (weak scaling: 2^20 poses per GPU), there is no
 data-path collective, timing is CUDA events, max over ranks.  Rank 0 prints ONE JSON line.
+
+The same line carries `secondary`: at N = 1 the other BASELINE.json configs (batch sweep, training step, preprocessing,
+evaluation, realtime frame); at N > 1 `train_dp` - the data-parallel training step (configs[3]: global batch 64 / 4096 and
+4096 rows per GPU, SyncBN + gradient exchange, with the exchange split out) - and `stress_width4096` (configs[4]: 2^21
+poses per GPU, 8 x 2^21 = 16 M).
 
 --impl reference times the reference's own CPU implementation of the path.  TensorFlow is not
 installable here (no network), so this is the NumPy restatement of linear_model.py's graph
@@ -155,8 +160,9 @@ def run_reference(args):
         return 0
     threads = use_all_host_threads()
     rate0, _ = cpu_port_rate(16384, threads)
-    # size the per-step sample so that the whole run stays within ~2 minutes
-    budget = 120.0 / max(1, args.steps + args.warmup)
+    # size the per-step sample so that the whole run stays within ~4 minutes: at the ~170 K poses/s of a 16-core host
+    # that is the full 2^20-pose batch of our arm's config (same_config), fewer poses on a smaller host
+    budget = 240.0 / max(1, args.steps + args.warmup)
     sample = int(min(B_PER_GPU, max(4096, (rate0 * budget) // 4096 * 4096)))
     from oracle import mlp_ref as M
     from oracle import synth
@@ -175,7 +181,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "TensorFlow not installable (no network): NumPy restatement of the "
-                   "reference graph (oracle/mlp_ref.py) on the host cores; each step = a bounded sample"},
+                   "reference graph (oracle/mlp_ref.py) on the host cores; each step = a bounded sample",
+                   "sample_poses": sample, "full_batch": sample == B_PER_GPU},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} poses per step (of 2^20), fp32, NumPy restatement of the TF graph, row blocks of 2048 "
                                    f"poses over {threads} threads"},
@@ -186,6 +193,119 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads (and with them the pinned staging buffers it is about to allocate: first touch) to the
+    NUMA node its GPU hangs off.  With every rank on node 0 the host-buffer step of 8 ranks crosses the socket
+    interconnect for half of the GPUs (round 1: end-to-end efficiency 0.27 at N = 8).  Returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) <= 1:
+            return {"numa_nodes": len(nodes), "gpu_node": node, "bound": False}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_nodes": len(nodes), "gpu_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_nodes": len(nodes), "gpu_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:          # no NVML / sysfs: leave the affinity alone
+        return {"bound": False, "error": str(e)[:80]}
+
+
+def train_dp_measurements(torch, dist, lib, _lib, dev, local_rank, rank, world):
+    """BASELINE configs[3] under data parallelism (all ranks take part): LinearModel(1024, 2, residual, batch_norm,
+    max_norm) training step, dropout 0.5, Adam, SyncBN, rows of the global batch split over the ranks.  Per case:
+    the step (CUDA events, max over ranks), the same rows per GPU WITHOUT any exchange (a single-GPU model on the local
+    shard: what the GPU itself needs), the flat gradient all-reduce alone and one standalone SyncBN-sized peer-memory
+    exchange; `exchange_us_derived` = step - local step - gradient all-reduce = the SyncBN / loss exchanges as they sit
+    inside the step (in-kernel over NVLink peer memory when the tiles fit, waits for the slowest rank included)."""
+    from p3d import LinearModel
+
+    def timed(fn, iters, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / iters], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) * 1e3          # us
+
+    runs = []
+    g = torch.Generator(device=dev).manual_seed(11)
+    sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for label, Bg in (("global 64", 64), ("global 4096", 4096), ("4096 rows per GPU", 4096 * world)):
+        m = LinearModel(L, NL, True, True, True, Bg, 1e-3, mode="bf16", device=local_rank, seed=1, dist=dist)
+        x = torch.randn((Bg, IN), device=dev, generator=g); t = torch.randn((Bg, OUT), device=dev, generator=g)
+        dist.broadcast(x, 0); dist.broadcast(t, 0)
+        us = timed(lambda: m.step(None, x, t, 0.5, isTraining=True), 20)
+        ar = timed(lambda: _lib.check(lib.p3d_debug_dp_part(m._handle, 0, sptr)), 20)
+        ex = timed(lambda: _lib.check(lib.p3d_debug_dp_part(m._handle, 1, sptr)), 50)
+        peer = bool(getattr(m, "p2p", False))
+        m.close()
+        rows = Bg // world
+        ml = LinearModel(L, NL, True, True, True, rows, 1e-3, mode="bf16", device=local_rank, seed=1)
+        xl, tl = x[:rows].contiguous(), t[:rows].contiguous()
+        local = timed(lambda: ml.step(None, xl, tl, 0.5, isTraining=True), 20)
+        ml.close()
+        runs.append({"case": label, "global_batch": Bg, "rows_per_gpu": rows, "us_per_step": round(us, 1),
+                     "poses_per_s": round(Bg / (us * 1e-6)), "tflops": round(Bg * 25_591_808 / (us * 1e-6) / 1e12, 2),
+                     "local_step_us_no_exchange": round(local, 1), "grad_allreduce_us": round(ar, 1),
+                     "one_syncbn_exchange_us_standalone": round(ex, 1),
+                     "exchange_us_derived": round(us - local - ar, 1), "peer_memory_exchange": peer})
+    return {"config": "dropout keep 0.5, max_norm, Adam, SyncBN; bf16 tcgen05 GEMMs, fp32 master weights; 17.2 MB fp32 gradient",
+            "n_gpus": world, "runs": runs}
+
+
+def stress_measurement(torch, lib, _lib, peaks, dev, local_rank, world, dist):
+    """BASELINE configs[4]: linear_size=4096, num_layers=4 (269 MB of bf16 weights > L2), 2^21 poses per GPU (8 GPUs: 16 M
+    poses), rows sharded, no collective.  CUDA events, max over ranks."""
+    from p3d import LinearModel
+    ms_model = LinearModel(4096, 4, True, True, True, 64, 1e-3, seed=3, mode="bf16", device=local_rank)
+    Bs = 1 << 21
+    g = torch.Generator(device=dev).manual_seed(21)
+    xs = torch.randn((Bs, IN), device=dev, generator=g); ys = torch.empty((Bs, OUT), device=dev)
+    sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        _lib.check(lib.p3d_model_forward(ms_model._handle, xs.data_ptr(), ys.data_ptr(), Bs, sptr))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        _lib.check(lib.p3d_model_forward(ms_model._handle, xs.data_ptr(), ys.data_ptr(), Bs, sptr))
+    b.record(); torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / 3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    flop = 2 * (IN * 4096 + 2 * 4 * 4096 * 4096 + 4096 * OUT)
+    ms_model.close()
+    del xs, ys
+    return {"config": f"linear_size=4096, num_layers=4, residual, batch_norm, max_norm; 2^21 poses per GPU x {world} GPUs = {world << 21} poses",
+            "ms": round(ms, 3), "poses_per_s": round(world * Bs / (ms * 1e-3)),
+            "tflops_per_gpu": round(Bs * flop / (ms * 1e-3) / 1e12, 1),
+            "frac_of_bf16_peak": round(Bs * flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], 4)}
+
+
 def pinned_array(lib, shape, dtype=np.float32):
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     ptr = C.c_void_p()
@@ -227,22 +347,10 @@ def secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr):
                       "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 4)})
     out["inference_batch_sweep"] = sweep
 
-    # BASELINE configs[4]: width-scaled stress variant, linear_size=4096, num_layers=4 (269 MB of bf16 weights > L2);
-    # per-GPU share of the 8-GPU run = 2^21 poses, timed here on 2^18
-    ms_model = LinearModel(4096, 4, True, True, True, 64, 1e-3, seed=3, mode="bf16")
-    Bs = 1 << 18
-    xs = torch.randn((Bs, IN), device=dev, generator=g); ys = torch.empty((Bs, OUT), device=dev)
-    ms = timed(lambda: lib.p3d_model_forward(ms_model._handle, xs.data_ptr(), ys.data_ptr(), Bs, sptr), 3, warm=2)
-    flop = 2 * (IN * 4096 + 2 * 4 * 4096 * 4096 + 4096 * OUT)
-    out["stress_width4096"] = {"config": "linear_size=4096, num_layers=4, residual, batch_norm, max_norm; batch 2^18 on one GPU",
-                               "ms": round(ms, 3), "poses_per_s": round(Bs / (ms * 1e-3)),
-                               "tflops": round(Bs * flop / (ms * 1e-3) / 1e12, 1),
-                               "frac_of_bf16_peak": round(Bs * flop / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], 4)}
-    ms_model.close()
-    del xs, ys
+    out["stress_width4096"] = stress_measurement(torch, lib, _lib, peaks, dev, dev.index or 0, 1, None)
 
     train = []
-    for Bt, mode in ((64, "bf16"), (4096, "bf16"), (64, "fp32"), (4096, "fp32")):
+    for Bt, mode in ((64, "bf16"), (4096, "bf16"), (32768, "bf16"), (64, "fp32"), (4096, "fp32")):
         mt = LinearModel(L, NL, True, True, True, Bt, 1e-3, seed=1, mode=mode)
         xt = torch.randn((Bt, IN), device=dev, generator=g); tt = torch.randn((Bt, OUT), device=dev, generator=g)
         ms = timed(lambda: mt.step(None, xt, tt, 0.5, isTraining=True), 20 if mode == "bf16" else 5)
@@ -314,6 +422,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"bound": False, "note": "single rank: affinity left alone"}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -401,6 +510,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(e2.item())
+    mine = torch.tensor([B * (IN + OUT) * 4 * e2e_steps / e2e_s / 1e9, (B * OUT * 4) * e2e_steps / e2e_s / 1e9], device=dev, dtype=torch.float64)
+    per_rank = [torch.zeros(2, device=dev, dtype=torch.float64) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [{"rank": r, "h2d_gbs": round(float(v[0]), 2), "d2h_gbs": round(float(v[1]), 2)} for r, v in enumerate(per_rank)]
     ok = bool(np.isfinite(yh[:1024]).all()) and bool(np.allclose(yh[:4096], y[:4096].cpu().numpy(), atol=1e-5))
     # the same call without a target (decoder_outputs=None, an extension of the reference contract: its callers pass
     # zeros when they only want predictions): 128 B per pose up instead of 320
@@ -452,15 +568,27 @@ def run_ours(args):
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_measurements(torch, model, lib, _lib, peaks, dev, stream, sptr)
+    if world > 1 and not args.no_secondary:          # every rank takes part; rank 0 reports
+        secondary = {"train_dp": train_dp_measurements(torch, dist, lib, _lib, dev, local_rank, rank, world),
+                     "stress_width4096": stress_measurement(torch, lib, _lib, peaks, dev, local_rank, world, dist)}
 
     if rank == 0:
         k_ms = kms.value / max(1, kn.value)
         achieved = B * FLOP_PER_POSE / (k_ms * 1e-3) / 1e12
-        traffic = None
+        # dram__bytes of ONE launch of the timed kernel from an ncu capture (tools/capture_traffic.sh); the file names the
+        # source it was captured from - a capture of another version of the kernel is refused
+        traffic, traffic_note = None, "no capture"
         tpath = os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")
         if os.path.exists(tpath):
+            import hashlib
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            with open(os.path.join(ROOT, "3d-pose-baseline_b200", "csrc", "mlp_tc.cu"), "rb") as f:
+                sha = hashlib.sha256(f.read()).hexdigest()[:16]
+            if tj.get("kernel_src_sha16") == sha:
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu capture of {tj.get('when', '?')} ({tj.get('capture', '')})"
+            else:
+                traffic_note = f"stale capture refused (made from mlp_tc.cu {tj.get('kernel_src_sha16')}, built from {sha})"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -469,13 +597,15 @@ def run_ours(args):
                        "l2": "x (134 MB) + y (201 MB) per step exceed the 126 MB L2; no flush needed",
                        "weights": "random init (kaiming), BN statistics non-trivial and folded"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_note,
+                         "algorithmic_bytes_per_launch": B * (128 + 192),
                          "peak_source": peaks["source"] + " burst bf16 (MEASURED_PEAKS.json)",
                          "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                          "kernel": "mlp_forward_tc_kernel", "kernel_ms": k_ms, "kernel_launches": int(kn.value),
                          "flop_per_launch": B * FLOP_PER_POSE},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (IN + OUT) * 4,
                     "d2h_bytes_per_step": B * OUT * 4 + 4, "steps": e2e_steps, "outputs_match_device_path": ok,
+                    "per_rank": per_rank, "host_numa": numa,
                     "predictions_only": {"value": e2e_nt_value, "unit": UNIT, "h2d_bytes_per_step": B * IN * 4,
                                          "api": "LinearModel.step(None, x_pinned, None, 1.0, isTraining=False, out=y_pinned)"},
                     "api": "LinearModel.step(None, x_pinned, dec_out_pinned, 1.0, isTraining=False, out=y_pinned)"},

@@ -48,11 +48,6 @@ int p3d_profile_read(double* ms_total, int64_t* launches);
 /* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
 int p3d_host_alloc(void** out_host, size_t bytes);
 int p3d_host_free(void* host);
-/* fp32 -> bf16 on the HOST (round to nearest even, NaN -> 0x7FFF: bit-identical to the device's cvt.rn.bf16.f32), split
- * over `threads` host threads (<= 0: the library's default, at most 8).  What p3d_model_step_eval_host uses under
- * P3D_PIPE_XBF16=1 to send the network input - which the tensor-core forward rounds to bf16 anyway - across PCIe at
- * half the bytes.  No GPU needed. */
-int p3d_host_pack_bf16(const float* src_host, uint16_t* dst_host, int64_t n, int threads);
 
 /* ---------------------------------------------------------------- LinearModel -----------------
  * linear_model.LinearModel.__init__ (src/linear_model.py:34-151): same flags. */
@@ -121,12 +116,21 @@ int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t 
 int p3d_nccl_unique_id(uint8_t* id_host /*[128]*/);
 int p3d_model_attach_nccl(p3d_model* m, const uint8_t* id_host, int rank, int world);
 
-/* Optional, after attach_nccl, ranks of ONE node: the eleven latency-bound reductions of a data-parallel step (SyncBN
- * sums, loss) then run as single kernels over NVLink peer memory instead of NCCL calls.  Every rank exports the CUDA
- * IPC handle of its exchange buffer (64 bytes), the host layer all-gathers them, every rank attaches all `world`
- * handles (rank-major, 64 bytes each).  If a peer is not reachable attach fails and the step keeps using NCCL. */
+/* Optional, after attach_nccl, ranks of ONE node: the latency-bound reductions of a data-parallel step (SyncBN sums
+ * forward and backward, loss) then travel over NVLink peer memory instead of NCCL calls - inside the GEMM kernels that
+ * need them (fused training epilogues: batches whose tiles all fit the SMs) or as single kernels.  Every rank exports
+ * the CUDA IPC handle of its exchange buffer (64 bytes), the host layer all-gathers them, every rank attaches all
+ * `world` handles (rank-major, 64 bytes each).  If a peer is not reachable attach fails, closes what it had opened and
+ * the step keeps using NCCL; p3d_model_p2p_detach does the same on request (the host layer calls it on every rank when
+ * ANY rank failed to attach, so that all ranks take the same path).  The exchange waits for its peers like an NCCL
+ * collective (no timeout; P3D_SYNC_TIMEOUT_S=<s> makes a longer wait trap): ranks must step in lockstep. */
 int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle64_host);
 int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, int world);
+int p3d_model_p2p_detach(p3d_model* m);
+/* Measurement aid (bench.py `secondary.train_dp`): one exchange of a data-parallel step on its own, on `stream`.
+ * what = 0: the flat fp32 gradient all-reduce (NCCL); 1: one SyncBN-sized (2 x linear_size doubles) sum over peer memory
+ * (NCCL when no peer memory is attached).  The buffers hold whatever the last step left; they are summed in place. */
+int p3d_debug_dp_part(p3d_model* m, int what, void* stream);
 int64_t p3d_model_global_step(p3d_model* m);
 
 /* CRC-32C of a HOST buffer (host code, slice-by-8): the checksum TensorFlow's checkpoint format uses for table blocks

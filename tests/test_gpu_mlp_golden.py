@@ -1,0 +1,185 @@
+"""The CUDA LinearModel against tests/golden/mlp.npz - what the reference's own `src/linear_model.py` (unmodified,
+executed over the TensorFlow op stand-in of tests/tf_shim by oracle/make_golden_mlp.py) returned from
+`LinearModel.step` for the same variables, inputs and dropout stream.
+
+Tolerances (north_star): fp32 mode 1e-4, bf16 mode 1e-2 (row-wise relative L2 for outputs, relative for the loss);
+gradients in fp32 mode 2e-4 of each tensor's largest entry.  The dropout noise is NOT injected here: the model draws it
+itself (Philox4x32-10 keyed by seed / global row / column / layer / global step) and the fixture was generated with
+the same documented stream, so these tests also pin the generator."""
+import numpy as np
+import pytest
+
+from oracle import mlp_ref as M
+from test_oracle_mlp_golden import GOLD, KEEP, SEED, case_setup
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["s_res_bn_mn", "s_res_bn", "s_bn_mn_1", "s_res_3", "s_mn", "s_p14", "s_fresh", "h_1024_b64", "h_1024_b64_nomn",
+       "h_1024_b4096"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def model_for(cfg, p, B, lr0, mode):
+    from p3d import LinearModel
+    m = LinearModel(cfg.linear_size, cfg.num_layers, cfg.residual, cfg.batch_norm, cfg.max_norm, B, lr0,
+                    predict_14=(cfg.out_size == 42), mode=mode, seed=SEED)
+    m.set_variables({k: v.astype(np.float32) for k, v in p.items()})
+    return m
+
+
+def fetch(z, key, a):
+    """(what the fixture holds under key, the matching part of `a`) - whole tensor or its first rows."""
+    if key in z.files:
+        return z[key], np.asarray(a, np.float64)
+    head = z[key + "@head"]
+    return head, np.asarray(a, np.float64)[: head.shape[0]]
+
+
+def rowrel(a, ref):
+    return (np.linalg.norm(a - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-30)).max()
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("tag", ALL)
+def test_inference_matches_reference_graph(gold, tag, mode, tol):
+    z = gold
+    cfg, p, x, t, B, steps, big, lr0 = case_setup(z, tag)
+    m = model_for(cfg, p, B, lr0, mode)
+    loss, _, y = m.step(None, x, t, 1.0, isTraining=False)          # fp64 inputs, as the reference's callers pass them
+    m.close()
+    ref, got = fetch(z, tag + "/eval_y", y)
+    assert y.dtype == np.float32 and y.shape == (B, cfg.out_size)
+    assert rowrel(got, ref) <= tol, (tag, mode, rowrel(got, ref))
+    assert abs(float(loss) - float(z[tag + "/eval_loss"])) <= tol * float(z[tag + "/eval_loss"])
+
+
+@pytest.mark.parametrize("tag", ALL)
+def test_fp32_training_steps_match_reference_graph(gold, tag):
+    """LinearModel.step(isTraining=True) x steps: loss, outputs, decayed learning rate of every step; then the
+    variables, the BatchNorm moving statistics and an inference pass on them."""
+    z = gold
+    cfg, p, x, t, B, steps, big, lr0 = case_setup(z, tag)
+    m = model_for(cfg, p, B, lr0, "fp32")
+    for s in range(steps):
+        loss, _, lrs, y = m.step(None, x, t, KEEP, isTraining=True)
+        rl = float(z[tag + "/train_loss"][s])
+        assert abs(float(loss) - rl) <= 2e-4 * max(1.0, rl), (tag, s, float(loss), rl)
+        assert abs(float(lrs.value) - float(z[tag + "/train_lr"][s])) <= 1e-6 * lr0
+        ref, got = fetch(z, tag + "/train_y%d" % s, y)
+        assert np.abs(got - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1.0), (tag, s, np.abs(got - ref).max())
+        if s == 0:
+            grads = m.get_gradients()
+            for n in [str(v) for v in z[tag + "/grad_names"]]:
+                gref, g = fetch(z, tag + "/grad0/" + n, grads[n])
+                if (tag + "/grad0/" + n) in z.files and np.abs(gref).max() < 1e-13:
+                    assert np.abs(g).max() == 0.0, n           # bias in front of BatchNorm: exactly zero
+                    continue
+                if (tag + "/grad0/" + n + "@norm") in z.files:
+                    nrm = float(z[tag + "/grad0/" + n + "@norm"])
+                    assert abs(np.linalg.norm(grads[n].astype(np.float64)) - nrm) <= 2e-4 * nrm, n
+                    flat = grads[n].astype(np.float64).reshape(-1)
+                    smp, sref = flat[:: max(1, flat.size // 4093)][:4093], z[tag + "/grad0/" + n + "@sample"]
+                    assert np.abs(smp - sref).max() <= 2e-4 * max(np.abs(sref).max(), np.abs(gref).max()), n
+                assert np.abs(g - gref).max() <= 2e-4 * max(np.abs(gref).max(), 1e-12), (n, np.abs(g - gref).max(), np.abs(gref).max())
+    assert int(m.global_step) == steps
+    got = m.get_variables()
+    move = lr0 * steps
+    for n in p:
+        leaf = n.rsplit("/", 1)[-1]
+        if cfg.batch_norm and leaf[0] == "b" and leaf not in ("b4", "beta"):
+            assert np.array_equal(got[n], p[n].astype(np.float32)), n       # zero gradient: the CUDA path does not move it
+            continue
+        ref, g = fetch(z, tag + "/final/" + n, got[n])
+        if n.endswith(("moving_mean", "moving_variance")):
+            assert np.abs(g - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), n
+            continue
+        # Adam's m/(sqrt(v)+eps) turns fp32 rounding of near-zero gradients into O(lr) differences on a few elements
+        err = np.abs(g - ref)
+        assert np.quantile(err, 0.995) <= 0.02 * move + 1e-6 * np.abs(ref).max(), (n, np.quantile(err, 0.995))
+        assert err.max() <= 2.2 * move, (n, err.max())
+    loss2, _, y2 = m.step(None, x, t, 1.0, isTraining=False)
+    m.close()
+    assert abs(float(loss2) - float(z[tag + "/eval2_loss"])) <= 5e-3 * max(1.0, float(z[tag + "/eval2_loss"]))
+
+
+@pytest.mark.parametrize("tag", ["h_1024_b64", "h_1024_b64_nomn", "h_1024_b4096", "s_res_bn_mn"])
+def test_bf16_training_steps_match_reference_graph(gold, tag):
+    """The tensor-core training step against the same fixture at north_star's bf16 tolerance (1e-2)."""
+    z = gold
+    cfg, p, x, t, B, steps, big, lr0 = case_setup(z, tag)
+    m = model_for(cfg, p, B, lr0, "bf16")
+    for s in range(steps):
+        loss, _, lrs, y = m.step(None, x, t, KEEP, isTraining=True)
+        rl = float(z[tag + "/train_loss"][s])
+        assert abs(float(loss) - rl) <= 1e-2 * max(1.0, rl), (tag, s, float(loss), rl)
+        ref, got = fetch(z, tag + "/train_y%d" % s, y)
+        assert np.abs(got - ref).max() <= 1e-2 * max(np.abs(ref).max(), 1.0), (tag, s, np.abs(got - ref).max())
+    got = m.get_variables()
+    m.close()
+    for n in p:
+        if n.endswith(("moving_mean", "moving_variance")):
+            ref, g = fetch(z, tag + "/final/" + n, got[n])
+            assert np.abs(g - ref).max() <= 1e-2 * max(np.abs(ref).max(), 1e-3), n
+
+
+def exclude_ambiguous_units(p, x, cfg, masks, keep, quant, thr=2.0 ** -8):
+    """Zero, in the injected keep-masks, every hidden unit whose pre-ReLU value lies within thr*rms of zero in the
+    oracle (layer by layer, since a mask changes what the next layer sees).  Such a unit is dropped on both sides, so
+    whether its ReLU derivative is 0 or 1 - which operand rounding decides - no longer enters any gradient."""
+    names = M.layer_names(cfg.num_layers)
+    n_amb = 0
+    for li in range(len(names) - 1):
+        _, cache = M.forward(p, x, cfg, training=True, keep_prob=keep, masks=masks, want_cache=True, quant=quant)
+        c = cache[li]
+        if cfg.batch_norm:
+            bns = names[li][2]
+            a = c["xhat"] * p[bns + "/gamma"] + p[bns + "/beta"]
+        else:
+            # without BatchNorm the cache does not hold z; recompute it from the layer's operands
+            a = (c["h_in"] @ c["wc"]) * c["s"] + p[names[li][1]]
+        amb = np.abs(a) < thr * np.sqrt(np.mean(a * a))
+        n_amb += int((amb & (masks[li] > 0)).sum())
+        masks[li] = np.where(amb, 0, masks[li]).astype(np.uint8)
+    return masks, n_amb
+
+
+@pytest.mark.parametrize("B,fused", [(64, "1"), (1024, "1"), (4096, "1"), (4096, "0")],
+                         ids=["B64-one-tile", "B1024-grid-sync", "B4096-grid-sync", "B4096-unfused"])
+@pytest.mark.parametrize("max_norm", [True, False])
+def test_bf16_gradients_flip_excluded(B, fused, max_norm, monkeypatch):
+    """Gradients of the tensor-core step against the oracle restated with the same rounding points, with the units whose
+    ReLU derivative is decided by rounding taken out of the comparison (dropped through the injected mask on both
+    sides): every gradient tensor within 1e-3 relative L2 - a wrong split-K partial, a dropped d-gamma term or a
+    mis-scaled clip pull-back on any layer would be orders of magnitude above that.  Includes the BASELINE training
+    batch 4096."""
+    from helpers import bf16_round, make_model
+    from oracle import synth
+    monkeypatch.setenv("P3D_TRAIN_FUSED", fused)
+    cfg = M.Config(1024, 2, True, True, max_norm)
+    keep = 0.5
+    m, p = make_model(cfg, seed=31, bn="trained", mode="bf16", lr=1e-3)
+    x, t = synth.mlp_inputs(B, seed=77)
+    x64, t64 = x.astype(np.float64), t.astype(np.float64)
+    q = lambda a: bf16_round(a).astype(np.float64)  # noqa: E731
+    masks = [(np.random.RandomState(40 + li).uniform(size=(B, 1024)) < keep).astype(np.uint8) for li in range(5)]
+    masks, n_amb = exclude_ambiguous_units(p, x64, cfg, masks, keep, q)
+    assert 0 < n_amb < 0.02 * 5 * B * 1024
+    loss, _, _, yk = m.step(None, x, t, keep, isTraining=True, dropout_mask=np.stack(masks))
+    got = m.get_gradients()
+    m.close()
+    yq, cq = M.forward(p, x64, cfg, training=True, keep_prob=keep, masks=masks, want_cache=True, quant=q)
+    gq = M.backward(p, x64, t64, cfg, cq, yq, quant=q)
+    assert abs(float(loss) - M.loss_fn(yq, t64)) <= 1e-4 * max(1.0, M.loss_fn(yq, t64))
+    assert np.abs(yk - yq).max() <= 3e-3 * max(np.abs(yq).max(), 1.0)
+    worst = {}
+    for name, g in gq.items():
+        if np.abs(g).max() < 1e-12:
+            assert np.abs(got[name]).max() == 0.0, name
+            continue
+        worst[name] = np.linalg.norm(got[name].astype(np.float64) - g) / np.linalg.norm(g)
+    bad = {k: v for k, v in worst.items() if v > 1e-3}
+    assert not bad, bad

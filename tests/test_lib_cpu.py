@@ -95,54 +95,3 @@ def test_get_all_batches_contract():
     np.random.seed(0)
     perm = np.random.permutation(22)
     assert np.array_equal(np.vstack(ex2), np.vstack(list(dx.values()))[perm][:16])
-
-
-@pytest.mark.parametrize("threads", [1, 3, 0])
-def test_host_pack_bf16_is_the_device_rounding(threads):
-    """p3d_host_pack_bf16 (host threads, no GPU): bit-identical to round-to-nearest-even fp32 -> bf16 as torch / the
-    device's cvt.rn.bf16.f32 do it - ties, subnormals, overflow to inf, signed zeros; NaN becomes the canonical 0x7FFF."""
-    import ctypes as C
-
-    import torch
-    from p3d import _lib
-    rng = np.random.RandomState(3)
-    n = 1 << 18 if threads != 1 else 70001
-    x = rng.standard_normal(n).astype(np.float32) * np.float32(10.0) ** rng.randint(-30, 30, n).astype(np.float32)
-    special = np.array([0.0, -0.0, np.inf, -np.inf, 3.3895314e38, -3.4e38, 1e-40, -1e-45, 1.0, 1.00390625, 1.01171875,
-                        1.0078125, -1.00390625], dtype=np.float32)       # 1 + 2^-8, 1 + 3*2^-8: exact ties (even / odd neighbour)
-    bits = rng.randint(0, 1 << 32, 4096, dtype=np.uint64).astype(np.uint32)
-    x[:special.size] = special
-    x[special.size:special.size + bits.size] = bits.view(np.float32)       # arbitrary bit patterns, NaNs among them
-    out = np.empty(n, dtype=np.uint16)
-    _lib.check(_lib.lib.p3d_host_pack_bf16(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, threads))
-    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
-    nan = np.isnan(x)
-    assert np.array_equal(out[~nan], ref[~nan])
-    assert nan.any() and np.all(out[nan] == 0x7FFF)
-    _lib.check(_lib.lib.p3d_host_pack_bf16(None, None, 0, threads))         # empty input
-
-
-def test_host_pack_bf16_from_concurrent_callers():
-    """The library's host thread pool runs one job at a time; callers from several threads queue up behind each other
-    (distinct model handles may be driven from distinct threads, include/p3d.h) - no deadlock, no torn output."""
-    import ctypes as C
-    import threading
-
-    import torch
-    from p3d import _lib
-    rng = np.random.RandomState(5)
-    xs = [rng.standard_normal(300000 + 1000 * i).astype(np.float32) for i in range(4)]
-    outs = [np.zeros(x.size, dtype=np.uint16) for x in xs]
-
-    def work(i):
-        for _ in range(10):
-            _lib.check(_lib.lib.p3d_host_pack_bf16(xs[i].ctypes.data_as(C.c_void_p), outs[i].ctypes.data_as(C.c_void_p), xs[i].size, 0))
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join(timeout=120)
-    assert not any(t.is_alive() for t in th)
-    for x, o in zip(xs, outs):
-        assert np.array_equal(o, torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))

@@ -1,6 +1,8 @@
-"""Multi-GPU check (launch with torchrun, one process per GPU): data-parallel training steps with SyncBN +
-NCCL gradient all-reduce must reproduce the single-device oracle on the GLOBAL batch, and sharded MPJPE
-with the 18-double all-reduce must equal the full-set result.  Prints 'DP CHECK OK' on rank 0."""
+"""Multi-GPU check (launch with torchrun, one process per GPU; tests/test_gpu_dp.py does that with 2 ranks): data-parallel
+training steps with SyncBN + gradient all-reduce must reproduce the single-device oracle on the GLOBAL batch; the fused
+tensor-core step with the SyncBN exchange inside its GEMMs must equal the same step on one GPU (BASELINE batch 4096
+included), on the fused and on the unfused path; sharded MPJPE with the 18-double all-reduce must equal the full-set
+result.  Prints 'DP CHECK OK' on rank 0."""
 import os
 import sys
 
@@ -83,6 +85,41 @@ if why:
     print("bf16 data-parallel step FAILED on rank %d: %s" % (rank, "; ".join(why)), flush=True)
 ok &= bool(ok_b)
 mb.close()
+
+# The headline model, tensor-core path, generated dropout (Philox on GLOBAL rows): a data-parallel step == the same step
+# on ONE GPU over the global batch, up to the order of the fp32 / fp64 sums.  Global batches 512 and 4096 (BASELINE
+# configs[3]), on the fused path (SyncBN exchange inside the GEMM epilogues, loss on the first backward exchange) and
+# with P3D_TRAIN_FUSED=0 (separate reduction kernels).
+for fused_env, Bq in (("1", 512), ("1", 4096), ("0", 4096), ("1", 65)):
+    os.environ["P3D_TRAIN_FUSED"] = fused_env
+    md = LinearModel(1024, 2, True, True, True, Bq, 1e-3, mode="bf16", device=local, seed=11, dist=dist)
+    ms = LinearModel(1024, 2, True, True, True, Bq, 1e-3, mode="bf16", device=local, seed=11)
+    ms._seed = md._seed
+    ms.set_variables(md.get_variables())
+    xq, tq = synth.mlp_inputs(Bq, seed=40)
+    whyq = []
+    for s_ in range(2):
+        ld, _, _, yd = md.step(None, xq, tq, keep, isTraining=True)
+        ls, _, _, ys = ms.step(None, xq, tq, keep, isTraining=True)
+        if not abs(float(ld) - float(ls)) <= 2e-5 * max(1.0, float(ls)):
+            whyq.append("step %d loss %r vs %r" % (s_, float(ld), float(ls)))
+        if not np.abs(yd - ys).max() <= 2e-3 * max(np.abs(ys).max(), 1.0):
+            whyq.append("step %d outputs differ by %.3e" % (s_, np.abs(yd - ys).max()))
+    vd, vs_ = md.get_variables(), ms.get_variables()
+    for name in ("linear_model/w1", "linear_model/two_linear_0/w3_0", "linear_model/w4", "linear_model/batch_normalization/gamma",
+                 "linear_model/two_linear_1/batch_normalization21/beta", "linear_model/batch_normalization/moving_variance"):
+        err = np.abs(vd[name].astype(np.float64) - vs_[name])
+        if not np.quantile(err, 0.99) <= 0.05 * 2e-3 + 1e-5 * np.abs(vs_[name]).max():
+            whyq.append("%s: 99%% quantile of |dp - single| = %.3e" % (name, np.quantile(err, 0.99)))
+    wq = torch.from_numpy(vd["linear_model/two_linear_1/w2_1"]).cuda()
+    wq0 = wq.clone(); dist.broadcast(wq0, 0)
+    if not bool(torch.equal(wq, wq0)):
+        whyq.append("w2_1 differs between ranks after the update")
+    if whyq:
+        print("dp == single-GPU check FAILED on rank %d (fused=%s, B=%d, peer memory %s): %s" % (rank, fused_env, Bq, getattr(md, "p2p", None), "; ".join(whyq)), flush=True)
+    ok &= not whyq
+    md.close(); ms.close()
+os.environ.pop("P3D_TRAIN_FUSED", None)
 
 # sharded evaluation
 N = 10007
