@@ -260,7 +260,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     mbar_init(accf, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
+  constexpr uint32_t TMEM_MULT = (OUT == 4) ? 2u : 1u;      // the fused backward epilogue keeps xhat in a second half
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_MULT * static_cast<uint32_t>(p.bn)); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -350,8 +351,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
     if constexpr (OUT == 3 || OUT == 4) {
       // ------------------------------------------------------------ fused training epilogues
-      // Two passes over the TMEM accumulator with the column statistics of the (global) batch in between
-      // (column_totals): GEMM + statistics + finalize + activation kernels -> 1 launch, both directions.
+      // Two passes over the tile with the column statistics of the (global) batch in between (column_totals): GEMM +
+      // statistics + finalize + activation kernels -> 1 launch, both directions.  Eight warps cannot hide the latency
+      // of an elementwise pass the way a standalone kernel with 64 warps per SM does (first version: 27 of the 34 us
+      // of a 4096-pose forward layer were epilogue), so the work is arranged around what they CAN overlap:
+      //   phase 0, under the mainloop (these warps would only wait for the accumulator): everything that does not need
+      //            it.  Forward: the dropout keep-bits (Philox or the injected mask) - kept as one bit per element in
+      //            registers, the mask bytes stored for the backward pass.  Backward: z and the keep-mask are read,
+      //            xhat = (z - mean) rstd goes into the spare half of the TMEM allocation, relu' * keep into bits.
+      //   pass 1:  accumulator -> (alpha, bias, residual) -> column partial sums; the values every lane has produced are
+      //            written back over the accumulator chunk they came from with tcgen05.st - lane l's 32 registers go to
+      //            TMEM lane l, so TMEM serves as 128 bytes per lane and chunk of private scratch, already in the
+      //            4-columns-x-8-rows arrangement the global accesses want (no second trip through shared memory).
+      //   pass 2:  reads that scratch; no global loads besides the residual operand.
       const int ew = warp & 3, half = (warp - 2) >> 2;
       const int hw = p.bn >= 64 ? p.bn / 2 : 32;
       const int cbeg = half * hw, cend = (cbeg + hw < p.bn) ? cbeg + hw : p.bn;
@@ -363,7 +375,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       grid_dependency_wait();
       const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
       for (int j = et; j < p.bn; j += EPI_THREADS) sbias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-      named_bar_sync(1, EPI_THREADS);
       constexpr int TP = 36;
       const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
       const uint32_t sbias_s = smem_u32(sbias);
@@ -371,9 +382,81 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int mrow0 = m0 + ew * 32 + rg;
       const float keep = sc->keep, inv_keep = sc->inv_keep;
       const bool writer = (blockIdx.y == 0);                   // of the CTAs that share a column: the one that stores per-column results
+      const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
+      const double invB = static_cast<double>(p.ft.invB);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      // chunk k of this warp: bit (4 i + j) = row mrow0 + 4 i, column cq + j.  Four scalars picked by selects: an array
+      // indexed by the chunk counter would live in local memory.
+      uint32_t g0 = 0xffffffffu, g1 = 0xffffffffu, g2 = 0xffffffffu, g3 = 0xffffffffu;
+      auto set_gate = [&](int k, uint32_t b) { if (k == 0) g0 = b; else if (k == 1) g1 = b; else if (k == 2) g2 = b; else g3 = b; };
+      auto get_gate = [&](int k) { return k == 0 ? g0 : (k == 1 ? g1 : (k == 2 ? g2 : g3)); };
+
+      // ---------------------------------------------------------------- phase 0 (under the mainloop)
+      if constexpr (OUT == 3) {
+        if (dropout) {
+          for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
+            const int n = n0 + c0 + cq;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + 4 * i;
+              if (m >= p.M) continue;
+              const size_t off = static_cast<size_t>(m) * p.N + n;
+              uchar4 kb;
+              if (p.ft.mask_in) {
+                kb = *reinterpret_cast<const uchar4*>(p.ft.mask_in + off);
+              } else {
+                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer),
+                                                      static_cast<uint32_t>(p.ft.row0 + m), static_cast<uint32_t>(n >> 2));
+                kb = make_uchar4(train::keep_bit(w4.x, keep), train::keep_bit(w4.y, keep), train::keep_bit(w4.z, keep), train::keep_bit(w4.w, keep));
+              }
+              *reinterpret_cast<uchar4*>(p.ft.mask + off) = kb;
+              bits |= ((kb.x ? 1u : 0u) | (kb.y ? 2u : 0u) | (kb.z ? 4u : 0u) | (kb.w ? 8u : 0u)) << (4 * i);
+            }
+            set_gate(k, bits);
+          }
+        }
+      } else {
+        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
+          const int n = n0 + c0 + cq;
+          float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+          if (has_bn) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
+            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+          }
+          float4 z4[8];
+          uchar4 mk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const size_t off = static_cast<size_t>(m < p.M ? m : 0) * p.N + n;
+            z4[i] = __ldg(reinterpret_cast<const float4*>(p.ft.z + off));
+            mk[i] = dropout ? *reinterpret_cast<const uchar4*>(p.ft.mask + off) : make_uchar4(1, 1, 1, 1);
+          }
+          uint32_t xh[32], bits = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool live = mrow0 + 4 * i < p.M;
+            const float zz[4] = {z4[i].x, z4[i].y, z4[i].z, z4[i].w};
+            const unsigned char kk[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x = has_bn ? (zz[j] - mu[j]) * rs[j] : 0.f;
+              const float act = has_bn ? ga[j] * x + be[j] : zz[j];
+              xh[4 * i + j] = __float_as_uint(x);
+              if (live && act > 0.f && kk[j]) bits |= 1u << (4 * i + j);
+            }
+          }
+          set_gate(k, bits);
+          tmem_st_32x32b_x32(taddr + p.bn + c0, xh);          // the spare half of the allocation: columns bn .. 2 bn
+        }
+        tmem_st_wait();
+      }
+      named_bar_sync(1, EPI_THREADS);                          // sbias staged
       mbar_wait(accf, 0, 3);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
       // accumulator chunk -> this lane's 4 columns x 8 rows (rows mrow0 + 4 i), as alpha * acc + bias
       auto chunk = [&](int c0, float (&o)[8][4]) {
         uint32_t v[32];
@@ -390,6 +473,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           o[i][0] = alpha * t.x + b4.x; o[i][1] = alpha * t.y + b4.y; o[i][2] = alpha * t.z + b4.z; o[i][3] = alpha * t.w + b4.w;
         }
       };
+      auto stash = [&](uint32_t col, const float (&o)[8][4]) {          // this lane's 32 values -> its private TMEM scratch
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[4 * i + j] = __float_as_uint(o[i][j]);
+        tmem_st_32x32b_x32(taddr + col, v);
+      };
+      auto unstash = [&](uint32_t col, float (&o)[8][4]) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + col, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[i][j] = __uint_as_float(v[4 * i + j]);
+      };
       auto publish = [&](int c0, float (&s1)[4], float (&s2)[4]) {     // fold the 4 row groups, quadrant partial -> smem
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -402,22 +502,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           *reinterpret_cast<float4*>(q1 + 256) = make_float4(s2[0], s2[1], s2[2], s2[3]);
         }
       };
-      const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
-      const double invB = static_cast<double>(p.ft.invB);
       if constexpr (OUT == 3) {
-        // ---- forward: z = alpha acc + bias; batch statistics; BN, ReLU, dropout, residual
-        if (has_bn) {
-          for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-            float o[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-            chunk(c0, o);
+        // ---- forward pass 1: z = alpha acc + bias -> global (the backward pass needs it), column sums, z -> scratch
+        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+          float o[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          chunk(c0, o);
+          const int n = n0 + c0 + cq;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool live = mrow0 + 4 * i < p.M;
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            const bool live = m < p.M;
+            if (live) *reinterpret_cast<float4*>(p.C + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float q = live ? o[i][j] : 0.f; s1[j] += q; s2[j] += q * q; }
-            }
-            publish(c0, s1, s2);
+            for (int j = 0; j < 4; ++j) { const float q = live ? o[i][j] : 0.f; s1[j] += q; s2[j] += q * q; }
           }
+          if (has_bn) publish(c0, s1, s2);
+          stash(c0, o);
+        }
+        tmem_st_wait();
+        if (has_bn) {
           named_bar_sync(1, EPI_THREADS);
           column_totals(p, n0, et, scol, stot, sflag, seq);
           // mean / biased variance over the global batch in double, as train.cu's bn_finalize_kernel does it;
@@ -437,48 +540,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
           named_bar_sync(1, EPI_THREADS);
         }
-        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-          float o[8][4];
-          chunk(c0, o);
+        // ---- forward pass 2: BN, ReLU, dropout, + residual -> h (fp32, where a later layer adds it), hb (bf16 operand)
+        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
           const int n = n0 + c0 + cq;
-          float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
-          if (has_bn) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
-            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
-            const float4 m4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), r4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
-            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
-          }
           float4 hr[8];
-          uchar4 mi[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
-            const size_t off = static_cast<size_t>(m < p.M ? m : 0) * p.N + n;
-            hr[i] = p.ft.hres ? __ldg(reinterpret_cast<const float4*>(p.ft.hres + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mi[i] = (dropout && p.ft.mask_in) ? *reinterpret_cast<const uchar4*>(p.ft.mask_in + off) : make_uchar4(1, 1, 1, 1);
+            hr[i] = p.ft.hres ? __ldg(reinterpret_cast<const float4*>(p.ft.hres + static_cast<size_t>(m < p.M ? m : 0) * p.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float o[8][4];
+          unstash(c0, o);
+          float sc_[4] = {1.f, 1.f, 1.f, 1.f}, sh_[4] = {0.f, 0.f, 0.f, 0.f};      // BN as one multiply-add: a = z * sc + sh
+          if (has_bn) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+            const float4 m4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), r4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
+            const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sc_[j] = rs[j]; sh_[j] = mu[j]; (void)ga; (void)be; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[i][j] = ga[j] * ((o[i][j] - sh_[j]) * sc_[j]) + be[j];      // same operation order as the unfused kernels
+          }
+          const uint32_t bits = get_gate(k);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
             if (m >= p.M) continue;
             const size_t off = static_cast<size_t>(m) * p.N + n;
-            *reinterpret_cast<float4*>(p.C + off) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);      // z, for the backward pass
             float r[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a = has_bn ? ga[j] * ((o[i][j] - mu[j]) * rs[j]) + be[j] : o[i][j];
-              r[j] = fmaxf(a, 0.f);
-            }
-            if (dropout) {
-              uint8_t kb[4] = {mi[i].x, mi[i].y, mi[i].z, mi[i].w};
-              if (!p.ft.mask_in) {
-                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer),
-                                                      static_cast<uint32_t>(p.ft.row0 + m), static_cast<uint32_t>(n >> 2));
-                kb[0] = train::keep_bit(w4.x, keep); kb[1] = train::keep_bit(w4.y, keep); kb[2] = train::keep_bit(w4.z, keep); kb[3] = train::keep_bit(w4.w, keep);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) r[j] = kb[j] ? r[j] * inv_keep : 0.f;
-              *reinterpret_cast<uchar4*>(p.ft.mask + off) = make_uchar4(kb[0], kb[1], kb[2], kb[3]);
+              r[j] = fmaxf(o[i][j], 0.f);
+              if (dropout) r[j] = ((bits >> (4 * i + j)) & 1u) ? r[j] * inv_keep : 0.f;
             }
             r[0] += hr[i].x; r[1] += hr[i].y; r[2] += hr[i].z; r[3] += hr[i].w;
             if (p.ft.h) *reinterpret_cast<float4*>(p.ft.h + off) = make_float4(r[0], r[1], r[2], r[3]);
@@ -488,62 +584,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       } else {
-        // ---- backward: dh = alpha acc (+ res); da = dh * dropout * relu'(act); BN backward with the global column sums
-        auto da_of = [&](int c0, float (&o)[8][4], float (&xh)[8][4], const float (&mu)[4], const float (&rs)[4], const float (&ga)[4],
-                         const float (&be)[4], bool store_dh) {
+        // ---- backward pass 1: dh = alpha acc (+ res) (-> dh_out); da = dh * keep/relu' gate; column sums of da, da * xhat
+        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
           const int n = n0 + c0 + cq;
-          // all global operands of the 8 rows first (independent loads in flight), then the arithmetic
-          float4 z4[8], r4[8];
-          uchar4 mk[8];
+          float4 r4[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
-            const size_t off = static_cast<size_t>(m < p.M ? m : 0) * p.N + n;
-            z4[i] = __ldg(reinterpret_cast<const float4*>(p.ft.z + off));
-            mk[i] = dropout ? *reinterpret_cast<const uchar4*>(p.ft.mask + off) : make_uchar4(1, 1, 1, 1);
-            r4[i] = p.res ? __ldg(reinterpret_cast<const float4*>(p.res + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r4[i] = p.res ? __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(m < p.M ? m : 0) * p.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float o[8][4], xh[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          chunk(c0, o);
+          unstash(p.bn + c0, xh);
+          const uint32_t bits = get_gate(k);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
-            const bool live = m < p.M;
             o[i][0] += r4[i].x; o[i][1] += r4[i].y; o[i][2] += r4[i].z; o[i][3] += r4[i].w;
-            if (store_dh && p.ft.dh_out && live)
+            if (p.ft.dh_out && m < p.M)
               *reinterpret_cast<float4*>(p.ft.dh_out + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-            const float zz[4] = {z4[i].x, z4[i].y, z4[i].z, z4[i].w};
-            const unsigned char kk[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              xh[i][j] = has_bn ? (zz[j] - mu[j]) * rs[j] : 0.f;
-              const float act = has_bn ? ga[j] * xh[i][j] + be[j] : zz[j];
               float gr = o[i][j];
-              if (dropout) gr = kk[j] ? gr * inv_keep : 0.f;
-              o[i][j] = (live && act > 0.f) ? gr : 0.f;            // da
+              if (dropout) gr *= inv_keep;
+              const float da = ((bits >> (4 * i + j)) & 1u) ? gr : 0.f;
+              o[i][j] = da;
+              s1[j] += da; s2[j] += da * xh[i][j];
             }
           }
-        };
-        auto bn_consts = [&](int c0, float (&mu)[4], float (&rs)[4], float (&ga)[4], float (&be)[4]) {
-          const int n = n0 + c0 + cq;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { mu[j] = 0.f; rs[j] = 1.f; ga[j] = 1.f; be[j] = 0.f; }
-          if (has_bn) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
-            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
-            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
-          }
-        };
-        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-          chunk(c0, o);
-          bn_consts(c0, mu, rs, ga, be);
-          da_of(c0, o, xh, mu, rs, ga, be, true);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s1[j] += o[i][j]; s2[j] += o[i][j] * xh[i][j]; }
           publish(c0, s1, s2);
+          stash(c0, o);
         }
+        tmem_st_wait();
         named_bar_sync(1, EPI_THREADS);
         column_totals(p, n0, et, scol, stot, sflag, seq);
         // sum da (= dbeta, or the bias gradient) and sum da * xhat (= dgamma) over the global batch; every rank holds
@@ -558,22 +630,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
         named_bar_sync(1, EPI_THREADS);
+        // ---- backward pass 2: dz = gamma rstd (da - mean(da) - xhat mean(da xhat)) -> bf16 operand of the next GEMMs
         const float invBf = p.ft.invB;
         for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-          float o[8][4], xh[8][4], mu[4], rs[4], ga[4], be[4];
-          chunk(c0, o);
-          bn_consts(c0, mu, rs, ga, be);
-          da_of(c0, o, xh, mu, rs, ga, be, false);
-          const float4 P4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), Q4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
-          const float P[4] = {P4.x, P4.y, P4.z, P4.w}, Q[4] = {Q4.x, Q4.y, Q4.z, Q4.w};
           const int n = n0 + c0 + cq;
+          float o[8][4], xh[8][4];
+          unstash(c0, o);
+          float gr[4] = {1.f, 1.f, 1.f, 1.f}, P[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
+          if (has_bn) {
+            unstash(p.bn + c0, xh);
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
+            const float4 P4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), Q4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
+            gr[0] = g4.x * r4.x; gr[1] = g4.y * r4.y; gr[2] = g4.z * r4.z; gr[3] = g4.w * r4.w;
+            P[0] = P4.x * invBf; P[1] = P4.y * invBf; P[2] = P4.z * invBf; P[3] = P4.w * invBf;
+            Q[0] = Q4.x * invBf; Q[1] = Q4.y * invBf; Q[2] = Q4.z * invBf; Q[3] = Q4.w * invBf;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = mrow0 + 4 * i;
             if (m >= p.M) continue;
             float d[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = has_bn ? ga[j] * rs[j] * (o[i][j] - P[j] * invBf - xh[i][j] * (Q[j] * invBf)) : o[i][j];
+            for (int j = 0; j < 4; ++j) d[j] = has_bn ? gr[j] * (o[i][j] - P[j] - xh[i][j] * Q[j]) : o[i][j];
             __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
             uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.ft.dzb) + static_cast<size_t>(m) * p.N + n) = pk;
@@ -736,7 +814,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 0) P3D_STAMP(7);
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, static_cast<uint32_t>(p.bn)); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_MULT * static_cast<uint32_t>(p.bn)); }
 }
 
 // ----------------------------------------------------------------------------- MMA issue-rate probe

@@ -48,6 +48,29 @@ def test_world_camera_roundtrip_golden(geo):
         np.testing.assert_allclose(c2w, P, atol=1e-8)
 
 
+def test_dictionary_drivers_batch_sequences_per_subject(geo):
+    """project_to_cameras / transform_world_to_camera send all sequences of a subject to the device in one buffer and
+    run each camera once: keys, shapes and values must equal the per-sequence, per-camera calls of the reference loop
+    (data_utils.py:243-255, 349-362) - ragged sequence lengths, two subjects with different cameras."""
+    from p3d import cameras, data_utils
+    cams = cams_of(geo)
+    rcams = {(s, ci + 1): cams[(ci + s) % 4] + (f"c{s}{ci}",) for s in (1, 5) for ci in range(4)}
+    w = geo["world"]
+    poses = {(1, "Walking", "Walking 1.h5"): w[:7].copy(), (1, "Eating", "Eating.h5"): w[7:20].copy(),
+             (5, "Sitting", "Sitting 2.h5"): w[20:21].copy()}
+    t2d = data_utils.project_to_cameras(poses, rcams, ncams=4)
+    t3d = data_utils.transform_world_to_camera(poses, rcams, ncams=4)
+    assert len(t2d) == 12 and len(t3d) == 12
+    for (subj, a, seq), arr in poses.items():
+        for ci in range(4):
+            R, T, f, c, k, p_, name = rcams[(subj, ci + 1)]
+            key = (subj, a, seq[:-3] + "." + name + ".h5")
+            ref2 = cameras.project_point_radial(arr.reshape(-1, 3), R, T, f, c, k, p_)[0].reshape(-1, 64)
+            ref3 = cameras.world_to_camera_frame(arr.reshape(-1, 3), R, T).reshape(-1, 96)
+            assert t2d[key].shape == ref2.shape and t3d[key].shape == ref3.shape
+            assert np.array_equal(t2d[key], ref2) and np.array_equal(t3d[key], ref3)
+
+
 def test_dictionary_pipeline_golden(geo):
     """train()'s preprocessing calls (predict_3dpose.py:197-207) through the mirrored data_utils API."""
     from p3d import data_utils
