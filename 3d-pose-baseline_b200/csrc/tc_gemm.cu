@@ -42,10 +42,20 @@ constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int BOX_BYTES = 64 * BK * 2;      // one [64 rows x 64 cols] bf16 box = 8 KB
 constexpr int NTHREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int EPI_THREADS = 256;
+// Epilogue warps of the fused training kernels (a multiple of 4: warps per TMEM lane quadrant).  Measured on B200 at 4096
+// poses: 12 warps (448 threads, 128 registers, small spills) 408.5 us per step against 408.4 us with 8 - the fused
+// epilogues are bound by their instruction COUNT (~67 K warp instructions per 128 x 256 tile, half of them Philox), not
+// by the number of warps that share it.
+#ifndef P3D_FUSED_EPI_WARPS
+#define P3D_FUSED_EPI_WARPS 8
+#endif
+constexpr int FUSED_EPI_THREADS = 32 * P3D_FUSED_EPI_WARPS;
+constexpr int FUSED_NTHREADS = 64 + FUSED_EPI_THREADS;
 constexpr int RING_BYTES = 4 * (A_BYTES + 256 * BK * 2);   // 192 KB: 4 stages at BN=256, 6 at 128, 8 at 64
 constexpr int BAR_BYTES = 512;               // full[16] | empty[16] | accf | tmem slot | grid-sync scratch
 // align slack | operand ring | barriers | bias[256] | column sums [4 quadrants][2][256] | per-column finals [2][256] f32 | totals [2][256] f64
-constexpr int TAIL_BYTES = 1024 + 8192 + 2048 + 4096;
+// | per-column constants of the fused epilogues [4][256] f32 (gamma, beta, mean, rstd)
+constexpr int TAIL_BYTES = 1024 + 8192 + 2048 + 4096 + 4096;
 constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + TAIL_BYTES;
 // the narrower the tile, the deeper the ring: small problems are latency bound on the L2 -> SM round trip
 
@@ -68,12 +78,12 @@ struct Params {
   int stages;               // ring depth: what fits into 192 KB at this tile size, 16 at most
   int a_bytes;              // bytes of A actually fetched per stage (K-major A of a short problem: only round_up(M, 8) rows)
   int b_independent;        // B does not depend on preceding kernels of the stream (weights): prefetch it before the PDL wait
-  unsigned long long* dbg;  // optional [ctas][16] globaltimer stamps (diagnostics)
+  unsigned long long* dbg;  // optional [ctas][32] globaltimer stamps (diagnostics)
   FusedTrain ft;            // OUT = 3 / 4 only
   long long wait_limit_ns;  // > 0: a wait for peers / the grid longer than this traps (diagnostics; 0 = wait like NCCL does)
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = gtime(); } while (0)
+#define P3D_STAMP(i) do { if (p.dbg && lane == 0) p.dbg[(static_cast<size_t>(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -126,12 +136,13 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
   return v;
 }
 
-// Column sums of the whole (global) batch for the columns n0 .. n0 + bn of this CTA, called by the 256 epilogue threads
+// Column sums of the whole (global) batch for the columns n0 .. n0 + bn of this CTA (totals_arrive + totals_wait: whatever
+// does not need the sums runs between the two, in the shadow of the barrier), called by the 256 epilogue threads
 // after pass 1 has left this CTA's per-quadrant partial sums in scol ([4][2][256] floats).  Result: tot[j], tot[256 + j]
 // (doubles, shared memory) for column n0 + j.
 //   one M tile, one GPU : the four quadrant partials are the batch.
 //   otherwise           : partials -> gsum (fp64 atomics) -> arrival counter; the CTA that arrives last owns the complete
-//                         sums of this GPU.  One GPU: it raises the completion flag the others spin on.  Data parallel: it
+//                         sums of this GPU.  One GPU: everybody spins on the counter reaching the grid size.  Data parallel: it
 //                         stores the vector into slot [seq % NSLOTS][rank] of EVERY rank's exchange buffer (16-byte NVLink
 //                         stores), then one thread per peer raises that peer's flag with st.release.sys (cumulative: the
 //                         block barrier before it orders the whole CTA's stores); all CTAs of all ranks spin on their own
@@ -139,7 +150,8 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
 //                         bit-identical sums.  Slot reuse is safe with >= 2 slots: nobody can be more than one exchange
 //                         ahead of the slowest rank (it needs that rank's flag).  No timeout by default: like an NCCL
 //                         collective this waits for its peers (Params::wait_limit_ns is the diagnostics switch).
-__device__ __forceinline__ void column_totals(const Params& p, int n0, int et, const float* scol, double* tot, uint32_t* sflag,
+template <int EPI_THREADS>
+__device__ __forceinline__ void totals_arrive(const Params& p, int n0, int et, const float* scol, double* tot, uint32_t* sflag,
                                               unsigned long long seq) {
   const FusedTrain& ft = p.ft;
   const int N = p.N;
@@ -148,7 +160,6 @@ __device__ __forceinline__ void column_totals(const Params& p, int n0, int et, c
       tot[j] = static_cast<double>((scol[j] + scol[512 + j]) + (scol[1024 + j] + scol[1536 + j]));
       tot[256 + j] = static_cast<double>((scol[256 + j] + scol[768 + j]) + (scol[1280 + j] + scol[1792 + j]));
     }
-    named_bar_sync(1, EPI_THREADS);
     return;
   }
   for (int j = et; j < p.bn; j += EPI_THREADS) {
@@ -157,35 +168,46 @@ __device__ __forceinline__ void column_totals(const Params& p, int n0, int et, c
       atomicAdd(ft.gsum + N + n0 + j, static_cast<double>((scol[256 + j] + scol[768 + j]) + (scol[1280 + j] + scol[1792 + j])));
     }
   }
-  __threadfence();
+  // arrive: the block barrier orders the CTA's atomics before thread 0, whose fence (cumulative) publishes them before the
+  // counter moves - one membar per CTA instead of 256 (ncu: ERRBAR among the top stall sites of the first version)
   named_bar_sync(1, EPI_THREADS);
   const unsigned nctas = gridDim.x * gridDim.y;
-  if (et == 0) *sflag = (atomicAdd(ft.gcount, 1u) == nctas - 1u) ? 1u : 0u;
+  if (et == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(ft.gcount, 1u);
+    *sflag = (prev == nctas - 1u) ? 1u : 0u;
+  }
+  if (ft.world == 1) return;                            // one GPU: everybody spins on the counter itself (totals_wait)
   named_bar_sync(1, EPI_THREADS);
-  const bool last = *sflag != 0u;
+  if (*sflag != 0u) {                                   // the last CTA of this GPU: its sums are complete
+    const p2p::Peers* peers = static_cast<const p2p::Peers*>(ft.peers);
+    const int slot = static_cast<int>(seq % p2p::NSLOTS);
+    if (et == 0) __threadfence();
+    named_bar_sync(1, EPI_THREADS);
+    const int n2 = N;                                    // 2 N doubles = N double2
+    for (int r = 0; r < ft.world; ++r) {
+      double2* dst = reinterpret_cast<double2*>(peers->p[r]->data[slot][ft.rank]);
+      for (int i = et; i < n2; i += EPI_THREADS) {
+        double2 v;
+        v.x = ld_cg_f64(ft.gsum + 2 * i); v.y = ld_cg_f64(ft.gsum + 2 * i + 1);
+        dst[i] = v;
+      }
+    }
+    // one more scalar rides along (the step's loss sum on the first backward exchange)
+    if (ft.xsum && et < ft.world) peers->p[et]->data[slot][ft.rank][2 * N] = ld_cg_f64(ft.xsum);
+    named_bar_sync(1, EPI_THREADS);
+    if (et < ft.world) st_release_sys(&peers->p[et]->flag[slot][ft.rank], seq);
+    if (et == 0) peers->p[ft.rank]->seq = seq;
+  }
+}
+
+template <int EPI_THREADS>
+__device__ __forceinline__ void totals_wait(const Params& p, int n0, int et, double* tot, unsigned long long seq) {
+  const FusedTrain& ft = p.ft;
+  const int N = p.N;
+  if (ft.gsum == nullptr) { named_bar_sync(1, EPI_THREADS); return; }
   const p2p::Peers* peers = static_cast<const p2p::Peers*>(ft.peers);
   const int slot = static_cast<int>(seq % p2p::NSLOTS);
-  if (last) {
-    __threadfence();
-    if (ft.world > 1) {
-      const int n2 = N;                                  // 2 N doubles = N double2
-      for (int r = 0; r < ft.world; ++r) {
-        double2* dst = reinterpret_cast<double2*>(peers->p[r]->data[slot][ft.rank]);
-        for (int i = et; i < n2; i += EPI_THREADS) {
-          double2 v;
-          v.x = ld_cg_f64(ft.gsum + 2 * i); v.y = ld_cg_f64(ft.gsum + 2 * i + 1);
-          dst[i] = v;
-        }
-      }
-      // one more scalar rides along (the step's loss sum on the first backward exchange)
-      if (ft.xsum && et < ft.world) peers->p[et]->data[slot][ft.rank][2 * N] = ld_cg_f64(ft.xsum);
-      named_bar_sync(1, EPI_THREADS);
-      if (et < ft.world) st_release_sys(&peers->p[et]->flag[slot][ft.rank], seq);
-      if (et == 0) peers->p[ft.rank]->seq = seq;
-    } else if (et == 0) {
-      st_release_gpu(ft.gcount + 1, 1u);
-    }
-  }
   // wait: the other CTAs of this GPU (one GPU) / every rank's vector (data parallel)
   const unsigned long long t0 = p.wait_limit_ns > 0 ? gtime() : 0ull;
   if (ft.world > 1) {
@@ -197,8 +219,9 @@ __device__ __forceinline__ void column_totals(const Params& p, int n0, int et, c
         }
       }
     }
-  } else if (et == 0 && !last) {
-    while (ld_acquire_gpu(ft.gcount + 1) == 0u) {
+  } else if (et == 0) {
+    const unsigned nctas = gridDim.x * gridDim.y;
+    while (ld_acquire_gpu(ft.gcount) < nctas) {
       if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) { printf("p3d: grid barrier timed out\n"); __trap(); }
     }
   }
@@ -228,7 +251,7 @@ __device__ __forceinline__ void column_totals(const Params& p, int n0, int et, c
 // training epilogues (forward / backward).  RES: a residual operand is added.  CS: column sums of the result and its
 // square are accumulated (BatchNorm statistics of a forward layer on the unfused path).
 template <int OUT, bool RES, int CS>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__((OUT >= 3) ? FUSED_NTHREADS : NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -246,6 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   float* scol = sbias + 256;
   float* sfin = scol + 2048;                     // [2][256] per-column finals of the fused epilogues
   double* stot = reinterpret_cast<double*>(sfin + 512);   // [2][256] column totals of the global batch
+  float* scst = reinterpret_cast<float*>(stot + 512);     // [4][256] gamma | beta | mean | rstd of this CTA's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) P3D_STAMP(0);
@@ -351,22 +375,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // is a per-lane constant and the column sums need 2 shuffle steps instead of a 31-shuffle butterfly.
     if constexpr (OUT == 3 || OUT == 4) {
       // ------------------------------------------------------------ fused training epilogues
-      // Two passes over the tile with the column statistics of the (global) batch in between (column_totals): GEMM +
-      // statistics + finalize + activation kernels -> 1 launch, both directions.  Eight warps cannot hide the latency
-      // of an elementwise pass the way a standalone kernel with 64 warps per SM does (first version: 27 of the 34 us
-      // of a 4096-pose forward layer were epilogue), so the work is arranged around what they CAN overlap:
+      // Two passes over the tile with the column statistics of the (global) batch in between (totals_arrive / _wait):
+      // GEMM + statistics + finalize + activation kernels -> 1 launch, both directions.  Eight warps cannot hide the
+      // latency of an elementwise pass the way a standalone kernel with 64 warps per SM does (first version: 27 of the
+      // 34 us of a 4096-pose forward layer were epilogue), so the work is arranged around what they CAN overlap:
       //   phase 0, under the mainloop (these warps would only wait for the accumulator): everything that does not need
       //            it.  Forward: the dropout keep-bits (Philox or the injected mask) - kept as one bit per element in
-      //            registers, the mask bytes stored for the backward pass.  Backward: z and the keep-mask are read,
+      //            registers, the mask bytes stored for the backward pass; what is not finished when the accumulator
+      //            arrives is done later in the shadow of the grid barrier.  Backward: z and the keep-mask are read,
       //            xhat = (z - mean) rstd goes into the spare half of the TMEM allocation, relu' * keep into bits.
       //   pass 1:  accumulator -> (alpha, bias, residual) -> column partial sums; the values every lane has produced are
       //            written back over the accumulator chunk they came from with tcgen05.st - lane l's 32 registers go to
       //            TMEM lane l, so TMEM serves as 128 bytes per lane and chunk of private scratch, already in the
       //            4-columns-x-8-rows arrangement the global accesses want (no second trip through shared memory).
-      //   pass 2:  reads that scratch; no global loads besides the residual operand.
-      const int ew = warp & 3, half = (warp - 2) >> 2;
-      const int hw = p.bn >= 64 ? p.bn / 2 : 32;
-      const int cbeg = half * hw, cend = (cbeg + hw < p.bn) ? cbeg + hw : p.bn;
+      //   shadow:  between arriving at the grid barrier and the sums being known (3-4 us): the stores of z (forward).
+      //   pass 2:  reads the scratch; per-column constants come from shared memory (staged once; an __ldg per chunk
+      //            exposed an L2 round trip each time); no global loads besides the residual operand.
+      constexpr int EPI_THREADS = FUSED_EPI_THREADS;           // (shadows the plain epilogues' constant)
+      constexpr int PARTS = P3D_FUSED_EPI_WARPS / 4;           // warps per TMEM lane quadrant
+      const int ew = warp & 3, part = (warp - 2) >> 2;
+      // the tile's 32-column chunks go round robin over the warps of a quadrant: chunk k of this warp = columns
+      // 32 (part + PARTS k) ..
+      const int cbeg = 32 * part;
+      constexpr int CSTEP = 32 * PARTS;
+      int nch = 0;                                             // chunks this warp owns (<= 4)
+      for (int c0 = cbeg; c0 < p.bn && n0 + c0 < p.N; c0 += CSTEP) ++nch;
       const train::StepScalars* sc = static_cast<const train::StepScalars*>(p.ft.sc);
       const int et = (warp - 2) * 32 + lane;
       // data parallel: the sequence number of this exchange - read before anybody of this grid can have advanced it
@@ -374,7 +407,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (p.ft.world > 1) seq = static_cast<const p2p::Peers*>(p.ft.peers)->p[p.ft.rank]->seq + 1;
       grid_dependency_wait();
       const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
-      for (int j = et; j < p.bn; j += EPI_THREADS) sbias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
+      for (int j = et; j < p.bn; j += EPI_THREADS) {
+        const int n = n0 + j;
+        const bool okc = n < p.N;
+        sbias[j] = (p.bias && okc) ? __ldg(p.bias + n) : 0.f;
+        scst[j] = (has_bn && okc) ? __ldg(p.ft.gamma + n) : 1.f;
+        scst[256 + j] = (has_bn && okc) ? __ldg(p.ft.beta + n) : 0.f;
+        if (OUT == 4) {
+          scst[512 + j] = (has_bn && okc) ? __ldg(p.ft.mean + n) : 0.f;
+          scst[768 + j] = (has_bn && okc) ? __ldg(p.ft.rstd + n) : 1.f;
+        }
+      }
+      named_bar_sync(1, EPI_THREADS);
       constexpr int TP = 36;
       const uint32_t tile_s = smem_u32(smem) + (warp - 2) * 32 * TP * 4;
       const uint32_t sbias_s = smem_u32(sbias);
@@ -382,7 +427,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int mrow0 = m0 + ew * 32 + rg;
       const float keep = sc->keep, inv_keep = sc->inv_keep;
       const bool writer = (blockIdx.y == 0);                   // of the CTAs that share a column: the one that stores per-column results
-      const bool has_bn = p.ft.has_bn != 0, dropout = p.ft.dropout != 0;
       const double invB = static_cast<double>(p.ft.invB);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
       // chunk k of this warp: bit (4 i + j) = row mrow0 + 4 i, column cq + j.  Four scalars picked by selects: an array
@@ -390,42 +434,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t g0 = 0xffffffffu, g1 = 0xffffffffu, g2 = 0xffffffffu, g3 = 0xffffffffu;
       auto set_gate = [&](int k, uint32_t b) { if (k == 0) g0 = b; else if (k == 1) g1 = b; else if (k == 2) g2 = b; else g3 = b; };
       auto get_gate = [&](int k) { return k == 0 ? g0 : (k == 1 ? g1 : (k == 2 ? g2 : g3)); };
+      auto cst4 = [&](int which, int c) { return *reinterpret_cast<const float4*>(scst + which * 256 + c); };
 
-      // ---------------------------------------------------------------- phase 0 (under the mainloop)
-      if constexpr (OUT == 3) {
-        if (dropout) {
-          for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
-            const int n = n0 + c0 + cq;
-            uint32_t bits = 0;
+      // ---------------------------------------------------------------- phase 0 (under the mainloop), one chunk at a time
+      auto pre_chunk = [&](int k) {
+        const int c0 = cbeg + CSTEP * k;
+        const int n = n0 + c0 + cq;
+        if constexpr (OUT == 3) {
+          uint32_t bits = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = mrow0 + 4 * i;
-              if (m >= p.M) continue;
-              const size_t off = static_cast<size_t>(m) * p.N + n;
-              uchar4 kb;
-              if (p.ft.mask_in) {
-                kb = *reinterpret_cast<const uchar4*>(p.ft.mask_in + off);
-              } else {
-                const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer),
-                                                      static_cast<uint32_t>(p.ft.row0 + m), static_cast<uint32_t>(n >> 2));
-                kb = make_uchar4(train::keep_bit(w4.x, keep), train::keep_bit(w4.y, keep), train::keep_bit(w4.z, keep), train::keep_bit(w4.w, keep));
-              }
-              *reinterpret_cast<uchar4*>(p.ft.mask + off) = kb;
-              bits |= ((kb.x ? 1u : 0u) | (kb.y ? 2u : 0u) | (kb.z ? 4u : 0u) | (kb.w ? 8u : 0u)) << (4 * i);
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            if (m >= p.M) continue;
+            const size_t off = static_cast<size_t>(m) * p.N + n;
+            uchar4 kb;
+            if (p.ft.mask_in) {
+              kb = *reinterpret_cast<const uchar4*>(p.ft.mask_in + off);
+            } else {
+              const uint4 w4 = train::dropout_words(sc->seed, sc->step, static_cast<uint32_t>(p.ft.layer),
+                                                    static_cast<uint32_t>(p.ft.row0 + m), static_cast<uint32_t>(n >> 2));
+              kb = make_uchar4(train::keep_bit(w4.x, keep), train::keep_bit(w4.y, keep), train::keep_bit(w4.z, keep), train::keep_bit(w4.w, keep));
             }
-            set_gate(k, bits);
+            *reinterpret_cast<uchar4*>(p.ft.mask + off) = kb;
+            bits |= ((kb.x ? 1u : 0u) | (kb.y ? 2u : 0u) | (kb.z ? 4u : 0u) | (kb.w ? 8u : 0u)) << (4 * i);
           }
-        }
-      } else {
-        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
-          const int n = n0 + c0 + cq;
-          float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
-          if (has_bn) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ft.mean + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
-            mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
-            ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w; be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
-          }
+          set_gate(k, bits);
+        } else {
+          const float4 g4 = cst4(0, c0 + cq), b4 = cst4(1, c0 + cq), m4 = cst4(2, c0 + cq), r4 = cst4(3, c0 + cq);
+          const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+          const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
           float4 z4[8];
           uchar4 mk[8];
 #pragma unroll
@@ -452,20 +489,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           set_gate(k, bits);
           tmem_st_32x32b_x32(taddr + p.bn + c0, xh);          // the spare half of the allocation: columns bn .. 2 bn
         }
+      };
+      int kdone = 0;
+      if constexpr (OUT == 3) {
+        if (!dropout) kdone = nch;
+        while (kdone < nch && !mbar_try_wait(accf, 0)) pre_chunk(kdone++);     // the rest follows in the barrier's shadow
+      } else {
+        while (kdone < nch) pre_chunk(kdone++);                                // pass 1 needs all of it
         tmem_st_wait();
       }
-      named_bar_sync(1, EPI_THREADS);                          // sbias staged
+      if (warp == 2) P3D_STAMP(14);                            // phase 0 done (forward: as far as the mainloop allowed)
       mbar_wait(accf, 0, 3);
+      if (warp == 2) P3D_STAMP(5);
       tc_fence_after();
-      // accumulator chunk -> this lane's 4 columns x 8 rows (rows mrow0 + 4 i), as alpha * acc + bias
-      auto chunk = [&](int c0, float (&o)[8][4]) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
+      // accumulator chunk (already in registers, row per lane) -> this lane's 4 columns x 8 rows (rows mrow0 + 4 i), as
+      // alpha * acc + bias.  The registers are free again after the shared-memory stores: the caller re-issues the TMEM
+      // load of the next chunk into them before it works on this one.
+      auto transpose = [&](int c0, uint32_t (&v)[32], float (&o)[8][4], bool more) {
         tmem_ld_wait();
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) sts128(tile_s + (lane * TP + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
+        if (more) tmem_ld_32x32b_x32(taddr + c0 + CSTEP, v);
         const float4 b4 = lds128(sbias_s + (c0 + cq) * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -502,27 +548,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           *reinterpret_cast<float4*>(q1 + 256) = make_float4(s2[0], s2[1], s2[2], s2[3]);
         }
       };
+      uint32_t acc[32];
+      if (nch > 0) tmem_ld_32x32b_x32(taddr + cbeg, acc);
       if constexpr (OUT == 3) {
-        // ---- forward pass 1: z = alpha acc + bias -> global (the backward pass needs it), column sums, z -> scratch
-        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
+        // ---- forward pass 1: z = alpha acc + bias, column sums, z -> scratch
+        const bool z_in_shadow = has_bn && p.ft.gsum != nullptr;       // with a grid barrier to wait for, z is stored behind it
+        for (int k = 0; k < nch; ++k) {
+          const int c0 = cbeg + CSTEP * k;
           float o[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-          chunk(c0, o);
-          const int n = n0 + c0 + cq;
+          transpose(c0, acc, o, k + 1 < nch);
+          if (!z_in_shadow) {
+            const int n = n0 + c0 + cq;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = mrow0 + 4 * i;
-            const bool live = m < p.M;
-            if (live) *reinterpret_cast<float4*>(p.C + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float q = live ? o[i][j] : 0.f; s1[j] += q; s2[j] += q * q; }
+            for (int i = 0; i < 8; ++i) {
+              const int m = mrow0 + 4 * i;
+              if (m < p.M) *reinterpret_cast<float4*>(p.C + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            }
           }
-          if (has_bn) publish(c0, s1, s2);
+          if (has_bn) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool live = mrow0 + 4 * i < p.M;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float q = live ? o[i][j] : 0.f; s1[j] += q; s2[j] += q * q; }
+            }
+            publish(c0, s1, s2);
+          }
           stash(c0, o);
         }
         tmem_st_wait();
+        if (warp == 2) P3D_STAMP(15);                          // pass 1 done
         if (has_bn) {
           named_bar_sync(1, EPI_THREADS);
-          column_totals(p, n0, et, scol, stot, sflag, seq);
+          totals_arrive<EPI_THREADS>(p, n0, et, scol, stot, sflag, seq);
+        }
+        // ---- in the shadow of the barrier: what is left of the dropout bits, and z -> global (the backward pass reads it)
+        while (kdone < nch) pre_chunk(kdone++);
+        for (int k = 0; z_in_shadow && k < nch; ++k) {
+          const int c0 = cbeg + CSTEP * k, n = n0 + c0 + cq;
+          float o[8][4];
+          unstash(c0, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i;
+            if (m < p.M) *reinterpret_cast<float4*>(p.C + static_cast<size_t>(m) * p.N + n) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+          }
+        }
+        if (has_bn) {
+          totals_wait<EPI_THREADS>(p, n0, et, stot, seq);
+          if (warp == 2) P3D_STAMP(16);                        // column totals of the global batch known
           // mean / biased variance over the global batch in double, as train.cu's bn_finalize_kernel does it;
           // moving averages with momentum .99 (one writer per column)
           for (int j = et; j < p.bn; j += EPI_THREADS) {
@@ -541,8 +615,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           named_bar_sync(1, EPI_THREADS);
         }
         // ---- forward pass 2: BN, ReLU, dropout, + residual -> h (fp32, where a later layer adds it), hb (bf16 operand)
-        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
-          const int n = n0 + c0 + cq;
+        for (int k = 0; k < nch; ++k) {
+          const int c0 = cbeg + CSTEP * k, n = n0 + c0 + cq;
           float4 hr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -551,18 +625,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
           float o[8][4];
           unstash(c0, o);
-          float sc_[4] = {1.f, 1.f, 1.f, 1.f}, sh_[4] = {0.f, 0.f, 0.f, 0.f};      // BN as one multiply-add: a = z * sc + sh
           if (has_bn) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), b4 = __ldg(reinterpret_cast<const float4*>(p.ft.beta + n));
+            const float4 g4 = cst4(0, c0 + cq), b4 = cst4(1, c0 + cq);
             const float4 m4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), r4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
             const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
             const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { sc_[j] = rs[j]; sh_[j] = mu[j]; (void)ga; (void)be; }
-#pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[i][j] = ga[j] * ((o[i][j] - sh_[j]) * sc_[j]) + be[j];      // same operation order as the unfused kernels
+              for (int j = 0; j < 4; ++j) o[i][j] = ga[j] * ((o[i][j] - mu[j]) * rs[j]) + be[j];      // same operation order as the unfused kernels
           }
           const uint32_t bits = get_gate(k);
 #pragma unroll
@@ -585,8 +656,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       } else {
         // ---- backward pass 1: dh = alpha acc (+ res) (-> dh_out); da = dh * keep/relu' gate; column sums of da, da * xhat
-        for (int c0 = cbeg, k = 0; c0 < cend && n0 + c0 < p.N; c0 += 32, ++k) {
-          const int n = n0 + c0 + cq;
+        for (int k = 0; k < nch; ++k) {
+          const int c0 = cbeg + CSTEP * k, n = n0 + c0 + cq;
           float4 r4[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -594,7 +665,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             r4[i] = p.res ? __ldg(reinterpret_cast<const float4*>(p.res + static_cast<size_t>(m < p.M ? m : 0) * p.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           float o[8][4], xh[8][4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-          chunk(c0, o);
+          transpose(c0, acc, o, k + 1 < nch);
           unstash(p.bn + c0, xh);
           const uint32_t bits = get_gate(k);
 #pragma unroll
@@ -616,8 +687,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           stash(c0, o);
         }
         tmem_st_wait();
+        if (warp == 2) P3D_STAMP(15);
         named_bar_sync(1, EPI_THREADS);
-        column_totals(p, n0, et, scol, stot, sflag, seq);
+        totals_arrive<EPI_THREADS>(p, n0, et, scol, stot, sflag, seq);
+        totals_wait<EPI_THREADS>(p, n0, et, stot, seq);
+        if (warp == 2) P3D_STAMP(16);
         // sum da (= dbeta, or the bias gradient) and sum da * xhat (= dgamma) over the global batch; every rank holds
         // them in full, so they enter the flat gradient pre-divided by the world size
         for (int j = et; j < p.bn; j += EPI_THREADS) {
@@ -632,14 +706,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         named_bar_sync(1, EPI_THREADS);
         // ---- backward pass 2: dz = gamma rstd (da - mean(da) - xhat mean(da xhat)) -> bf16 operand of the next GEMMs
         const float invBf = p.ft.invB;
-        for (int c0 = cbeg; c0 < cend && n0 + c0 < p.N; c0 += 32) {
-          const int n = n0 + c0 + cq;
+        for (int k = 0; k < nch; ++k) {
+          const int c0 = cbeg + CSTEP * k, n = n0 + c0 + cq;
           float o[8][4], xh[8][4];
           unstash(c0, o);
           float gr[4] = {1.f, 1.f, 1.f, 1.f}, P[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
           if (has_bn) {
             unstash(p.bn + c0, xh);
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ft.gamma + n)), r4 = __ldg(reinterpret_cast<const float4*>(p.ft.rstd + n));
+            const float4 g4 = cst4(0, c0 + cq), r4 = cst4(3, c0 + cq);
             const float4 P4 = *reinterpret_cast<const float4*>(sfin + c0 + cq), Q4 = *reinterpret_cast<const float4*>(sfin + 256 + c0 + cq);
             gr[0] = g4.x * r4.x; gr[1] = g4.y * r4.y; gr[2] = g4.z * r4.z; gr[3] = g4.w * r4.w;
             P[0] = P4.x * invBf; P[1] = P4.y * invBf; P[2] = P4.z * invBf; P[3] = P4.w * invBf;
@@ -956,6 +1030,13 @@ int plan(const GemmArgs& g, GemmPlan* out) {
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.b_independent = g.pdl ? 1 : 0;
   p.dbg = static_cast<unsigned long long*>(g.dbg);
+  {   // diagnostics (tools/diag_fused_phases.py): stamp the fused kernel of one layer / direction of a training step
+    const char* e = getenv("P3D_GEMM_DBG_PTR");
+    const char* em = getenv("P3D_GEMM_DBG_MODE");
+    const char* el = getenv("P3D_GEMM_DBG_LAYER");
+    if (!p.dbg && e && em && g.fused_mode == atoi(em) && (!el || g.fused.layer == atoi(el)))
+      p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  }
   // diagnostics: P3D_SYNC_TIMEOUT_S=<seconds> makes a grid / peer wait that long trap with a message; by default
   // the fused epilogues wait for their peers like an NCCL collective does (ranks must stay in lockstep)
   static const long long wait_ns = [] { const char* e = getenv("P3D_SYNC_TIMEOUT_S"); return e ? static_cast<long long>(atof(e) * 1e9) : 0LL; }();
@@ -1013,7 +1094,7 @@ int launch(const GemmPlan& pl, cudaStream_t st) {
     attr.mark();
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = d->grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = d->grid; cfg.blockDim = dim3(d->fused_mode ? FUSED_NTHREADS : NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   if (d->pdl) {
     // programmatic dependent launch: this kernel may start while its predecessor in the stream drains; it orders

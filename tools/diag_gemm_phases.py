@@ -10,7 +10,7 @@ def run(M, N, K, a_mn, b_mn, split_k=0, colsum=False, res=False):
     C = torch.zeros((M, N), device="cuda")
     cs = torch.zeros(2 * N, dtype=torch.float64, device="cuda") if colsum else None
     rv = torch.randn((M, N), device="cuda") if res else None
-    dbg = torch.zeros((4096, 16), dtype=torch.int64, device="cuda")
+    dbg = torch.zeros((4096, 32), dtype=torch.int64, device="cuda")
     def call():
         _lib.check(_lib.lib.p3d_debug_tc_gemm(A.data_ptr(), A.shape[1], a_mn, B.data_ptr(), B.shape[1], b_mn, C.data_ptr(), N, M, N, K,
                                               None, rv.data_ptr() if res else None, 1.0, split_k, cs.data_ptr() if colsum else None, None))
