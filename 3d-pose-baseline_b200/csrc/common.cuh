@@ -252,6 +252,8 @@ int gemm(const GemmArgs& g, cudaStream_t st);
 bool fused_fits(int M, int N, int K, int num_sms);   // can the fused training epilogues serve an M x N layer (all tiles resident)?
 }  // namespace tcg
 int sqerr_accumulate(const float* y, const float* t, size_t n, double* acc, cudaStream_t st);
+int l2persist_acquire(int dev, size_t bytes);                // mlp_tc.cu: persisting-L2 set-aside for the fused inference kernel
+int l2persist_release(int dev);                              // ... handed back (training steps want the whole L2)
 int mark_model_work(p3d_model* m, cudaStream_t st);          // record ev_done on st
 int order_after_model_work(p3d_model* m, cudaStream_t st);   // st waits for the last recorded ev_done
 
@@ -283,7 +285,6 @@ struct p3d_model {
   int num_sms = 0;
   __nv_bfloat16* act_scratch = nullptr;  // [2][grid*128][L] bf16 (tcgen05 path)
   int act_grid = 0;
-  bool l2_persist_used = false;          // the fused kernel left persisting lines in the L2 (reset before a training step)
   __nv_bfloat16* xb = nullptr;           // packed input [cap][64]
   int64_t xb_cap = 0;
   // layered (one tcgen05 GEMM per layer) forward for small/medium batches: plans cached per batch size

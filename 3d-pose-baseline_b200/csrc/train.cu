@@ -985,10 +985,7 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
                int64_t Bg, int64_t row0, float* loss, float* lr_used, float* y, cudaStream_t st) {
   P3D_TRY(ensure_workspace(m, B));
   TrainWorkspace& w = m->tw;
-  if (m->l2_persist_used) {     // hand the L2 set-aside of the fused inference kernel back to normal traffic
-    cudaCtxResetPersistingL2Cache();
-    m->l2_persist_used = false;
-  }
+  P3D_TRY(l2persist_release(m->cfg.device));     // the fused inference kernel's L2 set-aside goes back to normal traffic
   P3D_TRY(push_scalars(m, keep, seed, st));
   // data parallel: the NCCL all-reduces (SyncBN sums, gradient) are captured into the graph with everything else
   static const bool dp_graph = [] { const char* e = getenv("P3D_TRAIN_GRAPH_DP"); return !(e && e[0] == '0'); }();
@@ -1031,6 +1028,7 @@ int train_epoch(p3d_model* m, const float* X, const float* T, int64_t n, const l
                 float* losses, float* lr_last, cudaStream_t st) {
   P3D_REQUIRE(m->world == 1, "train_epoch: data-parallel models step through p3d_model_train_step");
   P3D_TRY(ensure_workspace(m, B));
+  P3D_TRY(l2persist_release(m->cfg.device));
   TrainWorkspace& w = m->tw;
   const int64_t nb = n / B;                                   // the n % B tail is dropped (linear_model.py:311-313)
   int g = static_cast<int>((B * (kIn + m->out_size) + 255) / 256);
