@@ -176,9 +176,16 @@ struct Layout {
   double data[NSLOTS][MAXW][MAXN];
   unsigned long long flag[NSLOTS][MAXW];
   unsigned long long seq;           // last completed sequence number (local)
+  // gradient all-reduce (p2p.cu grad_allreduce_kernel): entry / exit flags per peer, sequence number, CTA counter
+  unsigned long long gflag[2][MAXW];
+  unsigned long long gseq;
+  unsigned int gdone;
 };
 struct Peers { Layout* p[MAXW]; };
+struct GradPeers { float* g[MAXW]; };   // every rank's flat gradient buffer, peer-mapped
 bool ready(const p3d_model* m);
+bool grad_ready(const p3d_model* m);               // the gradient buffers of all ranks are mapped too
+int allreduce_grad(p3d_model* m, size_t n, cudaStream_t st);   // m->grad <- sum over ranks, summed in rank order
 const Peers* device_peers(const p3d_model* m);     // device copy of the peer table (null until attached)
 struct BnFinalize {                 // optional fused tail: BatchNorm statistics from the reduced [sum | sumsq]
   double invB = 0.0;

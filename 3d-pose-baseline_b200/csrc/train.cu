@@ -63,6 +63,8 @@ static int allreduce(p3d_model* m, void* buf, size_t n, ncclDataType_t dt, cudaS
   if (m->world <= 1) return P3D_OK;
   // the latency-bound reductions (SyncBN sums, loss) go over NVLink peer memory in one kernel each (p2p.cu)
   if (dt == ncclDouble && n <= 8192 && p2p::ready(m)) return p2p::allreduce_small(m, static_cast<double*>(buf), n, st);
+  // the flat gradient: pulled, summed in rank order and pushed back over peer memory (one kernel)
+  if (dt == ncclFloat && buf == m->grad && p2p::grad_ready(m)) return p2p::allreduce_grad(m, n, st);
   P3D_NCCL(nccl()->AllReduce(buf, buf, n, dt, ncclSum, static_cast<ncclComm_t>(m->nccl_comm), st));
   return P3D_OK;
 }

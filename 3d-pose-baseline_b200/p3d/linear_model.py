@@ -290,9 +290,9 @@ class LinearModel(object):
         # single node: the small SyncBN / loss reductions go over NVLink peer memory (CUDA IPC); NCCL otherwise
         self.p2p = False
         if os.environ.get("P3D_P2P", "1") != "0" and int(os.environ.get("LOCAL_WORLD_SIZE", self.world)) == self.world:
-            mine = np.zeros(64, dtype=np.uint8)
+            mine = np.zeros(128, dtype=np.uint8)
             check(lib.p3d_model_p2p_handle(self._handle, _lib.np_ptr(mine)))
-            hs = [torch.zeros(64, dtype=torch.uint8, device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
+            hs = [torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
                   for _ in range(self.world)]
             src = torch.from_numpy(mine)
             dist.all_gather(hs, src.cuda(self.device) if dist.get_backend() == "nccl" else src)

@@ -118,13 +118,14 @@ int p3d_model_attach_nccl(p3d_model* m, const uint8_t* id_host, int rank, int wo
 
 /* Optional, after attach_nccl, ranks of ONE node: the latency-bound reductions of a data-parallel step (SyncBN sums
  * forward and backward, loss) then travel over NVLink peer memory instead of NCCL calls - inside the GEMM kernels that
- * need them (fused training epilogues: batches whose tiles all fit the SMs) or as single kernels.  Every rank exports
- * the CUDA IPC handle of its exchange buffer (64 bytes), the host layer all-gathers them, every rank attaches all
- * `world` handles (rank-major, 64 bytes each).  If a peer is not reachable attach fails, closes what it had opened and
+ * need them (fused training epilogues: batches whose tiles all fit the SMs) or as single kernels; and the flat gradient
+ * all-reduce becomes one pull / sum-in-rank-order / push kernel over the peer-mapped gradient buffers instead of
+ * ncclAllReduce (P3D_P2P_GRAD=0 keeps NCCL).  Every rank exports two CUDA IPC handles (exchange buffer, gradient buffer:
+ * 128 bytes), the host layer all-gathers them, every rank attaches all `world` entries (rank-major, 128 bytes each).  If a peer is not reachable attach fails, closes what it had opened and
  * the step keeps using NCCL; p3d_model_p2p_detach does the same on request (the host layer calls it on every rank when
  * ANY rank failed to attach, so that all ranks take the same path).  The exchange waits for its peers like an NCCL
  * collective (no timeout; P3D_SYNC_TIMEOUT_S=<s> makes a longer wait trap): ranks must step in lockstep. */
-int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle64_host);
+int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle128_host);   /* [exchange buffer | flat gradient buffer] */
 int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, int world);
 int p3d_model_p2p_detach(p3d_model* m);
 /* Measurement aid (bench.py `secondary.train_dp`): one exchange of a data-parallel step on its own, on `stream`.

@@ -111,7 +111,7 @@ for fused_env, Bq in (("1", 512), ("1", 4096), ("0", 4096), ("1", 65)):
     for name in ("linear_model/w1", "linear_model/two_linear_0/w3_0", "linear_model/w4", "linear_model/batch_normalization/gamma",
                  "linear_model/two_linear_1/batch_normalization21/beta", "linear_model/batch_normalization/moving_variance"):
         err = np.abs(vd[name].astype(np.float64) - vs_[name])
-        if not np.quantile(err, 0.99) <= (0.05 if Bq >= 512 else 0.2) * 2e-3 + 1e-5 * np.abs(vs_[name]).max():
+        if not np.quantile(err, 0.99) <= (0.1 if Bq >= 512 else 0.2) * 2e-3 + 1e-5 * np.abs(vs_[name]).max():
             whyq.append("%s: 99%% quantile of |dp - single| = %.3e" % (name, np.quantile(err, 0.99)))
     wq = torch.from_numpy(vd["linear_model/two_linear_1/w2_1"]).cuda()
     wq0 = wq.clone(); dist.broadcast(wq0, 0)
