@@ -180,6 +180,10 @@ struct Layout {
   unsigned long long gflag[2][MAXW];
   unsigned long long gseq;
   unsigned int gdone;
+  // Low-latency form of `data` for the exchanges inside the fused GEMM epilogues: every double travels as two 8-byte
+  // words {32 payload bits, 32-bit sequence tag}; a word is valid when its tag is the exchange's sequence number, so the
+  // receiver polls the data itself - no release fence and no separate flag hop (one NVLink write latency per exchange).
+  uint4 ll[NSLOTS][MAXW][MAXN + 8];
 };
 struct Peers { Layout* p[MAXW]; };
 struct GradPeers { float* g[MAXW]; };   // every rank's flat gradient buffer, peer-mapped

@@ -139,15 +139,31 @@ __global__ void __launch_bounds__(256) grad_allreduce_kernel(const Peers peers, 
   __syncthreads();
   const long long per = (n4 + world - 1) / world;
   const long long beg = static_cast<long long>(rank) * per, end = (beg + per < n4) ? beg + per : n4;
-  for (long long i = beg + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < end; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 v[W];
+  // U independent float4 positions per thread and trip: all their peer loads are in flight together (an NVLink round trip is
+  // ~2-3 us; position by position the two-rank case spent 7 of them in sequence: 45 us for 2 x 8.6 MB)
+  constexpr int U = (W <= 2) ? 4 : ((W <= 4) ? 2 : 1);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = beg + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < end; i0 += U * stride) {
+    float4 v[U][W];
 #pragma unroll
-    for (int r = 0; r < W; ++r) v[r] = ld_relaxed_sys_f4(gp.g[r] + 4 * i);
-    float4 a = v[0];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < end) {
 #pragma unroll
-    for (int r = 1; r < W; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+        for (int r = 0; r < W; ++r) v[u][r] = ld_relaxed_sys_f4(gp.g[r] + 4 * i);
+      }
+    }
 #pragma unroll
-    for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(gp.g[r] + 4 * i) = a;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < end) {
+        float4 a = v[u][0];
+#pragma unroll
+        for (int r = 1; r < W; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+#pragma unroll
+        for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(gp.g[r] + 4 * i) = a;
+      }
+    }
   }
   if (rank == 0 && blockIdx.x == 0) {                   // a length that is not a multiple of 4: the tail, element by element
     for (long long i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {

@@ -130,6 +130,14 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_volatile_u4(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -143,13 +151,14 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
 //   one M tile, one GPU : the four quadrant partials are the batch.
 //   otherwise           : partials -> gsum (fp64 atomics) -> arrival counter; the CTA that arrives last owns the complete
 //                         sums of this GPU.  One GPU: everybody spins on the counter reaching the grid size.  Data parallel: it
-//                         stores the vector into slot [seq % NSLOTS][rank] of EVERY rank's exchange buffer (16-byte NVLink
-//                         stores), then one thread per peer raises that peer's flag with st.release.sys (cumulative: the
-//                         block barrier before it orders the whole CTA's stores); all CTAs of all ranks spin on their own
-//                         rank's flags (ld.acquire.sys) and add the `world` vectors in rank order - every rank gets
-//                         bit-identical sums.  Slot reuse is safe with >= 2 slots: nobody can be more than one exchange
-//                         ahead of the slowest rank (it needs that rank's flag).  No timeout by default: like an NCCL
-//                         collective this waits for its peers (Params::wait_limit_ns is the diagnostics switch).
+//                         stores the vector into slot [seq % NSLOTS][rank] of EVERY rank's exchange buffer as self-validating
+//                         16-byte words {lo, tag, hi, tag} (tag = sequence number; 8-byte halves arrive whole over NVLink), and
+//                         every thread of every CTA of every rank polls exactly the words it consumes and adds the `world`
+//                         values in rank order - bit-identical sums everywhere, one NVLink write latency per exchange (the
+//                         first version published the vector with a system-scope release fence and a flag per peer: two more
+//                         hops, 17 us per exchange on 8 GPUs).  Slot reuse is safe: nobody can be more than one exchange ahead
+//                         of the slowest rank (it needs that rank's words).  No timeout by default: like an NCCL collective
+//                         this waits for its peers (Params::wait_limit_ns is the diagnostics switch).
 template <int EPI_THREADS>
 __device__ __forceinline__ void totals_arrive(const Params& p, int n0, int et, const float* scol, double* tot, uint32_t* sflag,
                                               unsigned long long seq) {
@@ -182,21 +191,18 @@ __device__ __forceinline__ void totals_arrive(const Params& p, int n0, int et, c
   if (*sflag != 0u) {                                   // the last CTA of this GPU: its sums are complete
     const p2p::Peers* peers = static_cast<const p2p::Peers*>(ft.peers);
     const int slot = static_cast<int>(seq % p2p::NSLOTS);
+    const uint32_t tag = static_cast<uint32_t>(seq);
     if (et == 0) __threadfence();
     named_bar_sync(1, EPI_THREADS);
-    const int n2 = N;                                    // 2 N doubles = N double2
-    for (int r = 0; r < ft.world; ++r) {
-      double2* dst = reinterpret_cast<double2*>(peers->p[r]->data[slot][ft.rank]);
-      for (int i = et; i < n2; i += EPI_THREADS) {
-        double2 v;
-        v.x = ld_cg_f64(ft.gsum + 2 * i); v.y = ld_cg_f64(ft.gsum + 2 * i + 1);
-        dst[i] = v;
-      }
+    // every value to every rank (this one included) as self-validating 16-byte stores {lo, tag, hi, tag}; one more scalar
+    // rides along at index 2 N (the step's loss sum on the first backward exchange)
+    const int nv = 2 * N + (ft.xsum ? 1 : 0);
+    for (int i = et; i < nv; i += EPI_THREADS) {
+      const double d = ld_cg_f64(i < 2 * N ? ft.gsum + i : ft.xsum);
+      const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(d));
+      const uint4 w = make_uint4(static_cast<uint32_t>(u), tag, static_cast<uint32_t>(u >> 32), tag);
+      for (int r = 0; r < ft.world; ++r) st_volatile_u4(&peers->p[r]->ll[slot][ft.rank][i], w);
     }
-    // one more scalar rides along (the step's loss sum on the first backward exchange)
-    if (ft.xsum && et < ft.world) peers->p[et]->data[slot][ft.rank][2 * N] = ld_cg_f64(ft.xsum);
-    named_bar_sync(1, EPI_THREADS);
-    if (et < ft.world) st_release_sys(&peers->p[et]->flag[slot][ft.rank], seq);
     if (et == 0) peers->p[ft.rank]->seq = seq;
   }
 }
@@ -206,43 +212,49 @@ __device__ __forceinline__ void totals_wait(const Params& p, int n0, int et, dou
   const FusedTrain& ft = p.ft;
   const int N = p.N;
   if (ft.gsum == nullptr) { named_bar_sync(1, EPI_THREADS); return; }
-  const p2p::Peers* peers = static_cast<const p2p::Peers*>(ft.peers);
-  const int slot = static_cast<int>(seq % p2p::NSLOTS);
-  // wait: the other CTAs of this GPU (one GPU) / every rank's vector (data parallel)
   const unsigned long long t0 = p.wait_limit_ns > 0 ? gtime() : 0ull;
-  if (ft.world > 1) {
-    if (et < ft.world) {
-      const unsigned long long* f = &peers->p[ft.rank]->flag[slot][et];
-      while (ld_acquire_sys(f) < seq) {
+  if (ft.world == 1) {
+    // one GPU: wait for the other CTAs (the counter reaches the grid size), then read the sums
+    if (et == 0) {
+      const unsigned nctas = gridDim.x * gridDim.y;
+      while (ld_acquire_gpu(ft.gcount) < nctas) {
+        if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) { printf("p3d: grid barrier timed out\n"); __trap(); }
+      }
+    }
+    named_bar_sync(1, EPI_THREADS);
+    for (int j = et; j < p.bn; j += EPI_THREADS) {
+      double s1 = 0.0, s2 = 0.0;
+      if (n0 + j < N) { s1 = ld_cg_f64(ft.gsum + n0 + j); s2 = ld_cg_f64(ft.gsum + N + n0 + j); }
+      tot[j] = s1; tot[256 + j] = s2;
+    }
+  } else {
+    // data parallel: every thread polls the words it consumes (column n0 + j of every rank) until they carry this
+    // exchange's tag, and adds them in rank order - bit-identical sums on every rank
+    const p2p::Layout* me = static_cast<const p2p::Peers*>(ft.peers)->p[ft.rank];
+    const int slot = static_cast<int>(seq % p2p::NSLOTS);
+    const uint32_t tag = static_cast<uint32_t>(seq);
+    auto fetch = [&](int r, int i) {
+      uint4 w = ld_volatile_u4(&me->ll[slot][r][i]);
+      while (w.y != tag || w.w != tag) {
         if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) {
-          printf("p3d: SyncBN exchange timed out (rank %d waits for rank %d, seq %llu)\n", ft.rank, et, seq); __trap();
+          printf("p3d: SyncBN exchange timed out (rank %d waits for rank %d, seq %llu)\n", ft.rank, r, seq); __trap();
         }
+        w = ld_volatile_u4(&me->ll[slot][r][i]);
       }
-    }
-  } else if (et == 0) {
-    const unsigned nctas = gridDim.x * gridDim.y;
-    while (ld_acquire_gpu(ft.gcount) < nctas) {
-      if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) { printf("p3d: grid barrier timed out\n"); __trap(); }
-    }
-  }
-  named_bar_sync(1, EPI_THREADS);
-  for (int j = et; j < p.bn; j += EPI_THREADS) {
-    double s1 = 0.0, s2 = 0.0;
-    if (n0 + j < N) {
-      if (ft.world > 1) {
-        const p2p::Layout* me = peers->p[ft.rank];
-        for (int r = 0; r < ft.world; ++r) { s1 += ld_cg_f64(&me->data[slot][r][n0 + j]); s2 += ld_cg_f64(&me->data[slot][r][N + n0 + j]); }
-      } else {
-        s1 = ld_cg_f64(ft.gsum + n0 + j); s2 = ld_cg_f64(ft.gsum + N + n0 + j);
+      return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w.z) << 32) | w.x));
+    };
+    for (int j = et; j < p.bn; j += EPI_THREADS) {
+      double s1 = 0.0, s2 = 0.0;
+      if (n0 + j < N) {
+        for (int r = 0; r < ft.world; ++r) { s1 += fetch(r, n0 + j); s2 += fetch(r, N + n0 + j); }
       }
+      tot[j] = s1; tot[256 + j] = s2;
     }
-    tot[j] = s1; tot[256 + j] = s2;
-  }
-  if (ft.xsum && ft.world > 1 && et == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-    const p2p::Layout* me = peers->p[ft.rank];
-    double s = 0.0;
-    for (int r = 0; r < ft.world; ++r) s += ld_cg_f64(&me->data[slot][r][2 * N]);
-    *ft.xsum = s;
+    if (ft.xsum && et == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+      double sx = 0.0;
+      for (int r = 0; r < ft.world; ++r) sx += fetch(r, 2 * N);
+      *ft.xsum = sx;
+    }
   }
   named_bar_sync(1, EPI_THREADS);
 }
