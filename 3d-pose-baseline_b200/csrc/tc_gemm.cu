@@ -233,20 +233,46 @@ __device__ __forceinline__ void totals_wait(const Params& p, int n0, int et, dou
     const p2p::Layout* me = static_cast<const p2p::Peers*>(ft.peers)->p[ft.rank];
     const int slot = static_cast<int>(seq % p2p::NSLOTS);
     const uint32_t tag = static_cast<uint32_t>(seq);
+    auto valid = [&](const uint4& w) { return w.y == tag && w.w == tag; };
+    auto value = [&](const uint4& w) { return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w.z) << 32) | w.x)); };
     auto fetch = [&](int r, int i) {
       uint4 w = ld_volatile_u4(&me->ll[slot][r][i]);
-      while (w.y != tag || w.w != tag) {
+      while (!valid(w)) {
         if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) {
           printf("p3d: SyncBN exchange timed out (rank %d waits for rank %d, seq %llu)\n", ft.rank, r, seq); __trap();
         }
         w = ld_volatile_u4(&me->ll[slot][r][i]);
       }
-      return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w.z) << 32) | w.x));
+      return value(w);
     };
     for (int j = et; j < p.bn; j += EPI_THREADS) {
       double s1 = 0.0, s2 = 0.0;
       if (n0 + j < N) {
-        for (int r = 0; r < ft.world; ++r) { s1 += fetch(r, n0 + j); s2 += fetch(r, N + n0 + j); }
+        // four ranks at a time: their eight words are requested together and the whole batch is re-polled until every
+        // word carries the tag - one L2 round trip per poll (the first version polled word by word: eight to sixteen
+        // round trips in a row, 15 us per exchange on 8 GPUs)
+        for (int r0 = 0; r0 < ft.world; r0 += 4) {
+          uint4 a[4], b[4];
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int r = (r0 + q < ft.world) ? r0 + q : r0;
+              a[q] = ld_volatile_u4(&me->ll[slot][r][n0 + j]);
+              b[q] = ld_volatile_u4(&me->ll[slot][r][N + n0 + j]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ok = ok && valid(a[q]) && valid(b[q]);
+            if (ok) break;
+            if (p.wait_limit_ns > 0 && gtime() - t0 > static_cast<unsigned long long>(p.wait_limit_ns)) {
+              printf("p3d: SyncBN exchange timed out (rank %d waits for ranks %d.., seq %llu)\n", ft.rank, r0, seq); __trap();
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (r0 + q < ft.world) { s1 += value(a[q]); s2 += value(b[q]); }
+          }
+        }
       }
       tot[j] = s1; tot[256 + j] = s2;
     }
