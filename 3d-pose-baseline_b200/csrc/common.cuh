@@ -172,6 +172,7 @@ namespace p2p {
 constexpr int NSLOTS = 4;
 constexpr int MAXN = 8192;          // doubles per reduction (2 x linear_size <= 4096)
 constexpr int MAXW = 16;
+constexpr int YMAX = 1 << 19;       // floats of gathered step outputs (10922 rows of 48)
 struct Layout {
   double data[NSLOTS][MAXW][MAXN];
   unsigned long long flag[NSLOTS][MAXW];
@@ -184,12 +185,18 @@ struct Layout {
   // words {32 payload bits, 32-bit sequence tag}; a word is valid when its tag is the exchange's sequence number, so the
   // receiver polls the data itself - no release fence and no separate flag hop (one NVLink write latency per exchange).
   uint4 ll[NSLOTS][MAXW][MAXN + 8];
+  // outputs of the last data-parallel step for the GLOBAL batch: every rank writes its rows into every rank's copy from
+  // inside the gradient all-reduce kernel (between its handshakes), so model.step() needs no all-gather of its own
+  float ybuf[YMAX];
 };
 struct Peers { Layout* p[MAXW]; };
 struct GradPeers { float* g[MAXW]; };   // every rank's flat gradient buffer, peer-mapped
 bool ready(const p3d_model* m);
 bool grad_ready(const p3d_model* m);               // the gradient buffers of all ranks are mapped too
-int allreduce_grad(p3d_model* m, size_t n, cudaStream_t st);   // m->grad <- sum over ranks, summed in rank order
+// m->grad <- sum over ranks, summed in rank order; y_local (may be null): this rank's [rows][out] step outputs, written to
+// rows row0.. of every rank's Layout::ybuf on the way
+int allreduce_grad(p3d_model* m, size_t n, const float* y_local, long long rows, long long row0, int out, cudaStream_t st);
+const float* gathered_outputs(const p3d_model* m);          // this rank's Layout::ybuf
 const Peers* device_peers(const p3d_model* m);     // device copy of the peer table (null until attached)
 struct BnFinalize {                 // optional fused tail: BatchNorm statistics from the reduced [sum | sumsq]
   double invB = 0.0;
@@ -328,4 +335,7 @@ struct p3d_model {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   void* p2p_state = nullptr;          // peer-memory exchange buffers of the small all-reduces (p2p.cu)
+  // data parallel: what the gradient exchange of the current step gathers on the way (set by the step, read by p2p)
+  const float* dp_y = nullptr; long long dp_rows = 0, dp_row0 = 0, dp_Bg = 0;
+  bool dp_y_gathered = false;         // the last step left the global outputs in the exchange buffer
 };

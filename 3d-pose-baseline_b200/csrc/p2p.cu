@@ -125,7 +125,8 @@ __device__ __forceinline__ void spin_until(const unsigned long long* f, unsigned
 }
 template <int W>      // world size as a template parameter: the per-rank values stay in registers
 __global__ void __launch_bounds__(256) grad_allreduce_kernel(const Peers peers, const GradPeers gp, int rank, long long n4,
-                                                             long long n, long long wait_limit_ns) {
+                                                             long long n, long long wait_limit_ns, const float* __restrict__ y_local,
+                                                             long long y_count, long long y_off) {
   constexpr int world = W;
   Layout* me = peers.p[rank];
   __shared__ unsigned long long s_seq;
@@ -164,6 +165,11 @@ __global__ void __launch_bounds__(256) grad_allreduce_kernel(const Peers peers, 
         for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(gp.g[r] + 4 * i) = a;
       }
     }
+  }
+  // this rank's rows of the step outputs -> every rank's ybuf (CTA b serves peer b; the exit handshake below publishes them)
+  if (y_local != nullptr && blockIdx.x < static_cast<unsigned>(world)) {
+    float* dst = peers.p[blockIdx.x]->ybuf + y_off;
+    for (long long i = threadIdx.x; i < y_count; i += blockDim.x) dst[i] = y_local[i];
   }
   if (rank == 0 && blockIdx.x == 0) {                   // a length that is not a multiple of 4: the tail, element by element
     for (long long i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
@@ -283,14 +289,16 @@ bool grad_ready(const p3d_model* m) {
   const State* s = static_cast<const State*>(m->p2p_state);
   return s->grad_mapped && ((s->world >= 2 && s->world <= 8) || s->world == 16);
 }
-int allreduce_grad(p3d_model* m, size_t n, cudaStream_t st) {
+const float* gathered_outputs(const p3d_model* m) { return ready(m) ? static_cast<const State*>(m->p2p_state)->local->ybuf : nullptr; }
+int allreduce_grad(p3d_model* m, size_t n, const float* y_local, long long rows, long long row0, int out, cudaStream_t st) {
   State* s = state_of(m);
   P3D_REQUIRE(s && s->ready && s->grad_mapped, "peer gradient all-reduce: gradient buffers not mapped");
   static const long long wait_ns = [] { const char* e = getenv("P3D_SYNC_TIMEOUT_S"); return e ? static_cast<long long>(atof(e) * 1e9) : 0LL; }();
   const long long n4 = static_cast<long long>(n / 4), nn = static_cast<long long>(n);
   const dim3 grid(2 * m->num_sms), block(256);
+  const long long y_count = y_local ? rows * out : 0, y_off = row0 * out;
   switch (s->world) {
-#define P3D_GAR(W) case W: grad_allreduce_kernel<W><<<grid, block, 0, st>>>(s->peers, s->gpeers, s->rank, n4, nn, wait_ns); break;
+#define P3D_GAR(W) case W: grad_allreduce_kernel<W><<<grid, block, 0, st>>>(s->peers, s->gpeers, s->rank, n4, nn, wait_ns, y_local, y_count, y_off); break;
     P3D_GAR(2) P3D_GAR(3) P3D_GAR(4) P3D_GAR(5) P3D_GAR(6) P3D_GAR(7) P3D_GAR(8) P3D_GAR(16)
 #undef P3D_GAR
     default: set_error("peer gradient all-reduce: world size %d has no instantiation", s->world); return P3D_ERR_ARG;

@@ -64,7 +64,11 @@ static int allreduce(p3d_model* m, void* buf, size_t n, ncclDataType_t dt, cudaS
   // the latency-bound reductions (SyncBN sums, loss) go over NVLink peer memory in one kernel each (p2p.cu)
   if (dt == ncclDouble && n <= 8192 && p2p::ready(m)) return p2p::allreduce_small(m, static_cast<double*>(buf), n, st);
   // the flat gradient: pulled, summed in rank order and pushed back over peer memory (one kernel)
-  if (dt == ncclFloat && buf == m->grad && p2p::grad_ready(m)) return p2p::allreduce_grad(m, n, st);
+  if (dt == ncclFloat && buf == m->grad && p2p::grad_ready(m)) {
+    // the step's outputs ride along: after this kernel every rank holds the global batch's outputs
+    const bool gy = m->dp_y != nullptr && m->dp_Bg * m->out_size <= p2p::YMAX;
+    return p2p::allreduce_grad(m, n, gy ? m->dp_y : nullptr, m->dp_rows, m->dp_row0, m->out_size, st);
+  }
   P3D_NCCL(nccl()->AllReduce(buf, buf, n, dt, ncclSum, static_cast<ncclComm_t>(m->nccl_comm), st));
   return P3D_OK;
 }
@@ -720,6 +724,7 @@ static int train_body(p3d_model* m, const float* x, const float* t, int64_t B, b
   float* scale = w.scal;   // [nlay] clip scales
   const double invBg = 1.0 / static_cast<double>(Bg);
 
+  m->dp_y = y; m->dp_rows = B; m->dp_row0 = row0; m->dp_Bg = Bg;
   P3D_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(double) * (4ull * nh * L + nlay + 1 + 2ull * nh), st));
   P3D_CUDA(cudaMemsetAsync(m->grad, 0, sizeof(float) * m->n_train, st));
   if (clip) P3D_CUDA(cudaMemsetAsync(m->norm2, 0, sizeof(double) * nlay, st));
@@ -1005,6 +1010,9 @@ int train_step(p3d_model* m, const float* x, const float* t, int64_t B, float ke
   }
   m->global_step += 1;
   m->pack_valid = false;
+  // (set on every call: a replayed graph does not pass through the host code that decides it at capture time)
+  m->dp_Bg = Bg;
+  m->dp_y_gathered = m->world > 1 && p2p::grad_ready(m) && Bg * m->out_size <= p2p::YMAX;
   return mark_model_work(m, st);
 }
 
@@ -1078,10 +1086,22 @@ int p3d_model_train_epoch(p3d_model* m, const float* X, const float* T, int64_t 
                             lr_last_or_null, static_cast<cudaStream_t>(stream));
 }
 
+int p3d_model_gathered_outputs(p3d_model* m, float* y_global, int64_t global_B, void* stream) {
+  P3D_REQUIRE(m && y_global && global_B >= 1, "gathered_outputs: bad argument");
+  if (m->world <= 1 || !m->dp_y_gathered || global_B != m->dp_Bg) return 1;       // not available: the caller gathers
+  const float* src = p2p::gathered_outputs(m);
+  if (!src) return 1;
+  P3D_CUDA(cudaSetDevice(m->cfg.device));
+  P3D_CUDA(cudaMemcpyAsync(y_global, src, sizeof(float) * static_cast<size_t>(global_B) * m->out_size, cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  return P3D_OK;
+}
+
 int p3d_debug_dp_part(p3d_model* m, int what, void* stream) {
   P3D_REQUIRE(m && m->world > 1 && m->tw.stats, "debug_dp_part: needs an attached data-parallel model that has stepped once");
   P3D_CUDA(cudaSetDevice(m->cfg.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  m->dp_y = nullptr;
   if (what == 0) return train::allreduce(m, m->grad, m->n_train, ncclFloat, st);          // the flat gradient exchange
   return train::allreduce(m, m->tw.stats, 2ull * m->L, ncclDouble, st);                   // one SyncBN-sized exchange
 }

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "p3d_model_p2p_attach": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "p3d_model_p2p_detach": (c_int, [c_void_p]),
     "p3d_debug_dp_part": (c_int, [c_void_p, c_int, c_void_p]),
+    "p3d_model_gathered_outputs": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "p3d_model_train_epoch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, C.c_uint64,
                                       c_void_p, c_void_p, c_void_p]),
     "p3d_debug_tc_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,

@@ -382,10 +382,17 @@ class LinearModel(object):
                                            C.c_uint64(self._seed & 0xFFFFFFFFFFFFFFFF), mask_ptr, gB, row0,
                                            scal.data_ptr(), scal.data_ptr() + 4, y.data_ptr(), _lib.current_stream()))
             if self.world > 1:
-                parts = [torch.empty((shard_rows(B, r, self.world)[1] - shard_rows(B, r, self.world)[0],
-                                      self.output_size), dtype=torch.float32, device=dev) for r in range(self.world)]
-                self._dist.all_gather(parts, y)
-                y = torch.cat(parts, 0)
+                # the outputs of the global batch: normally they travelled with the gradient exchange (one D2D copy)
+                yg = torch.empty((B, self.output_size), dtype=torch.float32, device=dev)
+                rc = lib.p3d_model_gathered_outputs(self._handle, yg.data_ptr(), B, _lib.current_stream())
+                if rc == 1:
+                    parts = [torch.empty((shard_rows(B, r, self.world)[1] - shard_rows(B, r, self.world)[0],
+                                          self.output_size), dtype=torch.float32, device=dev) for r in range(self.world)]
+                    self._dist.all_gather(parts, y)
+                    yg = torch.cat(parts, 0)
+                else:
+                    check(rc)
+                y = yg
             if is_torch:
                 self._last_outputs, self._last_loss = y, scal[0]
                 return scal[0], Summary("loss/loss", scal[0]), Summary("learning_rate/learning_rate", scal[1]), y

@@ -128,6 +128,11 @@ int p3d_model_attach_nccl(p3d_model* m, const uint8_t* id_host, int rank, int wo
 int p3d_model_p2p_handle(p3d_model* m, uint8_t* handle128_host);   /* [exchange buffer | flat gradient buffer] */
 int p3d_model_p2p_attach(p3d_model* m, const uint8_t* handles_host, int rank, int world);
 int p3d_model_p2p_detach(p3d_model* m);
+/* Data parallel, after p3d_model_train_step: the outputs of the GLOBAL batch [global_B, out] (device pointer).  When the
+ * gradient travelled over peer memory, every rank's rows were written into every rank's exchange buffer on the way and
+ * this is one device-to-device copy; returns 1 (and copies nothing) when they are not available - NCCL gradient path,
+ * or a global batch beyond the buffer (10922 rows) - and the caller all-gathers the per-rank outputs itself. */
+int p3d_model_gathered_outputs(p3d_model* m, float* y_global, int64_t global_B, void* stream);
 /* Measurement aid (bench.py `secondary.train_dp`): one exchange of a data-parallel step on its own, on `stream`.
  * what = 0: the flat fp32 gradient all-reduce (NCCL); 1: one SyncBN-sized (2 x linear_size doubles) sum over peer memory
  * (NCCL when no peer memory is attached).  The buffers hold whatever the last step left; they are summed in place. */
