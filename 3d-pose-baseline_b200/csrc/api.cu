@@ -285,7 +285,7 @@ void p3d_model_destroy(p3d_model* m) {
   train::free_workspace(m);
   cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
   cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
-  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act);
+  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act); cudaFree(m->lat_act);
   if (m->ev_done) cudaEventDestroy(m->ev_done);
   for (auto& e : m->pipe_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; ++i) {

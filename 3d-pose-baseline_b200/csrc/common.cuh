@@ -314,6 +314,8 @@ struct p3d_model {
   int64_t lay_cap = 0;
   unsigned long long* lat_counter = nullptr;   // grid-barrier counter of the latency kernel (monotonic)
   unsigned long long lat_base = 0;
+  void* lat_act = nullptr;               // batch-1 whole-chip kernel: activation exchange words {value, tag} [16][1024]
+  unsigned lat_tag = 0;                  // ... and its call counter
   float* f32_a = nullptr;                // fp32-path activations [3][cap][L]
   int64_t f32_cap = 0;
   // host-step pipeline

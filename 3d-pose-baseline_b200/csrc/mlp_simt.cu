@@ -605,7 +605,177 @@ static int launch_latency_cluster(p3d_model* m, const float* x, float* y, const 
   return P3D_OK;
 }
 
-int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) { return launch_latency_cluster(m, x, y, nullptr, st); }
+
+// ----------------------------------------------------------------------------- batch-1 whole-chip kernel
+// The 16-CTA cluster kernel above streams 512 KB of weights per SM; it is bound by what ONE SM can ingest (measured:
+// 3.2-4.1 us per hidden layer = ~37 GB/s per SM, 19 us in the kernel, 16 of 148 SMs busy).  Here 128 CTAs (cooperative
+// launch: all resident) own 8 output features of every layer each: a CTA's whole share of the weights is 64 KB and is
+// requested in the first instructions (the chip pulls the 8.56 MB in parallel, ~2 us), so what remains is the layer
+// chain itself.  Activations travel between the layers through a global buffer of self-validating words {fp32 value,
+// call tag}: a producer stores its feature with one 8-byte store, every consumer polls the words it needs until they
+// carry this call's tag - no counter, no fence, no barrier: one L2 write + read per layer (~1 us) instead of the
+// ~3 us round trips of a grid-wide barrier.  The tag is a per-model call counter, so the buffer is never cleared.
+constexpr int GLC = 128;          // CTAs
+constexpr int GLT = 256;          // threads: 8 warps, one output feature per warp and layer
+constexpr int GLF = GLT / 32;     // features per CTA and layer
+struct GridLatArgs {
+  const float* x; float* y; const __nv_bfloat16* wt; const float* bias;
+  uint2* act;                     // [nlayers - 1][1024] {value bits, tag}
+  unsigned tag;
+  int nlayers, out, kpad, residual;
+  unsigned long long* stamps;
+};
+__device__ __forceinline__ void st_ll(uint2* p, float v, unsigned tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll2(const uint2* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+#define GLAT_STAMP(i) do { if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) a.stamps[i] = gtimer(); } while (0)
+
+__global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs a) {
+  constexpr int L = 1024;
+  extern __shared__ __align__(128) uint8_t glat_smem[];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nhid = a.nlayers - 2;
+  uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(glat_smem) + 127) & ~uintptr_t(127));
+  uint8_t* wout = wsm + nhid * (GLF * 2048);                        // this CTA's row of the output layer (c < out)
+  float* sP = reinterpret_cast<float*>(wout + 2048);
+  float* sQ = sP + L;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sQ + L);            // [nhid + 1]
+  GLAT_STAMP(0);
+  if (threadIdx.x == 0) {
+    for (int l = 0; l <= nhid; ++l) lat_mbar_init(&wbar[l], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the CTA's 8 rows of a hidden layer are contiguous in the packed weights: 16 KB per layer, everything requested now
+    for (int l = 0; l < nhid; ++l)
+      bulk_load(wsm + l * (GLF * 2048), a.wt + (static_cast<size_t>(1 + l) * L + c * GLF) * a.kpad, GLF * 2048, &wbar[l], 4);
+    if (c < a.out) bulk_load(wout, a.wt + (static_cast<size_t>(a.nlayers - 1) * L + c) * a.kpad, 2048, &wbar[nhid], 1);
+  }
+  const int n = c * GLF + warp;                                     // this warp's feature of every hidden layer
+  // ---- layer 0 (K = 32): weights and x straight from L2
+  {
+    float acc = 0.f;
+    if (lane < 8) {
+      const uint2 wv = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 4));
+      const float4 h = __ldg(reinterpret_cast<const float4*>(a.x + lane * 4));
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      acc = h.x * __low2float(w2[0]) + h.y * __high2float(w2[0]) + h.z * __low2float(w2[1]) + h.w * __high2float(w2[1]);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) st_ll(a.act + n, fmaxf(acc + __ldg(a.bias + n), 0.f), a.tag);
+  }
+  GLAT_STAMP(1);
+  // all of layer `lp`'s outputs -> dst (shared): every thread polls its own four words until they carry the tag
+  auto gather = [&](int lp, float* dst) {
+    const uint2* src = a.act + static_cast<size_t>(lp) * L + threadIdx.x * 4;
+    uint4 u, v;
+    unsigned spins = 0;
+    for (;;) {
+      u = ld_ll2(src); v = ld_ll2(src + 2);
+      if (u.y == a.tag && u.w == a.tag && v.y == a.tag && v.w == a.tag) break;
+      if (++spins > (1u << 24)) { printf("p3d: batch-1 kernel: layer %d never arrived (block %d)\n", lp, (int)blockIdx.x); __trap(); }
+    }
+    *reinterpret_cast<float4*>(dst + threadIdx.x * 4) = make_float4(__uint_as_float(u.x), __uint_as_float(u.z), __uint_as_float(v.x), __uint_as_float(v.z));
+  };
+  // ---- hidden layers: layer 0 and the even layers leave their outputs in P, the odd ones in Q (the residual of an even
+  // layer is the block input, still in P when the layer computes)
+  for (int l = 1; l <= nhid; ++l) {
+    float* src = (l & 1) ? sP : sQ;
+    const bool add_res = a.residual && l >= 2 && !(l & 1);
+    const float bias = __ldg(a.bias + l * L + n);
+    gather(l - 1, src);
+    __syncthreads();
+    float4 hreg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hreg[i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+    lat_mbar_wait(&wbar[l - 1], 0);
+    const uint2* wrow = reinterpret_cast<const uint2*>(wsm + (l - 1) * (GLF * 2048) + warp * 2048);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint2 wv = wrow[i * 32 + lane];                         // k = i*128 + lane*4 .. +3 : conflict-free
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+      acc0 = fmaf(hreg[i].x, __low2float(w2[0]), acc0); acc1 = fmaf(hreg[i].y, __high2float(w2[0]), acc1);
+      acc0 = fmaf(hreg[i].z, __low2float(w2[1]), acc0); acc1 = fmaf(hreg[i].w, __high2float(w2[1]), acc1);
+    }
+    float acc = acc0 + acc1;
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      float v = fmaxf(acc + bias, 0.f);
+      if (add_res) v += sP[n];
+      st_ll(a.act + static_cast<size_t>(l) * L + n, v, a.tag);
+    }
+    __syncthreads();                                               // the next gather overwrites what this layer still reads
+    GLAT_STAMP(1 + l);
+  }
+  // ---- output layer: CTA c < out computes feature c from its row in shared memory
+  if (c < a.out) {
+    const int l = a.nlayers - 1;
+    float* src = (l & 1) ? sP : sQ;
+    gather(l - 1, src);
+    __syncthreads();
+    if (warp == 0) {
+      lat_mbar_wait(&wbar[nhid], 0);
+      const uint2* wrow = reinterpret_cast<const uint2*>(wout);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint2 wv = wrow[i * 32 + lane];
+        const float4 hv = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+        acc = fmaf(hv.x, __low2float(w2[0]), acc); acc = fmaf(hv.y, __high2float(w2[0]), acc);
+        acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
+      }
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) a.y[c] = acc + __ldg(a.bias + l * L + c);
+    }
+  }
+  GLAT_STAMP(a.nlayers);
+}
+
+// returns 1 when the kernel cannot serve this model / device (the caller takes the cluster kernel)
+static int launch_latency_grid(p3d_model* m, const float* x, float* y, cudaStream_t st) {
+  static const bool on = [] { const char* e = getenv("P3D_LAT_GRIDLL"); return !(e && e[0] == '0'); }();
+  const int nlayers = static_cast<int>(m->layers.size()), nhid = nlayers - 2;
+  if (!on || m->L != 1024 || nhid < 1 || nhid > 10 || m->out_size > GLC || m->num_sms < GLC || m->kpad != 1024) return 1;
+  const int smem = 128 + nhid * (GLF * 2048) + 2048 + 2 * 1024 * 4 + 8 * (nhid + 1) + 64;
+  static PerDeviceOnce attr;
+  if (attr.needed()) {
+    P3D_CUDA(cudaFuncSetAttribute(latency_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + 10 * (GLF * 2048) + 2048 + 8192 + 256));
+    attr.mark();
+  }
+  if (!m->lat_act) {
+    P3D_CUDA(cudaMalloc(&m->lat_act, sizeof(uint2) * 1024 * 16));
+    P3D_CUDA(cudaMemset(m->lat_act, 0, sizeof(uint2) * 1024 * 16));
+  }
+  if (!m->lat_counter) {
+    P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long) * 32));
+    P3D_CUDA(cudaMemset(m->lat_counter, 0, sizeof(unsigned long long) * 32));
+  }
+  if (++m->lat_tag == 0) ++m->lat_tag;                 // 0 is what a fresh buffer holds
+  GridLatArgs a;
+  a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.act = static_cast<uint2*>(m->lat_act); a.tag = m->lat_tag;
+  a.nlayers = nlayers; a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
+  a.stamps = getenv("P3D_LAT_STAMPS") ? m->lat_counter + 8 : nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(GLC); cfg.blockDim = dim3(GLT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // every CTA polls what the others produce
+  cfg.attrs = at; cfg.numAttrs = 1;
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, latency_grid_kernel, a));
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) {
+  const int rc = launch_latency_grid(m, x, y, st);          // the whole chip; 1 = not applicable here
+  if (rc != 1) return rc;
+  return launch_latency_cluster(m, x, y, nullptr, st);
+}
 // the same launch running the whole realtime step (keypoints -> normalised input -> lifter -> un-normalised pose)
 int forward_latency_cluster_rt(p3d_model* m, const rt::Fused& f, float* y, cudaStream_t st) {
   if (m->L != 1024 || m->cfg.mode != P3D_MODE_BF16) return 1;

@@ -166,10 +166,16 @@ __global__ void __launch_bounds__(256) grad_allreduce_kernel(const Peers peers, 
       }
     }
   }
-  // this rank's rows of the step outputs -> every rank's ybuf (CTA b serves peer b; the exit handshake below publishes them)
-  if (y_local != nullptr && blockIdx.x < static_cast<unsigned>(world)) {
-    float* dst = peers.p[blockIdx.x]->ybuf + y_off;
-    for (long long i = threadIdx.x; i < y_count; i += blockDim.x) dst[i] = y_local[i];
+  // this rank's rows of the step outputs -> every rank's ybuf, spread over the whole grid as 8-byte stores (rows x 48 or 42
+  // floats: always an even count at an even offset); the exit handshake below publishes them
+  if (y_local != nullptr) {
+    const long long c2 = y_count >> 1;
+    const long long total = c2 * world;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int r = static_cast<int>(idx / c2);
+      const long long i = idx - r * c2;
+      reinterpret_cast<float2*>(peers.p[r]->ybuf + y_off)[i] = reinterpret_cast<const float2*>(y_local)[i];
+    }
   }
   if (rank == 0 && blockIdx.x == 0) {                   // a length that is not a multiple of 4: the tail, element by element
     for (long long i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
