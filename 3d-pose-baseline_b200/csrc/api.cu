@@ -27,6 +27,7 @@ namespace tc { int forward_bf16(p3d_model*, const __nv_bfloat16*, float*, int64_
 namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_small(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t);
+                 int forward_latency_grid(p3d_model*, const float*, float*, int, cudaStream_t);
                  int forward_latency_cluster(p3d_model*, const float*, float*, cudaStream_t); }
 namespace tcg { int mma_rate(int, int, long long*, cudaStream_t); }
 namespace layered { int forward(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t); }
@@ -383,9 +384,13 @@ static int forward_on(p3d_model* m, const float* x, float* y, int64_t B, cudaStr
   if (!m->pack_valid) P3D_TRY(prep::prepare(m, st));
   if (m->cfg.mode == P3D_MODE_FP32) return simt::forward_fp32(m, x, y, B, st);
   const int L = m->L;
-  if (B == 1 && L == 1024) {                            // single pose: 16-CTA cluster kernel, one launch
+  if (B == 1 && L == 1024) {                            // single pose: whole-chip kernel (or the 16-CTA cluster kernel), one launch
     const int rc = simt::forward_latency_cluster(m, x, y, st);
-    if (rc <= 0) return rc;                              // 1 = cluster of 16 not schedulable here -> fall through
+    if (rc <= 0) return rc;                              // 1 = not schedulable here -> fall through
+  }
+  if (B >= 2 && B <= 8 && L == 1024) {                  // a handful of poses: the same whole-chip kernel, fp32 activations
+    const int rc = simt::forward_latency_grid(m, x, y, static_cast<int>(B), st);
+    if (rc <= 0) return rc;
   }
   if ((L % 8) != 0) {                                    // widths no tensor-core tiling covers
     if (B <= kSmallBatchMax) return simt::forward_small(m, x, y, B, st);

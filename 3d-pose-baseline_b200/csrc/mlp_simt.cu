@@ -620,9 +620,9 @@ constexpr int GLT = 256;          // threads: 8 warps, one output feature per wa
 constexpr int GLF = GLT / 32;     // features per CTA and layer
 struct GridLatArgs {
   const float* x; float* y; const __nv_bfloat16* wt; const float* bias;
-  uint2* act;                     // [nlayers - 1][1024] {value bits, tag}
+  uint2* act;                     // [nlayers - 1][8 poses][1024] {value bits, tag}
   unsigned tag;
-  int nlayers, out, kpad, residual;
+  int nlayers, out, kpad, residual, rows, backoff_ns;
   unsigned long long* stamps;
 };
 __device__ __forceinline__ void st_ll(uint2* p, float v, unsigned tag) {
@@ -635,6 +635,7 @@ __device__ __forceinline__ uint4 ld_ll2(const uint2* p) {
 }
 #define GLAT_STAMP(i) do { if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) a.stamps[i] = gtimer(); } while (0)
 
+template <int ROWS>      // poses served by one launch (1, 2, 4 or 8; a.rows <= ROWS of them are live)
 __global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs a) {
   constexpr int L = 1024;
   extern __shared__ __align__(128) uint8_t glat_smem[];
@@ -642,9 +643,9 @@ __global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs 
   const int nhid = a.nlayers - 2;
   uint8_t* wsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(glat_smem) + 127) & ~uintptr_t(127));
   uint8_t* wout = wsm + nhid * (GLF * 2048);                        // this CTA's row of the output layer (c < out)
-  float* sP = reinterpret_cast<float*>(wout + 2048);
-  float* sQ = sP + L;
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(sQ + L);            // [nhid + 1]
+  float* sP = reinterpret_cast<float*>(wout + 2048);                // [ROWS][L]
+  float* sQ = sP + ROWS * L;
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sQ + ROWS * L);     // [nhid + 1]
   GLAT_STAMP(0);
   if (threadIdx.x == 0) {
     for (int l = 0; l <= nhid; ++l) lat_mbar_init(&wbar[l], 1);
@@ -656,30 +657,68 @@ __global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs 
     if (c < a.out) bulk_load(wout, a.wt + (static_cast<size_t>(a.nlayers - 1) * L + c) * a.kpad, 2048, &wbar[nhid], 1);
   }
   const int n = c * GLF + warp;                                     // this warp's feature of every hidden layer
+  // Layer l's outputs of pose r live in ONE shared copy that every CTA polls (pull).  Measured alternatives: a private inbox
+  // per consumer CTA that the producers write to (push: 128 scattered 8-byte stores per feature) was slower (23 us per
+  // call against 13-18); so were 8-byte stores from eight different warps into the shared copy - partial-sector writes into
+  // lines that 512 threads are polling.  A CTA therefore collects its eight features in shared memory and publishes them
+  // as ONE 64-byte row of four 16-byte stores (two whole sectors).
+  auto word = [&](int l, int r) { return a.act + (static_cast<size_t>(l) * 8 + r) * L; };
+  __shared__ float spub[ROWS][GLF];
+  auto publish_cta = [&](int l) {                                 // after a block barrier: spub holds the CTA's features
+    if (threadIdx.x < 4 * ROWS) {
+      const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+      if (r < a.rows) {
+        uint2* dst = word(l, r) + c * GLF + 2 * q;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__float_as_uint(spub[r][2 * q])), "r"(a.tag),
+                     "r"(__float_as_uint(spub[r][2 * q + 1])), "r"(a.tag) : "memory");
+      }
+    }
+  };
   // ---- layer 0 (K = 32): weights and x straight from L2
   {
-    float acc = 0.f;
-    if (lane < 8) {
-      const uint2 wv = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 4));
-      const float4 h = __ldg(reinterpret_cast<const float4*>(a.x + lane * 4));
-      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
-      acc = h.x * __low2float(w2[0]) + h.y * __high2float(w2[0]) + h.z * __low2float(w2[1]) + h.w * __high2float(w2[1]);
+    uint2 wv = make_uint2(0, 0);
+    if (lane < 8) wv = __ldg(reinterpret_cast<const uint2*>(a.wt + static_cast<size_t>(n) * a.kpad + lane * 4));
+    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+    const float b = __ldg(a.bias + n);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float acc = 0.f;
+      if (lane < 8 && r < a.rows) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(a.x + r * kIn + lane * 4));
+        acc = h.x * __low2float(w2[0]) + h.y * __high2float(w2[0]) + h.z * __low2float(w2[1]) + h.w * __high2float(w2[1]);
+      }
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) spub[r][warp] = fmaxf(acc + b, 0.f);
     }
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) st_ll(a.act + n, fmaxf(acc + __ldg(a.bias + n), 0.f), a.tag);
+    __syncthreads();
+    publish_cta(0);
   }
   GLAT_STAMP(1);
-  // all of layer `lp`'s outputs -> dst (shared): every thread polls its own four words until they carry the tag
+  // all of layer `lp`'s outputs -> dst (shared): every thread polls its own four words per pose until they carry the tag
   auto gather = [&](int lp, float* dst) {
-    const uint2* src = a.act + static_cast<size_t>(lp) * L + threadIdx.x * 4;
-    uint4 u, v;
+    // the words of ALL poses are requested together and the batch is re-polled until every word carries the tag: one L2
+    // round trip per poll (pose after pose, eight poses cost eight round trips per layer: 5.7 us)
+    uint4 u[ROWS], v[ROWS];
     unsigned spins = 0;
     for (;;) {
-      u = ld_ll2(src); v = ld_ll2(src + 2);
-      if (u.y == a.tag && u.w == a.tag && v.y == a.tag && v.w == a.tag) break;
+      bool ok = true;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const uint2* src = word(lp, r < a.rows ? r : 0) + threadIdx.x * 4;
+        u[r] = ld_ll2(src); v[r] = ld_ll2(src + 2);
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) ok = ok && u[r].y == a.tag && u[r].w == a.tag && v[r].y == a.tag && v[r].w == a.tag;
+      if (ok) break;
       if (++spins > (1u << 24)) { printf("p3d: batch-1 kernel: layer %d never arrived (block %d)\n", lp, (int)blockIdx.x); __trap(); }
+      // back off between polls: 32 K threads re-reading the same 8 KB as fast as they can keep the L2 slices that hold it
+      // busy, and the producers' stores queue up behind the reads (per-layer times of 2-4.5 us instead of 1.5)
+      if (a.backoff_ns > 0) __nanosleep(static_cast<unsigned>(a.backoff_ns));
     }
-    *reinterpret_cast<float4*>(dst + threadIdx.x * 4) = make_float4(__uint_as_float(u.x), __uint_as_float(u.z), __uint_as_float(v.x), __uint_as_float(v.z));
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+      *reinterpret_cast<float4*>(dst + r * L + threadIdx.x * 4) =
+          make_float4(__uint_as_float(u[r].x), __uint_as_float(u[r].z), __uint_as_float(v[r].x), __uint_as_float(v[r].z));
   };
   // ---- hidden layers: layer 0 and the even layers leave their outputs in P, the odd ones in Q (the residual of an even
   // layer is the block input, still in P when the layer computes)
@@ -689,27 +728,35 @@ __global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs 
     const float bias = __ldg(a.bias + l * L + n);
     gather(l - 1, src);
     __syncthreads();
-    float4 hreg[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) hreg[i] = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
     lat_mbar_wait(&wbar[l - 1], 0);
     const uint2* wrow = reinterpret_cast<const uint2*>(wsm + (l - 1) * (GLF * 2048) + warp * 2048);
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc0[ROWS], acc1[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint2 wv = wrow[i * 32 + lane];                         // k = i*128 + lane*4 .. +3 : conflict-free
       const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
-      acc0 = fmaf(hreg[i].x, __low2float(w2[0]), acc0); acc1 = fmaf(hreg[i].y, __high2float(w2[0]), acc1);
-      acc0 = fmaf(hreg[i].z, __low2float(w2[1]), acc0); acc1 = fmaf(hreg[i].w, __high2float(w2[1]), acc1);
+      const float w0 = __low2float(w2[0]), w1 = __high2float(w2[0]), w2f = __low2float(w2[1]), w3 = __high2float(w2[1]);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float4 h = *reinterpret_cast<const float4*>(src + r * L + i * 128 + lane * 4);
+        acc0[r] = fmaf(h.x, w0, acc0[r]); acc1[r] = fmaf(h.y, w1, acc1[r]);
+        acc0[r] = fmaf(h.z, w2f, acc0[r]); acc1[r] = fmaf(h.w, w3, acc1[r]);
+      }
     }
-    float acc = acc0 + acc1;
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
-      float v = fmaxf(acc + bias, 0.f);
-      if (add_res) v += sP[n];
-      st_ll(a.act + static_cast<size_t>(l) * L + n, v, a.tag);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float acc = acc0[r] + acc1[r];
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) {
+        float v = fmaxf(acc + bias, 0.f);
+        if (add_res) v += sP[r * L + n];
+        spub[r][warp] = v;
+      }
     }
     __syncthreads();                                               // the next gather overwrites what this layer still reads
+    publish_cta(l);
     GLAT_STAMP(1 + l);
   }
   // ---- output layer: CTA c < out computes feature c from its row in shared memory
@@ -718,39 +765,47 @@ __global__ void __launch_bounds__(GLT, 1) latency_grid_kernel(const GridLatArgs 
     float* src = (l & 1) ? sP : sQ;
     gather(l - 1, src);
     __syncthreads();
-    if (warp == 0) {
+    if (warp < ROWS && warp < a.rows) {                            // one pose per warp
       lat_mbar_wait(&wbar[nhid], 0);
       const uint2* wrow = reinterpret_cast<const uint2*>(wout);
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint2 wv = wrow[i * 32 + lane];
-        const float4 hv = *reinterpret_cast<const float4*>(src + i * 128 + lane * 4);
+        const float4 hv = *reinterpret_cast<const float4*>(src + warp * L + i * 128 + lane * 4);
         const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
         acc = fmaf(hv.x, __low2float(w2[0]), acc); acc = fmaf(hv.y, __high2float(w2[0]), acc);
         acc = fmaf(hv.z, __low2float(w2[1]), acc); acc = fmaf(hv.w, __high2float(w2[1]), acc);
       }
       for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-      if (lane == 0) a.y[c] = acc + __ldg(a.bias + l * L + c);
+      if (lane == 0) a.y[warp * a.out + c] = acc + __ldg(a.bias + l * L + c);
     }
   }
   GLAT_STAMP(a.nlayers);
 }
 
-// returns 1 when the kernel cannot serve this model / device (the caller takes the cluster kernel)
-static int launch_latency_grid(p3d_model* m, const float* x, float* y, cudaStream_t st) {
+// returns 1 when the kernel cannot serve this model / device (the caller takes another path)
+static int launch_latency_grid(p3d_model* m, const float* x, float* y, int rows, cudaStream_t st) {
   static const bool on = [] { const char* e = getenv("P3D_LAT_GRIDLL"); return !(e && e[0] == '0'); }();
   const int nlayers = static_cast<int>(m->layers.size()), nhid = nlayers - 2;
-  if (!on || m->L != 1024 || nhid < 1 || nhid > 10 || m->out_size > GLC || m->num_sms < GLC || m->kpad != 1024) return 1;
-  const int smem = 128 + nhid * (GLF * 2048) + 2048 + 2 * 1024 * 4 + 8 * (nhid + 1) + 64;
+  if (!on || m->L != 1024 || nhid < 1 || nhid > 6 || m->out_size > GLC || m->num_sms < GLC || m->kpad != 1024 || rows < 1 || rows > 8) return 1;
+  static const int rmin = [] { const char* e = getenv("P3D_LAT_RMIN"); return e ? atoi(e) : 1; }();      // diagnostics
+  int R = rows == 1 ? 1 : (rows == 2 ? 2 : (rows <= 4 ? 4 : 8));
+  if (R < rmin) R = rmin;
+  const int smem = 128 + nhid * (GLF * 2048) + 2048 + 2 * R * 1024 * 4 + 8 * (nhid + 1) + 64;
+  using K = void (*)(const GridLatArgs);
+  const K fn = R == 1 ? latency_grid_kernel<1> : (R == 2 ? latency_grid_kernel<2> : (R == 4 ? latency_grid_kernel<4> : latency_grid_kernel<8>));
   static PerDeviceOnce attr;
   if (attr.needed()) {
-    P3D_CUDA(cudaFuncSetAttribute(latency_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 + 10 * (GLF * 2048) + 2048 + 8192 + 256));
+    const int cap = 128 + 6 * (GLF * 2048) + 2048 + 2 * 8 * 1024 * 4 + 256;
+    for (K k : {static_cast<K>(latency_grid_kernel<1>), static_cast<K>(latency_grid_kernel<2>), static_cast<K>(latency_grid_kernel<4>), static_cast<K>(latency_grid_kernel<8>)})
+      P3D_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     attr.mark();
   }
   if (!m->lat_act) {
-    P3D_CUDA(cudaMalloc(&m->lat_act, sizeof(uint2) * 1024 * 16));
-    P3D_CUDA(cudaMemset(m->lat_act, 0, sizeof(uint2) * 1024 * 16));
+    // one pose: [128 consumer CTAs][layers <= 8][1024] (8 MB); more poses: [layers <= 8][poses 8][1024] in the same buffer
+    P3D_CUDA(cudaMalloc(&m->lat_act, sizeof(uint2) * 1024 * 8 * GLC));
+    P3D_CUDA(cudaMemset(m->lat_act, 0, sizeof(uint2) * 1024 * 8 * GLC));
   }
   if (!m->lat_counter) {
     P3D_CUDA(cudaMalloc(&m->lat_counter, sizeof(unsigned long long) * 32));
@@ -759,20 +814,24 @@ static int launch_latency_grid(p3d_model* m, const float* x, float* y, cudaStrea
   if (++m->lat_tag == 0) ++m->lat_tag;                 // 0 is what a fresh buffer holds
   GridLatArgs a;
   a.x = x; a.y = y; a.wt = m->wt_bf16; a.bias = m->bias_fold; a.act = static_cast<uint2*>(m->lat_act); a.tag = m->lat_tag;
-  a.nlayers = nlayers; a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual;
+  a.nlayers = nlayers; a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual; a.rows = rows;
+  static const int backoff = [] { const char* e = getenv("P3D_LAT_BACKOFF_NS"); return e ? atoi(e) : 0; }();
+  a.backoff_ns = backoff;
   a.stamps = getenv("P3D_LAT_STAMPS") ? m->lat_counter + 8 : nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(GLC); cfg.blockDim = dim3(GLT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // every CTA polls what the others produce
   cfg.attrs = at; cfg.numAttrs = 1;
-  P3D_CUDA(cudaLaunchKernelEx(&cfg, latency_grid_kernel, a));
+  P3D_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
+// 2 .. 8 poses through the same kernel (fp32 activations, bf16 weights; 1 = not applicable here)
+int forward_latency_grid(p3d_model* m, const float* x, float* y, int rows, cudaStream_t st) { return launch_latency_grid(m, x, y, rows, st); }
 
 int forward_latency_cluster(p3d_model* m, const float* x, float* y, cudaStream_t st) {
-  const int rc = launch_latency_grid(m, x, y, st);          // the whole chip; 1 = not applicable here
+  const int rc = launch_latency_grid(m, x, y, 1, st);       // the whole chip; 1 = not applicable here
   if (rc != 1) return rc;
   return launch_latency_cluster(m, x, y, nullptr, st);
 }
