@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "p3d", "libp3d.so")
-SOURCES = ["api.cu", "mlp_prep.cu", "mlp_tc.cu", "tc_gemm.cu", "mlp_layered.cu", "mlp_simt.cu", "geometry.cu", "procrustes.cu", "train.cu", "p2p.cu", "realtime.cu"]
+SOURCES = ["api.cu", "mlp_prep.cu", "mlp_tc.cu", "tc_gemm.cu", "mlp_layered.cu", "mlp_simt.cu", "mlp_mid.cu", "geometry.cu", "procrustes.cu", "train.cu", "p2p.cu", "realtime.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -29,6 +29,7 @@ namespace simt { int forward_fp32(p3d_model*, const float*, float*, int64_t, cud
                  int forward_latency(p3d_model*, const float*, float*, int64_t, cudaStream_t);
                  int forward_latency_grid(p3d_model*, const float*, float*, int, cudaStream_t);
                  int forward_latency_cluster(p3d_model*, const float*, float*, cudaStream_t); }
+namespace mid { int forward(p3d_model*, const float*, float*, int, cudaStream_t); }
 namespace tcg { int mma_rate(int, int, long long*, cudaStream_t); }
 namespace layered { int forward(p3d_model*, const __nv_bfloat16*, float*, int64_t, cudaStream_t); }
 namespace train { void free_workspace(p3d_model*); }
@@ -286,7 +287,7 @@ void p3d_model_destroy(p3d_model* m) {
   train::free_workspace(m);
   cudaFree(m->theta); cudaFree(m->grad); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->moving);
   cudaFree(m->wt_bf16); cudaFree(m->bias_fold); cudaFree(m->wfold); cudaFree(m->norm2); cudaFree(m->pipe_loss);
-  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act); cudaFree(m->lat_act);
+  cudaFree(m->act_scratch); cudaFree(m->xb); cudaFree(m->f32_a); cudaFree(m->lat_counter); cudaFree(m->lay_act); cudaFree(m->lat_act); cudaFree(m->mid_act);
   if (m->ev_done) cudaEventDestroy(m->ev_done);
   for (auto& e : m->pipe_ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 3; ++i) {
@@ -390,6 +391,10 @@ static int forward_on(p3d_model* m, const float* x, float* y, int64_t B, cudaStr
   }
   if (B >= 2 && B <= 8 && L == 1024) {                  // a handful of poses: the same whole-chip kernel, fp32 activations
     const int rc = simt::forward_latency_grid(m, x, y, static_cast<int>(B), st);
+    if (rc <= 0) return rc;
+  }
+  if (B >= 9 && B <= 64 && L == 1024) {                 // the reference's batch size: one whole-chip launch, mma.sync tiles, bf16 activations
+    const int rc = mid::forward(m, x, y, static_cast<int>(B), st);
     if (rc <= 0) return rc;
   }
   if ((L % 8) != 0) {                                    // widths no tensor-core tiling covers

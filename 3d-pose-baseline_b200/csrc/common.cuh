@@ -316,6 +316,7 @@ struct p3d_model {
   unsigned long long lat_base = 0;
   void* lat_act = nullptr;               // batch-1 whole-chip kernel: activation exchange words {value, tag} [16][1024]
   unsigned lat_tag = 0;                  // ... and its call counter
+  void* mid_act = nullptr;               // 9 .. 64 poses whole-chip kernel (mlp_mid.cu): exchange words {bf16 pair, tag} [8][64][512]
   float* f32_a = nullptr;                // fp32-path activations [3][cap][L]
   int64_t f32_cap = 0;
   // host-step pipeline

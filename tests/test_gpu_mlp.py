@@ -86,10 +86,11 @@ def test_bf16_forward_matches_oracle(cfg, B):
     m.close()
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 7, 8, 9, 16, 17, 64, 127, 129, 4097, 6143, 6144, 6145, 7000])
+@pytest.mark.parametrize("B", [1, 2, 3, 7, 8, 9, 10, 16, 17, 31, 32, 33, 48, 63, 64, 65, 127, 129, 4097, 6143, 6144, 6145, 7000])
 def test_bf16_forward_ragged_batches(B):
     """Any B is accepted (placeholders [None,32], linear_model.py:96-97): the whole-chip latency kernel (B <= 8,
-    fp32 activations), the layered per-layer GEMM path (9 <= B < 6144: partial tiles, tile+1 row) and the fused
+    fp32 activations), the whole-chip mma.sync kernel (9 <= B <= 64 when enabled: one or two row groups of 16 / 32
+    poses, ragged last group), the layered per-layer GEMM path (up to 6143: partial tiles, tile+1 row) and the fused
     persistent kernel (B >= 6144), either side of the crossovers."""
     cfg = M.Config(1024, 2, True, True, True)
     m, p = make_model(cfg, seed=3, bn="trained", mode="bf16")
@@ -100,6 +101,30 @@ def test_bf16_forward_ragged_batches(B):
     rms = np.sqrt(np.mean(ref ** 2))
     assert_matches_emulation(y, emu, rms, ref)
     assert rowwise_rel(y, ref).max() <= 1e-2
+    m.close()
+
+
+@pytest.mark.parametrize("cfg", [M.Config(1024, 1, True, False, False), M.Config(1024, 2, False, True, True),
+                                 M.Config(1024, 2, True, True, False, out_size=42)],
+                         ids=["L1024n1-nobn", "L1024n2-nores", "L1024n2-predict14"])
+@pytest.mark.parametrize("B", [9, 40, 64])
+def test_mid_batch_configs(cfg, B):
+    """The 9 .. 64 pose range (the reference's batch_size flag is 64) on the other graphs a 1024-wide model can have:
+    one residual block (2 hidden layers), no residual, 14-joint output (42 columns: a ragged last output group)."""
+    m, p = make_model(cfg, seed=5, bn="trained", mode="bf16", predict_14=(cfg.out_size == 42))
+    x, _ = synth.mlp_inputs(B, seed=7 + B)
+    t = np.zeros((B, cfg.out_size), np.float32)
+    _, _, y = m.step(None, x, t, 1.0, isTraining=False)
+    ref = M.forward(p, x.astype(np.float64), cfg, training=False)
+    emu = emulate_bf16_forward(p, x, cfg)
+    assert y.shape == (B, cfg.out_size) and np.isfinite(y).all()
+    assert_matches_emulation(y, emu, np.sqrt(np.mean(ref ** 2)), ref)
+    assert rowwise_rel(y, ref).max() <= 1e-2
+    # the same rows inside a larger batch go through another path (per-layer GEMMs): same rounding points
+    xb, _ = synth.mlp_inputs(200, seed=99)
+    xb[:B] = x
+    _, _, yb = m.step(None, xb, np.zeros((200, cfg.out_size), np.float32), 1.0, isTraining=False)
+    assert_matches_emulation(y, yb[:B].astype(np.float64), np.sqrt(np.mean(ref ** 2)))
     m.close()
 
 
