@@ -37,7 +37,6 @@ struct Args {
   unsigned tag;
   int nlayers, out, kpad, residual, rows;
   int sentinel;                           // poll one pose until it arrives before requesting the batch (diagnostics switch)
-  int batch;                              // poses per request after the sentinel: 16, or 32 (33 .. 64 poses: both halves at once)
   unsigned long long* stamps;             // optional [16] %globaltimer stamps of CTA 0 (P3D_LAT_STAMPS=1, tools/bench_latency.py)
 };
 #define MID_STAMP(i) do { if (a.stamps && threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.stamps[i] = t_; } } while (0)
@@ -167,7 +166,9 @@ __global__ void __launch_bounds__(MGT, 1) mid_grid_kernel(const Args a) {
     // sentinel - its two words of the group's first pose - and only when they carry the tag requests a batch of 16 poses:
     // the words of the other poses come from the same four producer CTAs and were stored by the same instruction, a few
     // warps apart, so the batch is almost always complete at the first try (it is re-polled until it is).  Poses that do
-    // not exist are not loaded at all.
+    // not exist are not loaded at all.  Measured alternatives (profiles/r2_mid_batch_latency.txt, 32 / 64 poses): no
+    // sentinel 20.4 / 26.7 us; unconditional loads (absent poses re-reading live ones) 21.9 / 32.8 us, with the sentinel
+    // 22.0 / 36.5 us; every CTA walking the poses from its own starting row 20.5 / 30.8 us; this form 18.4 / 26.6 us.
     const unsigned long long* src = words(lp, row0) + tid * 2;
     unsigned spins = 0;
     if (a.sentinel) {
@@ -177,25 +178,6 @@ __global__ void __launch_bounds__(MGT, 1) mid_grid_kernel(const Args a) {
         if (static_cast<uint32_t>(s0 >> 32) == a.tag && static_cast<uint32_t>(s1 >> 32) == a.tag) break;
         if (++spins > (1u << 24)) { printf("p3d: mid-batch kernel: layer %d never arrived (block %d)\n", lp, (int)blockIdx.x); __trap(); }
       }
-    }
-    if (MT == 2 && a.batch == 32) {                              // both halves of a 32-pose group in one request
-      unsigned long long w0[RG], w1[RG];
-      for (;;) {
-        bool ok = true;
-#pragma unroll
-        for (int r = 0; r < RG; ++r)
-          if (r < live) ld_words(src + static_cast<size_t>(r) * 512, w0[r], w1[r]);
-#pragma unroll
-        for (int r = 0; r < RG; ++r)
-          if (r < live) ok = ok && static_cast<uint32_t>(w0[r] >> 32) == a.tag && static_cast<uint32_t>(w1[r] >> 32) == a.tag;
-        if (ok) break;
-        if (++spins > (1u << 24)) { printf("p3d: mid-batch kernel: layer %d never arrived (block %d)\n", lp, (int)blockIdx.x); __trap(); }
-      }
-#pragma unroll
-      for (int r = 0; r < RG; ++r)
-        if (r < live)
-          *reinterpret_cast<uint2*>(sact + r * PITCH + tid * 8) = make_uint2(static_cast<uint32_t>(w0[r]), static_cast<uint32_t>(w1[r]));
-      return;
     }
 #pragma unroll
     for (int b = 0; b < MT; ++b) {
@@ -346,8 +328,6 @@ int forward(p3d_model* m, const float* x, float* y, int rows, cudaStream_t st) {
   a.nlayers = nlayers; a.out = m->out_size; a.kpad = m->kpad; a.residual = m->cfg.residual; a.rows = rows;
   static const int sentinel = [] { const char* e = getenv("P3D_MID_SENTINEL"); return e ? atoi(e) : 1; }();
   a.sentinel = sentinel;
-  static const int batch = [] { const char* e = getenv("P3D_MID_BATCH"); return e ? atoi(e) : 16; }();
-  a.batch = batch;
   a.stamps = nullptr;
   if (getenv("P3D_LAT_STAMPS")) {
     if (!m->lat_counter) {
