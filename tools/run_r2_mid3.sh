@@ -1,3 +1,4 @@
+# (historical) A/B of gather variants of mlp_mid.cu; the switches used here (P3D_MID_BATCH / _ROTATE / _UNCOND) were removed once measured - results: profiles/r2_mid_batch_latency.txt
 # Round 2: mlp_mid.cu - warm GPU first, then A/B of the poll batch (16 / 32 poses) with in-kernel stamps; launch durations from ncu last.
 mkdir -p gpurun_out
 O=gpurun_out/r2mid3

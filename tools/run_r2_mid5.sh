@@ -1,3 +1,4 @@
+# (historical) A/B of gather variants of mlp_mid.cu; the switches used here (P3D_MID_BATCH / _ROTATE / _UNCOND) were removed once measured - results: profiles/r2_mid_batch_latency.txt
 mkdir -p gpurun_out
 O=gpurun_out/r2mid5
 timeout 60 python tools/forward_once.py 1048576 40 > /dev/null 2>&1
