@@ -162,7 +162,7 @@ def run_reference(args):
     rate0, _ = cpu_port_rate(16384, threads)
     # size the per-step sample so that the whole run stays within ~4 minutes: at the ~170 K poses/s of a 16-core host
     # that is the full 2^20-pose batch of our arm's config (same_config), fewer poses on a smaller host
-    budget = 240.0 / max(1, args.steps + args.warmup)
+    budget = float(os.environ.get("P3D_BENCH_REF_BUDGET_S", "240")) / max(1, args.steps + args.warmup)
     sample = int(min(B_PER_GPU, max(4096, (rate0 * budget) // 4096 * 4096)))
     from oracle import mlp_ref as M
     from oracle import synth
