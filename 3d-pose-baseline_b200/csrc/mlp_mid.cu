@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(MGT, 1) mid_grid_kernel(const Args a) {
     // Polling all poses at once keeps the L2 busy with reads while the producers try to write (128 CTAs x 64 KB per poll
     // round; polling 32 poses at a time, a 64-pose call took 39 us instead of 25).  So every thread first polls ONE
     // sentinel - its two words of the group's first pose - and only when they carry the tag requests a batch of 16 poses:
-    // the words of the other poses come from the same four producer CTAs and were stored by the same instruction, a few
+    // the words of the other poses come from the same producer CTA and were stored by the same instruction, a few
     // warps apart, so the batch is almost always complete at the first try (it is re-polled until it is).  Poses that do
     // not exist are not loaded at all.  Measured alternatives (profiles/r2_mid_batch_latency.txt, 32 / 64 poses): no
     // sentinel 20.4 / 26.7 us; unconditional loads (absent poses re-reading live ones) 21.9 / 32.8 us, with the sentinel
