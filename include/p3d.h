@@ -134,8 +134,8 @@ int p3d_model_p2p_detach(p3d_model* m);
  * or a global batch beyond the buffer (10922 rows) - and the caller all-gathers the per-rank outputs itself. */
 int p3d_model_gathered_outputs(p3d_model* m, float* y_global, int64_t global_B, void* stream);
 /* Measurement aid (bench.py `secondary.train_dp`): one exchange of a data-parallel step on its own, on `stream`.
- * what = 0: the flat fp32 gradient all-reduce (NCCL); 1: one SyncBN-sized (2 x linear_size doubles) sum over peer memory
- * (NCCL when no peer memory is attached).  The buffers hold whatever the last step left; they are summed in place. */
+ * what = 0: the flat fp32 gradient all-reduce; 1: one SyncBN-sized (2 x linear_size doubles) sum - both over peer memory
+ * when it is attached (the step's own path), over NCCL otherwise.  The buffers hold whatever the last step left; they are summed in place. */
 int p3d_debug_dp_part(p3d_model* m, int what, void* stream);
 int64_t p3d_model_global_step(p3d_model* m);
 
